@@ -1,0 +1,112 @@
+"""ctypes binding of ``libjpb200.so`` (the C ABI declared in ``include/jpb200.h``).
+
+The product path has exactly one backend: the sm_100a CUDA library built in-tree by
+``jperceiver_b200.build``.  If it is missing, :func:`lib` raises — there is no CPU or PyTorch
+fallback.  (``use_library`` exists so the test-suite can install the host *emulation* build of the
+same sources, see ``tests/emu``; nothing in the package calls it.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libjpb200.so")
+MAX_SRC = 4
+
+_handle = None
+_emulated = False
+launches = 0  # number of kernel launches issued through this binding (bench.py reads it)
+
+
+class JpbError(RuntimeError):
+    pass
+
+
+class PhotoArgs(C.Structure):
+    _fields_ = [
+        ("target", C.c_void_p), ("src", C.c_void_p * MAX_SRC), ("T", C.c_void_p * MAX_SRC),
+        ("noise", C.c_void_p * MAX_SRC), ("disp", C.c_void_p), ("K", C.c_void_p), ("invK", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hs", C.c_int), ("ws", C.c_int), ("F", C.c_int),
+        ("automask", C.c_int), ("min_disp", C.c_float), ("max_disp", C.c_float), ("noise_scale", C.c_float),
+        ("seed", C.c_uint64), ("stream", C.c_uint64), ("loss_sum", C.c_void_p), ("min_index", C.c_void_p),
+        ("winner", C.c_void_p), ("warped", C.c_void_p * MAX_SRC),
+    ]
+
+
+class PhotoGrad(C.Structure):
+    _fields_ = [
+        ("grad_out", C.c_void_p), ("inv_count", C.c_float), ("winner", C.c_void_p), ("grad_disp", C.c_void_p),
+        ("grad_T", C.c_void_p * MAX_SRC),
+    ]
+
+
+def _declare(h):
+    h.jpb_abi_version.restype = C.c_int
+    h.jpb_build_info.restype = C.c_char_p
+    for name in dir(_Signatures):
+        if name.startswith("jpb_"):
+            fn = getattr(h, name)
+            fn.restype = C.c_int
+            fn.argtypes = getattr(_Signatures, name)
+
+
+class _Signatures:
+    """argtypes of every int-returning entry point (kept next to include/jpb200.h)."""
+    P, I, F, V = C.c_void_p, C.c_int, C.c_float, C.c_void_p
+    jpb_photometric_fwd = [C.POINTER(PhotoArgs), V]
+    jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
+    jpb_finalize = [P, P, F, P, I, V]
+
+
+def exported_symbols():
+    return ["jpb_abi_version", "jpb_build_info"] + [n for n in dir(_Signatures) if n.startswith("jpb_")]
+
+
+def lib():
+    """The loaded library; raises if the CUDA extension has not been built."""
+    global _handle
+    if _handle is None:
+        if not os.path.exists(LIB_PATH):
+            raise JpbError("libjpb200.so is missing (%s): build it with `python -m jperceiver_b200.build`; "
+                           "jperceiver_b200 has no CPU fallback" % LIB_PATH)
+        _handle = C.CDLL(LIB_PATH)
+        _declare(_handle)
+    return _handle
+
+
+def use_library(path, emulated=False):
+    """TESTS ONLY: bind a different build of the same ABI (the host emulation)."""
+    global _handle, _emulated
+    _handle = C.CDLL(path)
+    _declare(_handle)
+    _emulated = emulated
+    return _handle
+
+
+def is_emulated():
+    return _emulated
+
+
+def check(status, what):
+    global launches
+    launches += 1
+    if status != 0:
+        raise JpbError("%s failed with status %d" % (what, status))
+
+
+def ptr(t):
+    """Device pointer of a tensor (NULL for None).  Tensors must be CUDA (or CPU under emulation)."""
+    if t is None:
+        return None
+    if not t.is_cuda and not _emulated:
+        raise JpbError("jperceiver_b200 kernels take CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
+    return t.data_ptr()
+
+
+def stream_of(t):
+    if t.is_cuda:
+        return torch.cuda.current_stream(t.device).cuda_stream
+    return None

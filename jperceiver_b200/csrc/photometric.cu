@@ -1,0 +1,465 @@
+// Fused photometric-reprojection loss, one launch per scale (forward) and one per scale (backward).
+//
+// Replaces, per scale s, the reference chain (all paths under /root/reference/mono/model/mono_baseline):
+//   net.py:690-702  generate_images_pred : bilinear up-sample of disp_s -> disp_to_depth -> Backproject
+//                                          -> Project -> F.grid_sample(border)
+//   layers.py:41-82 Backproject / Project ; layers.py:85-107 SSIM ; net.py:84-92 robust_l1 + mix
+//   net.py:159-175  automask identity terms (+N(0,1)*1e-5), min over candidates, argmin, mean
+// which in eager PyTorch is ~10 kernels x F x 4 scales with ~30 full-resolution temporaries per call.
+// Here each CTA owns a 32x16 pixel tile of one sample: it stages target / identity / warped pixels
+// for the tile plus the 1-pixel SSIM apron in shared memory (reflect-indexed at the image border),
+// evaluates all 2F candidates from shared memory, takes min/argmin and reduces the tile's sum with
+// warp shuffles; HBM sees each input pixel once (+apron) and only scalar / 1-byte-per-pixel outputs.
+//
+// Algorithmic bytes per sample per scale: 4*H*W*(3+3F) + 4*hs*ws  (forward).
+#include "jpb_common.cuh"
+#include "../../include/jpb200.h"
+
+namespace {
+
+constexpr int PT_W = 32, PT_H = 16;           // output tile
+constexpr int P1_W = PT_W + 2, P1_H = PT_H + 2, P1_N = P1_W * P1_H;  // +1 apron (SSIM window)
+constexpr int P2_W = PT_W + 4, P2_H = PT_H + 4, P2_N = P2_W * P2_H;  // +2 apron (backward)
+constexpr float SSIM_C1 = 1e-4f, SSIM_C2 = 9e-4f;
+
+struct SrcGeom {  // P = (K T)[:3,:]  (layers.py:74); p = P * (z * invK3x3 * (x,y,1), 1) in the reference's order
+  float P[12];
+};
+
+__device__ __forceinline__ void make_geom(const float* K, const float* T, SrcGeom& g) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < 4; ++k) s += K[i * 4 + k] * T[k * 4 + j];
+      g.P[i * 4 + j] = s;
+    }
+}
+
+// camera ray invK[:3,:3] * (x, y, 1)   (layers.py:58)
+__device__ __forceinline__ void pixel_ray(const float* iK, int x, int y, float rc[3]) {
+  const float fx = (float)x, fy = (float)y;
+  rc[0] = iK[0] * fx + iK[1] * fy + iK[2];
+  rc[1] = iK[4] * fx + iK[5] * fy + iK[6];
+  rc[2] = iK[8] * fx + iK[9] * fy + iK[10];
+}
+
+// ATen upsample_bilinear2d(align_corners=False) source index + weights for one axis
+__device__ __forceinline__ void up_axis(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+struct DispTap {
+  int y0, y1, x0, x1;
+  float ly, lx;
+};
+
+__device__ __forceinline__ float disp_upsample(const float* d, int hs, int ws, float sy, float sx, int y, int x, DispTap& tp) {
+  up_axis(y, sy, hs, tp.y0, tp.y1, tp.ly);
+  up_axis(x, sx, ws, tp.x0, tp.x1, tp.lx);
+  const float a = d[tp.y0 * ws + tp.x0], b = d[tp.y0 * ws + tp.x1];
+  const float c = d[tp.y1 * ws + tp.x0], e = d[tp.y1 * ws + tp.x1];
+  return (1.f - tp.ly) * ((1.f - tp.lx) * a + tp.lx * b) + tp.ly * ((1.f - tp.lx) * c + tp.lx * e);
+}
+
+struct Sample {      // grid_sample(bilinear, border, align_corners=False) footprint
+  int x0, y0;        // north-west tap
+  float tx, ty;      // fractional offsets
+  float mx, my;      // d(ix)/d(unclipped ix): 0 where the coordinate was clipped
+  float p[3];        // projected homogeneous point
+};
+
+__device__ __forceinline__ void project(const SrcGeom& g, float z, const float rc[3], int W, int H, Sample& s) {
+  const float X0 = z * rc[0], X1 = z * rc[1], X2 = z * rc[2];
+  s.p[0] = g.P[0] * X0 + g.P[1] * X1 + g.P[2] * X2 + g.P[3];
+  s.p[1] = g.P[4] * X0 + g.P[5] * X1 + g.P[6] * X2 + g.P[7];
+  s.p[2] = g.P[8] * X0 + g.P[9] * X1 + g.P[10] * X2 + g.P[11];
+  const float den = s.p[2] + 1e-7f;
+  const float u = s.p[0] / den, v = s.p[1] / den;
+  const float gx = (u / (float)(W - 1) - 0.5f) * 2.f, gy = (v / (float)(H - 1) - 0.5f) * 2.f;
+  float ix = ((gx + 1.f) * (float)W - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)H - 1.f) * 0.5f;
+  s.mx = 1.f; s.my = 1.f;
+  // clip_coordinates: NaN-safe min/max order as ATen (min(max(x,0),size-1))
+  if (!(ix > 0.f)) { ix = 0.f; s.mx = 0.f; }
+  if (ix > (float)(W - 1)) { ix = (float)(W - 1); s.mx = 0.f; }
+  if (!(iy > 0.f)) { iy = 0.f; s.my = 0.f; }
+  if (iy > (float)(H - 1)) { iy = (float)(H - 1); s.my = 0.f; }
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  s.x0 = (int)fx0; s.y0 = (int)fy0;
+  s.tx = ix - fx0; s.ty = iy - fy0;
+}
+
+__device__ __forceinline__ void gather3(const float* img, int H, int W, const Sample& s, float out[3]) {
+  const int x1 = s.x0 + 1, y1 = s.y0 + 1;
+  const bool xin = x1 < W, yin = y1 < H;   // north-west tap is always inside after clipping
+  const float wnw = (1.f - s.tx) * (1.f - s.ty), wne = s.tx * (1.f - s.ty);
+  const float wsw = (1.f - s.tx) * s.ty, wse = s.tx * s.ty;
+  const size_t plane = (size_t)H * W;
+  const size_t o00 = (size_t)s.y0 * W + s.x0;
+  for (int c = 0; c < 3; ++c) {
+    const float* p = img + c * plane;
+    float v = p[o00] * wnw;
+    if (xin) v += p[o00 + 1] * wne;
+    if (yin) v += p[o00 + W] * wsw;
+    if (xin && yin) v += p[o00 + W + 1] * wse;
+    out[c] = v;
+  }
+}
+
+// 0.85*mean_c SSIM(x,y) + 0.15*mean_c sqrt((x-y)^2+1e-6) from 3x3 windows in shared memory
+__device__ __forceinline__ float reproj_error(const float* xs, const float* ys, int plane, int stride, int ctr,
+                                              const float* my, const float* syy) {
+  float ssim = 0.f, l1 = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    const float* x = xs + c * plane + ctr;
+    const float* y = ys + c * plane + ctr;
+    float sx = 0.f, sxx = 0.f, sxy = 0.f;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const float xv = x[dy * stride + dx], yv = y[dy * stride + dx];
+        sx += xv; sxx += xv * xv; sxy += xv * yv;
+      }
+    const float mx = sx * (1.f / 9.f), m_y = my[c];
+    const float vx = sxx * (1.f / 9.f) - mx * mx, vxy = sxy * (1.f / 9.f) - mx * m_y;
+    const float n = (2.f * mx * m_y + SSIM_C1) * (2.f * vxy + SSIM_C2);
+    const float d = (mx * mx + m_y * m_y + SSIM_C1) * (vx + syy[c] + SSIM_C2);
+    ssim += __saturatef((1.f - n / d) * 0.5f);
+    const float df = y[0] - x[0];
+    l1 += sqrtf(df * df + 1e-6f);
+  }
+  return 0.85f * (ssim * (1.f / 3.f)) + 0.15f * (l1 * (1.f / 3.f));
+}
+
+// ------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(256) photometric_fwd_kernel(JpbPhotoArgs a) {
+  JPB_DYN_SMEM(float, sm);
+  __shared__ SrcGeom geom[JPB_MAX_SRC];
+  __shared__ double red[32];
+  const int b = blockIdx.z, x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+  const int F = a.F, H = a.H, W = a.W;
+  const int nid = a.automask ? F : 0;
+  float* s_tgt = sm;                       // [3][P1_N]
+  float* s_id = s_tgt + 3 * P1_N;          // [nid][3][P1_N]
+  float* s_wp = s_id + nid * 3 * P1_N;     // [F][3][P1_N]
+  const size_t plane = (size_t)H * W;
+
+  for (int f = JPB_TID; f < F; f += JPB_NT) make_geom(a.K + b * 16, a.T[f] + b * 16, geom[f]);
+  __syncthreads();
+
+  const float* disp = a.disp + (size_t)b * a.hs * a.ws;
+  const float sy = (float)a.hs / (float)H, sx = (float)a.ws / (float)W;
+  for (int e = JPB_TID; e < P1_N; e += JPB_NT) {
+    const int hy = e / P1_W, hx = e - hy * P1_W;
+    const int y = jpb_reflect(min(y0 + hy - 1, H), H), x = jpb_reflect(min(x0 + hx - 1, W), W);
+    const size_t o = (size_t)y * W + x;
+    const float* tg = a.target + (size_t)b * 3 * plane + o;
+    s_tgt[e] = tg[0]; s_tgt[P1_N + e] = tg[plane]; s_tgt[2 * P1_N + e] = tg[2 * plane];
+    DispTap tp;
+    const float D = disp_upsample(disp, a.hs, a.ws, sy, sx, y, x, tp);
+    const float z = 1.f / (a.min_disp + (a.max_disp - a.min_disp) * D);
+    const bool interior = hy >= 1 && hy <= PT_H && hx >= 1 && hx <= PT_W && (y0 + hy - 1) < H && (x0 + hx - 1) < W;
+    float rc[3];
+    pixel_ray(a.invK + b * 16, x, y, rc);
+    for (int f = 0; f < F; ++f) {
+      const float* sp = a.src[f] + (size_t)b * 3 * plane;
+      if (nid) {
+        float* d = s_id + f * 3 * P1_N + e;
+        d[0] = sp[o]; d[P1_N] = sp[plane + o]; d[2 * P1_N] = sp[2 * plane + o];
+      }
+      Sample s;
+      project(geom[f], z, rc, W, H, s);
+      float v[3];
+      gather3(sp, H, W, s, v);
+      float* d = s_wp + f * 3 * P1_N + e;
+      d[0] = v[0]; d[P1_N] = v[1]; d[2 * P1_N] = v[2];
+      if (interior && a.warped[f]) {
+        float* wo = a.warped[f] + (size_t)b * 3 * plane + o;
+        wo[0] = v[0]; wo[plane] = v[1]; wo[2 * plane] = v[2];
+      }
+    }
+  }
+  __syncthreads();
+
+  float local = 0.f;
+  for (int e = JPB_TID; e < PT_W * PT_H; e += JPB_NT) {
+    const int ty = e / PT_W, tx = e - ty * PT_W;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    const int ctr = (ty + 1) * P1_W + tx + 1;
+    float my[3], vyy[3];
+    for (int c = 0; c < 3; ++c) {
+      const float* yp = s_tgt + c * P1_N + ctr;
+      float s1 = 0.f, s2 = 0.f;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const float v = yp[dy * P1_W + dx];
+          s1 += v; s2 += v * v;
+        }
+      my[c] = s1 * (1.f / 9.f);
+      vyy[c] = s2 * (1.f / 9.f) - my[c] * my[c];
+    }
+    float best = 3.0e38f;
+    int besti = 0;
+    const size_t po = (size_t)b * plane + (size_t)y * W + x;
+    for (int f = 0; f < nid; ++f) {
+      float err = reproj_error(s_id + f * 3 * P1_N, s_tgt, P1_N, P1_W, ctr, my, vyy);
+      if (a.noise[f]) err += a.noise[f][po];
+      else if (a.noise_scale != 0.f) err += a.noise_scale * jpb_randn(a.seed, a.stream + (uint64_t)f, (uint64_t)po);
+      if (err < best) { best = err; besti = f; }
+    }
+    for (int f = 0; f < F; ++f) {
+      const float err = reproj_error(s_wp + f * 3 * P1_N, s_tgt, P1_N, P1_W, ctr, my, vyy);
+      if (err < best) { best = err; besti = nid + f; }
+    }
+    if (a.min_index) a.min_index[po] = (long long)besti;
+    if (a.winner) a.winner[po] = (unsigned char)besti;
+    local += best;
+  }
+  const double tot = jpb_block_sum<double>((double)local, red);
+  if (JPB_TID == 0) atomicAdd(a.loss_sum, tot);
+}
+
+// ------------------------------------------------------------------------------------ backward
+// d(loss_s)/d(disp_s) and d(loss_s)/d(T_f).  Gradient reaches a warped candidate only where it is the
+// arg-min; each warped pixel feeds the (up to) 9 SSIM windows around it, with multiplicity 2 where the
+// reflect padding maps two taps of a border window onto the same pixel.
+__global__ void __launch_bounds__(256) photometric_bwd_kernel(JpbPhotoArgs a, JpbPhotoGrad g) {
+  JPB_DYN_SMEM(float, sm);
+  __shared__ SrcGeom geom[JPB_MAX_SRC];
+  __shared__ float red[32];
+  __shared__ float s_dd[(PT_H + 4) * (PT_W + 4)];  // disparity-gradient footprint of the tile (factor >= 1... <=2 px/px)
+  const int b = blockIdx.z, x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+  const int F = a.F, H = a.H, W = a.W;
+  const int nid = a.automask ? F : 0;
+  float* s_tgt = sm;                      // [3][P2_N]
+  float* s_wp = s_tgt + 3 * P2_N;         // [F][3][P2_N]
+  float* s_coef = s_wp + F * 3 * P2_N;    // [9][P1_N]  (alpha,beta,gamma) x 3 channels of the winning window
+  int* s_sel = reinterpret_cast<int*>(s_coef + 9 * P1_N);  // [P1_N] winning warped source of window q, or -1
+  const size_t plane = (size_t)H * W;
+  const float gpix = g.grad_out[0] * g.inv_count;
+
+  for (int f = JPB_TID; f < F; f += JPB_NT) make_geom(a.K + b * 16, a.T[f] + b * 16, geom[f]);
+  const float* disp = a.disp + (size_t)b * a.hs * a.ws;
+  const float sy = (float)a.hs / (float)H, sx = (float)a.ws / (float)W;
+  // disparity footprint of this tile
+  int fy0, fx0, tmp; float tl;
+  up_axis(min(y0, H - 1), sy, a.hs, fy0, tmp, tl);
+  up_axis(min(x0, W - 1), sx, a.ws, fx0, tmp, tl);
+  const int FW = PT_W + 4;
+  for (int e = JPB_TID; e < (PT_H + 4) * (PT_W + 4); e += JPB_NT) s_dd[e] = 0.f;
+  __syncthreads();
+
+  // phase A: target + warped sources on the 2-pixel apron
+  for (int e = JPB_TID; e < P2_N; e += JPB_NT) {
+    const int hy = e / P2_W, hx = e - hy * P2_W;
+    const int y = jpb_reflect(jpb_clampi(y0 + hy - 2, -(H - 1), H), H), x = jpb_reflect(jpb_clampi(x0 + hx - 2, -(W - 1), W), W);
+    const size_t o = (size_t)y * W + x;
+    const float* tg = a.target + (size_t)b * 3 * plane + o;
+    s_tgt[e] = tg[0]; s_tgt[P2_N + e] = tg[plane]; s_tgt[2 * P2_N + e] = tg[2 * plane];
+    DispTap tp;
+    const float D = disp_upsample(disp, a.hs, a.ws, sy, sx, y, x, tp);
+    const float z = 1.f / (a.min_disp + (a.max_disp - a.min_disp) * D);
+    float rc[3];
+    pixel_ray(a.invK + b * 16, x, y, rc);
+    for (int f = 0; f < F; ++f) {
+      Sample s;
+      project(geom[f], z, rc, W, H, s);
+      float v[3];
+      gather3(a.src[f] + (size_t)b * 3 * plane, H, W, s, v);
+      float* d = s_wp + f * 3 * P2_N + e;
+      d[0] = v[0]; d[P2_N] = v[1]; d[2 * P2_N] = v[2];
+    }
+  }
+  __syncthreads();
+
+  // phase B: per SSIM window q (tile + 1 apron): linear form of d(err_q)/d(x_i) = alpha + beta*x_i + gamma*y_i
+  for (int e = JPB_TID; e < P1_N; e += JPB_NT) {
+    const int hy = e / P1_W, hx = e - hy * P1_W;
+    const int y = y0 + hy - 1, x = x0 + hx - 1;
+    int sel = -1;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const int w = (int)g.winner[(size_t)b * plane + (size_t)y * W + x];
+      if (w >= nid) sel = w - nid;
+    }
+    s_sel[e] = sel;
+    if (sel < 0) continue;
+    const int ctr = (hy + 1) * P2_W + hx + 1;
+    for (int c = 0; c < 3; ++c) {
+      const float* xp = s_wp + (sel * 3 + c) * P2_N + ctr;
+      const float* yp = s_tgt + c * P2_N + ctr;
+      float sxv = 0.f, syv = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const float xv = xp[dy * P2_W + dx], yv = yp[dy * P2_W + dx];
+          sxv += xv; syv += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
+        }
+      const float ma = sxv * (1.f / 9.f), mb = syv * (1.f / 9.f);
+      const float va = sxx * (1.f / 9.f) - ma * ma, vb = syy * (1.f / 9.f) - mb * mb, vab = sxy * (1.f / 9.f) - ma * mb;
+      const float n1 = 2.f * ma * mb + SSIM_C1, n2 = 2.f * vab + SSIM_C2;
+      const float d1 = ma * ma + mb * mb + SSIM_C1, d2 = va + vb + SSIM_C2;
+      const float inv = 1.f / (d1 * d2);
+      const float S = (1.f - n1 * n2 * inv) * 0.5f;
+      float al = 0.f, be = 0.f, ga = 0.f;
+      if (S >= 0.f && S <= 1.f) {
+        // dS/dx_i = -(1/2) * (2/9) * [ (mb*n2 + n1*(y_i-mb))*inv - n1*n2*inv^2*(ma*d2 + d1*(x_i-ma)) ]
+        const float k = -(1.f / 9.f) * (0.85f / 3.f) * gpix;
+        const float q = n1 * n2 * inv * inv;
+        al = k * ((mb * n2 - n1 * mb) * inv - q * (ma * d2 - d1 * ma));
+        be = k * (-q * d1);
+        ga = k * (n1 * inv);
+      }
+      s_coef[(c * 3 + 0) * P1_N + e] = al;
+      s_coef[(c * 3 + 1) * P1_N + e] = be;
+      s_coef[(c * 3 + 2) * P1_N + e] = ga;
+    }
+  }
+  __syncthreads();
+
+  // phase C: gather window contributions per pixel, back through grid_sample / projection / up-sampling
+  float G[JPB_MAX_SRC][12];
+  for (int f = 0; f < JPB_MAX_SRC; ++f)
+    for (int i = 0; i < 12; ++i) G[f][i] = 0.f;
+  const float l1k = (0.15f / 3.f) * gpix;
+  for (int e = JPB_TID; e < PT_W * PT_H; e += JPB_NT) {
+    const int ty = e / PT_W, tx = e - ty * PT_W;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    const int c1 = (ty + 1) * P1_W + tx + 1, c2 = (ty + 2) * P2_W + tx + 2;
+    float gw[JPB_MAX_SRC][3];
+    bool any[JPB_MAX_SRC];
+    for (int f = 0; f < F; ++f) { gw[f][0] = gw[f][1] = gw[f][2] = 0.f; any[f] = false; }
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int qy = y + dy;
+      if (qy < 0 || qy >= H) continue;
+      const float mrow = ((qy == 0 && y == 1) || (qy == H - 1 && y == H - 2)) ? 2.f : 1.f;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int qx = x + dx;
+        if (qx < 0 || qx >= W) continue;
+        const int qe = c1 + dy * P1_W + dx;
+        const int f = s_sel[qe];
+        if (f < 0) continue;
+        const float m = mrow * (((qx == 0 && x == 1) || (qx == W - 1 && x == W - 2)) ? 2.f : 1.f);
+        any[f] = true;
+        for (int c = 0; c < 3; ++c) {
+          const float xv = s_wp[(f * 3 + c) * P2_N + c2], yv = s_tgt[c * P2_N + c2];
+          gw[f][c] += m * (s_coef[(c * 3 + 0) * P1_N + qe] + s_coef[(c * 3 + 1) * P1_N + qe] * xv + s_coef[(c * 3 + 2) * P1_N + qe] * yv);
+        }
+      }
+    }
+    {
+      const int f = s_sel[c1];
+      if (f >= 0)
+        for (int c = 0; c < 3; ++c) {
+          const float df = s_wp[(f * 3 + c) * P2_N + c2] - s_tgt[c * P2_N + c2];
+          gw[f][c] += l1k * df / sqrtf(df * df + 1e-6f);
+        }
+    }
+    DispTap tp;
+    const float D = disp_upsample(disp, a.hs, a.ws, sy, sx, y, x, tp);
+    const float sd = a.min_disp + (a.max_disp - a.min_disp) * D;
+    const float z = 1.f / sd;
+    float gz = 0.f;
+    float rc[3];
+    pixel_ray(a.invK + b * 16, x, y, rc);
+    const float X0 = z * rc[0], X1 = z * rc[1], X2 = z * rc[2];
+    for (int f = 0; f < F; ++f) {
+      if (!any[f]) continue;
+      Sample s;
+      project(geom[f], z, rc, W, H, s);
+      // d warped_c / d ix, d iy
+      const float* img = a.src[f] + (size_t)b * 3 * plane;
+      const int x1 = s.x0 + 1, y1 = s.y0 + 1;
+      const bool xin = x1 < W, yin = y1 < H;
+      const size_t o00 = (size_t)s.y0 * W + s.x0;
+      float gix = 0.f, giy = 0.f;
+      for (int c = 0; c < 3; ++c) {
+        const float* p = img + c * plane;
+        const float nw = p[o00], ne = xin ? p[o00 + 1] : 0.f, sw = yin ? p[o00 + W] : 0.f, se = (xin && yin) ? p[o00 + W + 1] : 0.f;
+        gix += gw[f][c] * ((ne - nw) * (1.f - s.ty) + (se - sw) * s.ty);
+        giy += gw[f][c] * ((sw - nw) * (1.f - s.tx) + (se - ne) * s.tx);
+      }
+      // ix = u*W/(W-1) - 0.5  (clip mask mx), u = px/(pz+eps)
+      const float gu = gix * s.mx * ((float)W / (float)(W - 1)), gv = giy * s.my * ((float)H / (float)(H - 1));
+      const float den = s.p[2] + 1e-7f, iden = 1.f / den;
+      const float gp0 = gu * iden, gp1 = gv * iden;
+      const float gp2 = -(gu * s.p[0] + gv * s.p[1]) * iden * iden;
+      const float* P = geom[f].P;
+      gz += gp0 * (P[0] * rc[0] + P[1] * rc[1] + P[2] * rc[2]) + gp1 * (P[4] * rc[0] + P[5] * rc[1] + P[6] * rc[2]) +
+            gp2 * (P[8] * rc[0] + P[9] * rc[1] + P[10] * rc[2]);
+      // G[i][j] += gp_i * Xh_j with Xh = (z*rc, 1)
+      const float gp[3] = {gp0, gp1, gp2};
+      for (int i = 0; i < 3; ++i) {
+        G[f][i * 4 + 0] += gp[i] * X0; G[f][i * 4 + 1] += gp[i] * X1;
+        G[f][i * 4 + 2] += gp[i] * X2; G[f][i * 4 + 3] += gp[i];
+      }
+    }
+    if (gz != 0.f) {
+      const float gD = gz * (-(a.max_disp - a.min_disp) * z * z);
+      const int r0 = (tp.y0 - fy0) * FW - fx0, r1 = (tp.y1 - fy0) * FW - fx0;
+      atomicAdd(&s_dd[r0 + tp.x0], gD * (1.f - tp.ly) * (1.f - tp.lx));
+      atomicAdd(&s_dd[r0 + tp.x1], gD * (1.f - tp.ly) * tp.lx);
+      atomicAdd(&s_dd[r1 + tp.x0], gD * tp.ly * (1.f - tp.lx));
+      atomicAdd(&s_dd[r1 + tp.x1], gD * tp.ly * tp.lx);
+    }
+  }
+  __syncthreads();
+  float* gd = g.grad_disp + (size_t)b * a.hs * a.ws;
+  for (int e = JPB_TID; e < (PT_H + 4) * (PT_W + 4); e += JPB_NT) {
+    const float v = s_dd[e];
+    if (v == 0.f) continue;
+    const int fy = fy0 + e / FW, fx = fx0 + e % FW;
+    if (fy < a.hs && fx < a.ws) atomicAdd(&gd[fy * a.ws + fx], v);
+  }
+  // pose gradient: dT[k][j] = sum_i K[i][k] * G[i][j]
+  for (int f = 0; f < F; ++f) {
+    if (!g.grad_T[f]) continue;
+    float tot[12];
+    for (int i = 0; i < 12; ++i) tot[i] = jpb_block_sum<float>(G[f][i], red);
+    if (JPB_TID == 0) {
+      const float* K = a.K + b * 16;
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 4; ++j) {
+          const float v = K[0 * 4 + k] * tot[0 * 4 + j] + K[1 * 4 + k] * tot[1 * 4 + j] + K[2 * 4 + k] * tot[2 * 4 + j];
+          if (v != 0.f) atomicAdd(&g.grad_T[f][b * 16 + k * 4 + j], v);
+        }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int jpb_photometric_fwd(const JpbPhotoArgs* a, void* stream) {
+  if (!a || a->F < 1 || a->F > JPB_MAX_SRC || a->H < 3 || a->W < 3 || !a->loss_sum) return JPB_ERR_ARG;
+  const int nid = a->automask ? a->F : 0;
+  const size_t smem = (size_t)(3 + 3 * nid + 3 * a->F) * P1_N * sizeof(float);
+  dim3 grid((a->W + PT_W - 1) / PT_W, (a->H + PT_H - 1) / PT_H, a->B);
+#ifndef JPB_HOST_EMU
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(photometric_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = smem;
+  }
+#endif
+  JPB_LAUNCH(photometric_fwd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+  return jpb_status();
+}
+
+extern "C" int jpb_photometric_bwd(const JpbPhotoArgs* a, const JpbPhotoGrad* g, void* stream) {
+  if (!a || !g || a->F < 1 || a->F > JPB_MAX_SRC || !g->winner || !g->grad_disp || !g->grad_out) return JPB_ERR_ARG;
+  if (a->hs > a->H || a->ws > a->W) return JPB_ERR_UNSUPPORTED;  // footprint buffer assumes up-sampling
+  const size_t smem = (size_t)(3 + 3 * a->F) * P2_N * sizeof(float) + (size_t)9 * P1_N * sizeof(float) + (size_t)P1_N * sizeof(int);
+  dim3 grid((a->W + PT_W - 1) / PT_W, (a->H + PT_H - 1) / PT_H, a->B);
+#ifndef JPB_HOST_EMU
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(photometric_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = smem;
+  }
+#endif
+  JPB_LAUNCH(photometric_bwd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a, *g);
+  return jpb_status();
+}

@@ -1,0 +1,40 @@
+"""Host emulation of the CUDA-core kernels — TEST INFRASTRUCTURE ONLY.
+
+The same ``jperceiver_b200/csrc/*.cu`` sources (minus the tcgen05/TMA files) are compiled as plain
+C++ with ``-DJPB_HOST_EMU`` (see ``csrc/jpb_common.cuh``): one "thread" per block, blocks run in
+sequence.  It exists so kernel *logic* can be checked against the oracle in the GPU-less authoring
+container; it is slow, never shipped, and ``jperceiver_b200`` never loads it on its own — tests
+install it explicitly through ``jperceiver_b200._lib.use_library``.
+"""
+from __future__ import annotations
+
+import glob
+import hashlib
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CSRC = os.path.join(ROOT, "jperceiver_b200", "csrc")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build")
+# files that contain inline PTX / TMA and cannot be emulated
+EXCLUDE = ("conv_tc.cu", "tma_util.cu")
+
+
+def build_emulation() -> str:
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [s for s in sorted(glob.glob(os.path.join(CSRC, "*.cu"))) if os.path.basename(s) not in EXCLUDE]
+    h = hashlib.sha256()
+    for p in srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "jpb200.h")]:
+        h.update(open(p, "rb").read())
+    lib = os.path.join(OUT, "libjpb200_emu_%s.so" % h.hexdigest()[:12])
+    if os.path.exists(lib):
+        return lib
+    for old in glob.glob(os.path.join(OUT, "libjpb200_emu_*.so")):
+        os.remove(old)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DJPB_HOST_EMU", "-Wno-unused-variable", "-Wno-unused-function", "-o", lib]
+    for s in srcs:
+        cmd += ["-x", "c++", s]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("emulation build failed:\n" + r.stdout + r.stderr)
+    return lib
