@@ -60,6 +60,80 @@ typedef struct JpbPhotoGrad {
 int jpb_photometric_fwd(const JpbPhotoArgs* args, void* stream);
 int jpb_photometric_bwd(const JpbPhotoArgs* args, const JpbPhotoGrad* grad, void* stream);
 
+/* ---- area-downsampled target pyramid -----------------------------------------------------------
+ * level[s] = F.interpolate(img, (H/2^(s+1), W/2^(s+1)), mode="area")  (net.py:762), all levels in one
+ * pass over the frame; H and W must be multiples of 2^nlev.                                        */
+typedef struct JpbPyramid {
+  int nlev;          /* 1..4 */
+  float* level[4];   /* [BC, H/2^(s+1), W/2^(s+1)] */
+} JpbPyramid;
+int jpb_area_pyramid(const float* img, int BC, int H, int W, const JpbPyramid* out, void* stream);
+
+/* ---- edge-aware smoothness (net.py:182-190, 758-786), one scale -------------------------------
+ * acc: [B,7] doubles, zero-filled by the caller (six stencil sums + sum of disp per sample), kept for
+ * backward.  out[0] = weight * smooth  with weight = smoothness_weight / 2^s / num_scales.        */
+int jpb_smooth_fwd(const float* disp, const float* J, int B, int h, int w, int disp_norm, float weight,
+                   double* acc, float* out, void* stream);
+int jpb_smooth_bwd(const float* disp, const float* J, int B, int h, int w, int disp_norm, float weight,
+                   const double* acc, const float* grad_out, float* grad_disp /* += */, void* stream);
+
+/* ---- CGT scale label (net.py:212-310 static, 403-476 both; layers.py:214-252) -------------------
+ * out[b] = warp(z_map) * warp(label)              (mode 0, "Argo_both")
+ *        = warp(z_map) * [warp(label)==1] * quad  (mode 1, "static"/"static_raw"; quad = the cv2-filled
+ *          rectangle projection of net.py:292-306, rasterised by the host from sample 0's calibration) */
+typedef struct JpbScaleLabelArgs {
+  const float* label;       /* [B,occ,occ] inputs[("both_dynamic"|"bothS",0,0)] in {0,1}           */
+  const float* K3;          /* inputs[("odometry_K",0,0)]: element (i,j) of sample b at K3[b*k_stride+i*k_row+j] */
+  int k_stride, k_row;
+  const float* Tr;          /* [B,4,4] inputs[("Tr_cam2_velo",0,0)]                                */
+  const unsigned char* quad;/* [Hf,Wf] (mode 1) or NULL                                            */
+  float* out;               /* [B,Hf,Wf]                                                           */
+  int B, occ, Hf, Wf;
+  int mode;                 /* 0 both, 1 static                                                    */
+  int align_corners;        /* torchgeometry 0.1.2 leaves it to torch's default: un-pinned, see DESIGN.md */
+  float z_offset;           /* 0.27 KITTI, 1.9 Argoverse (net.py:229-233)                          */
+  float cam_height;         /* 1.73 KITTI, 0.33 Argoverse (net.py:257-260)                         */
+} JpbScaleLabelArgs;
+int jpb_scale_label(const JpbScaleLabelArgs* args, void* stream);
+
+/* ---- CGT scale loss (net.py:193-211), one scale ----------------------------------------------
+ * acc[0] += sum |g-p|/g, acc[1] += count over label>0 (and the garg/eigen crop for static_raw).    */
+typedef struct JpbScaleLossArgs {
+  const float* disp;        /* [B,hs,ws]                    */
+  const float* label;       /* [B,Hf,Wf] from jpb_scale_label */
+  int B, hs, ws, Hf, Wf;
+  int crop;                 /* static_raw: rows 153..370, cols 44..1196 */
+  float min_disp, max_disp;
+  double* acc;              /* [2] */
+  float weight;             /* scale_weight / 2^s / num_scales (backward) */
+  const float* grad_out;    /* [1] (backward) */
+  float* grad_disp;         /* [B,hs,ws] += (backward) */
+} JpbScaleLossArgs;
+int jpb_scale_loss_fwd(const JpbScaleLossArgs* args, void* stream);
+int jpb_scale_loss_bwd(const JpbScaleLossArgs* args, void* stream);
+
+/* ---- signed distance map of binary BEV labels (boundary_loss.py:121-147) ------------------------
+ * sdf = EDT(background->foreground) - EDT(foreground->background), 0 on the inner 4-connected boundary,
+ * all-zero for an empty mask.  Exact (integer squared distances).  work: 2*B*n*n ints.              */
+int jpb_signed_distance(const float* label, int B, int n, int* work, float* sdf, void* stream);
+
+/* ---- BEV head loss: loss_weight*IoU + CE(weight=[1,w_fg]) + loss2_weight*BD (net.py:554-617) ------ */
+typedef struct JpbBevArgs {
+  const float* logits;      /* element (b,c,y,x) at logits[b*stride_b + (y*occ+x)*stride_p + c*stride_c] */
+  long long stride_b, stride_c, stride_p;
+  const float* label;       /* [B,occ,occ] in {0,1} */
+  const float* sdf;         /* [B,occ,occ] */
+  int B, occ;
+  float w_fg, loss_weight, loss2_weight;
+  double* acc;              /* [4*B + 3], zero-filled by the caller, kept for backward */
+} JpbBevArgs;
+int jpb_bev_loss_fwd(const JpbBevArgs* args, float* out, void* stream);
+int jpb_bev_loss_bwd(const JpbBevArgs* args, const float* grad_out, float* grad_logits, void* stream);
+
+/* ---- mean |x - y| (nn.L1Loss, net.py:619-622) -------------------------------------------------- */
+int jpb_l1_mean_fwd(const float* x, const float* y, long long n, double* acc /* [1] += */, void* stream);
+int jpb_l1_mean_bwd(const float* x, const float* y, long long n, const float* grad_out, float* gx, float* gy, void* stream);
+
 /* ---- accumulator finalisation: out[i] = (float)(acc[i] / (den ? den[i] : 1) * scale) --------------
  * (the `.mean()` / weight scalings of net.py:175-190, done on device so no loss term syncs the host) */
 int jpb_finalize(const double* acc, const double* den, float scale, float* out, int n, void* stream);

@@ -43,6 +43,34 @@ class PhotoGrad(C.Structure):
     ]
 
 
+class Pyramid(C.Structure):
+    _fields_ = [("nlev", C.c_int), ("level", C.c_void_p * 4)]
+
+
+class ScaleLabelArgs(C.Structure):
+    _fields_ = [
+        ("label", C.c_void_p), ("K3", C.c_void_p), ("k_stride", C.c_int), ("k_row", C.c_int), ("Tr", C.c_void_p),
+        ("quad", C.c_void_p), ("out", C.c_void_p), ("B", C.c_int), ("occ", C.c_int), ("Hf", C.c_int), ("Wf", C.c_int),
+        ("mode", C.c_int), ("align_corners", C.c_int), ("z_offset", C.c_float), ("cam_height", C.c_float),
+    ]
+
+
+class ScaleLossArgs(C.Structure):
+    _fields_ = [
+        ("disp", C.c_void_p), ("label", C.c_void_p), ("B", C.c_int), ("hs", C.c_int), ("ws", C.c_int), ("Hf", C.c_int),
+        ("Wf", C.c_int), ("crop", C.c_int), ("min_disp", C.c_float), ("max_disp", C.c_float), ("acc", C.c_void_p),
+        ("weight", C.c_float), ("grad_out", C.c_void_p), ("grad_disp", C.c_void_p),
+    ]
+
+
+class BevArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("stride_b", C.c_longlong), ("stride_c", C.c_longlong), ("stride_p", C.c_longlong),
+        ("label", C.c_void_p), ("sdf", C.c_void_p), ("B", C.c_int), ("occ", C.c_int), ("w_fg", C.c_float),
+        ("loss_weight", C.c_float), ("loss2_weight", C.c_float), ("acc", C.c_void_p),
+    ]
+
+
 def _declare(h):
     h.jpb_abi_version.restype = C.c_int
     h.jpb_build_info.restype = C.c_char_p
@@ -59,6 +87,17 @@ class _Signatures:
     jpb_photometric_fwd = [C.POINTER(PhotoArgs), V]
     jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
     jpb_finalize = [P, P, F, P, I, V]
+    jpb_area_pyramid = [P, I, I, I, C.POINTER(Pyramid), V]
+    jpb_smooth_fwd = [P, P, I, I, I, I, F, P, P, V]
+    jpb_smooth_bwd = [P, P, I, I, I, I, F, P, P, P, V]
+    jpb_scale_label = [C.POINTER(ScaleLabelArgs), V]
+    jpb_scale_loss_fwd = [C.POINTER(ScaleLossArgs), V]
+    jpb_scale_loss_bwd = [C.POINTER(ScaleLossArgs), V]
+    jpb_signed_distance = [P, I, I, P, P, V]
+    jpb_bev_loss_fwd = [C.POINTER(BevArgs), P, V]
+    jpb_bev_loss_bwd = [C.POINTER(BevArgs), P, P, V]
+    jpb_l1_mean_fwd = [P, P, C.c_longlong, P, V]
+    jpb_l1_mean_bwd = [P, P, C.c_longlong, P, P, P, V]
 
 
 def exported_symbols():

@@ -118,3 +118,186 @@ def photometric_loss(disp, target, sources, Ts, K, invK, *, num_scales=4, automa
     if debug_outputs:
         return loss, winner, out[2], list(out[3:])
     return loss, winner, None, []
+
+
+# --------------------------------------------------------------------------------------------------
+# area pyramid + smoothness
+# --------------------------------------------------------------------------------------------------
+def area_pyramid(img, nlev):
+    """[F.interpolate(img, /2^(s+1), mode='area') for s in range(nlev)] in one pass (no gradient)."""
+    img = _f32c(img)
+    B, Cc, H, W = img.shape
+    out = _lib.Pyramid()
+    out.nlev = nlev
+    levels = []
+    for s in range(nlev):
+        t = torch.empty(B, Cc, H >> (s + 1), W >> (s + 1), dtype=torch.float32, device=img.device)
+        levels.append(t)
+        out.level[s] = ptr(t)
+    check(_lib.lib().jpb_area_pyramid(ptr(img), B * Cc, H, W, C.byref(out), stream_of(img)), "jpb_area_pyramid")
+    return levels
+
+
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, J, weight, disp_norm):
+        disp_c, J = _f32c(disp), _f32c(J)
+        B, _, h, w = disp_c.shape
+        acc = torch.zeros(B, 7, dtype=torch.float64, device=disp_c.device)
+        out = torch.empty((), dtype=torch.float32, device=disp_c.device)
+        check(_lib.lib().jpb_smooth_fwd(ptr(disp_c), ptr(J), B, h, w, int(disp_norm), float(weight), ptr(acc), ptr(out),
+                                        stream_of(disp_c)), "jpb_smooth_fwd")
+        ctx.save_for_backward(disp_c, J, acc)
+        ctx.args = (float(weight), int(disp_norm))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, J, acc = ctx.saved_tensors
+        weight, disp_norm = ctx.args
+        B, _, h, w = disp.shape
+        gd = torch.zeros_like(disp)
+        check(_lib.lib().jpb_smooth_bwd(ptr(disp), ptr(J), B, h, w, disp_norm, weight, ptr(acc), ptr(_f32c(g).reshape(1)), ptr(gd),
+                                        stream_of(disp)), "jpb_smooth_bwd")
+        return gd, None, None, None
+
+
+def smooth_loss(disp, J, weight, disp_norm=True):
+    """``loss_dict[("smooth_loss", s)]`` (weight = smoothness_weight / 2^s / num_scales already applied)."""
+    return _Smooth.apply(disp, J, weight, disp_norm)
+
+
+# --------------------------------------------------------------------------------------------------
+# CGT scale label / loss
+# --------------------------------------------------------------------------------------------------
+def scale_label(label, odometry_K, Tr, out_hw, *, split, mode, quad=None, align_corners=True):
+    label, Kc, Tr = _f32c(label), _f32c(odometry_K), _f32c(Tr)
+    B, occ = label.shape[0], label.shape[-1]
+    Hf, Wf = out_hw
+    out = torch.empty(B, 1, Hf, Wf, dtype=torch.float32, device=label.device)
+    a = _lib.ScaleLabelArgs()
+    a.label, a.K3, a.Tr, a.out = ptr(label), ptr(Kc), ptr(Tr), ptr(out)
+    a.k_stride, a.k_row = Kc.shape[-2] * Kc.shape[-1], Kc.shape[-1]
+    a.quad = ptr(quad) if quad is not None else None
+    a.B, a.occ, a.Hf, a.Wf = B, occ, Hf, Wf
+    a.mode = {"both": 0, "static": 1}[mode]
+    a.align_corners = int(align_corners)
+    a.z_offset = 1.9 if split == "argo" else 0.27
+    a.cam_height = 0.33 if split == "argo" else 1.73
+    check(_lib.lib().jpb_scale_label(C.byref(a), stream_of(label)), "jpb_scale_label")
+    return out
+
+
+class _ScaleLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, label, weight, crop, min_depth, max_depth):
+        disp_c, label = _f32c(disp), _f32c(label)
+        acc = torch.zeros(2, dtype=torch.float64, device=disp_c.device)
+        a = _ScaleLoss._args(disp_c, label, acc, weight, crop, min_depth, max_depth)
+        check(_lib.lib().jpb_scale_loss_fwd(C.byref(a), stream_of(disp_c)), "jpb_scale_loss_fwd")
+        ctx.save_for_backward(disp_c, label, acc)
+        ctx.args = (weight, crop, min_depth, max_depth)
+        return finalize(acc[:1], weight, acc[1:]).reshape(())
+
+    @staticmethod
+    def _args(disp, label, acc, weight, crop, min_depth, max_depth):
+        a = _lib.ScaleLossArgs()
+        a.disp, a.label, a.acc = ptr(disp), ptr(label), ptr(acc)
+        a.B, a.hs, a.ws, a.Hf, a.Wf = disp.shape[0], disp.shape[-2], disp.shape[-1], label.shape[-2], label.shape[-1]
+        a.crop = int(crop)
+        a.min_disp, a.max_disp = 1.0 / max_depth, 1.0 / min_depth
+        a.weight = float(weight)
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, label, acc = ctx.saved_tensors
+        a = _ScaleLoss._args(disp, label, acc, *ctx.args)
+        gd = torch.zeros_like(disp)
+        gl = _f32c(g).reshape(1)
+        a.grad_out, a.grad_disp = ptr(gl), ptr(gd)
+        check(_lib.lib().jpb_scale_loss_bwd(C.byref(a), stream_of(disp)), "jpb_scale_loss_bwd")
+        return gd, None, None, None, None, None
+
+
+def scale_loss(disp, label, weight, crop=False, min_depth=0.1, max_depth=100.0):
+    """``loss_dict[("scale_loss", s)]`` (weight = scale_weight / 2^s / num_scales already applied)."""
+    return _ScaleLoss.apply(disp, label, float(weight), bool(crop), min_depth, max_depth)
+
+
+# --------------------------------------------------------------------------------------------------
+# BEV head losses
+# --------------------------------------------------------------------------------------------------
+def signed_distance(label):
+    """Exact signed distance map of every B×occ×occ binary label map, on device."""
+    label = _f32c(label)
+    B, n = label.shape[0], label.shape[-1]
+    work = torch.empty(2 * B * n * n, dtype=torch.int32, device=label.device)
+    sdf = torch.empty(B, n, n, dtype=torch.float32, device=label.device)
+    check(_lib.lib().jpb_signed_distance(ptr(label), B, n, ptr(work), ptr(sdf), stream_of(label)), "jpb_signed_distance")
+    return sdf
+
+
+class _BevLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, label, sdf, w_fg, lw, l2w):
+        if logits.dtype != torch.float32:
+            logits = logits.float()
+        if not (logits.is_contiguous() or logits.is_contiguous(memory_format=torch.channels_last)):
+            logits = logits.contiguous()
+        label = _f32c(label)
+        B, _, occ, _ = logits.shape
+        acc = torch.zeros(4 * B + 3, dtype=torch.float64, device=logits.device)
+        out = torch.empty((), dtype=torch.float32, device=logits.device)
+        a = _BevLoss._args(logits, label, sdf, acc, w_fg, lw, l2w)
+        check(_lib.lib().jpb_bev_loss_fwd(C.byref(a), ptr(out), stream_of(logits)), "jpb_bev_loss_fwd")
+        ctx.save_for_backward(logits, label, sdf, acc)
+        ctx.args = (w_fg, lw, l2w)
+        return out
+
+    @staticmethod
+    def _args(logits, label, sdf, acc, w_fg, lw, l2w):
+        a = _lib.BevArgs()
+        sb, sc, sy, sx = logits.stride()
+        assert sy == logits.shape[3] * sx, "logits rows must be dense"
+        a.logits, a.stride_b, a.stride_c, a.stride_p = ptr(logits), sb, sc, sx
+        a.label, a.sdf, a.acc = ptr(label), ptr(sdf), ptr(acc)
+        a.B, a.occ = logits.shape[0], logits.shape[2]
+        a.w_fg, a.loss_weight, a.loss2_weight = float(w_fg), float(lw), float(l2w)
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, label, sdf, acc = ctx.saved_tensors
+        a = _BevLoss._args(logits, label, sdf, acc, *ctx.args)
+        gl = torch.empty_like(logits)  # preserves the (dense) strides
+        check(_lib.lib().jpb_bev_loss_bwd(C.byref(a), ptr(_f32c(g).reshape(1)), ptr(gl), stream_of(logits)), "jpb_bev_loss_bwd")
+        return gl, None, None, None, None, None
+
+
+def bev_head_loss(logits, label, sdf, w_fg, loss_weight=20.0, loss2_weight=20.0):
+    """``compute_topview_loss`` for loss_type='iou', loss2_type='boundary', loss_sum=3."""
+    return _BevLoss.apply(logits, label, sdf, w_fg, loss_weight, loss2_weight)
+
+
+class _L1Mean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _f32c(x), _f32c(y)
+        acc = torch.zeros(1, dtype=torch.float64, device=x.device)
+        check(_lib.lib().jpb_l1_mean_fwd(ptr(x), ptr(y), x.numel(), ptr(acc), stream_of(x)), "jpb_l1_mean_fwd")
+        ctx.save_for_backward(x, y)
+        return finalize(acc, 1.0 / x.numel()).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        check(_lib.lib().jpb_l1_mean_bwd(ptr(x), ptr(y), x.numel(), ptr(_f32c(g).reshape(1)), ptr(gx), ptr(gy), stream_of(x)),
+              "jpb_l1_mean_bwd")
+        return gx, gy
+
+
+def l1_mean(x, y):
+    """``nn.L1Loss()(x, y)`` (compute_transform_losses).  x and y must share a memory layout."""
+    return _L1Mean.apply(x, y)

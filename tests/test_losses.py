@@ -1,0 +1,267 @@
+"""Parity of the fused loss-chain kernels with the oracle port (values and autograd gradients).
+
+Every case runs twice: ``[gpu]`` (marked ``gpu``) calls libjpb200.so through the C ABI on cuda:0 —
+the parity test proper; ``[emu]`` runs the same kernel sources compiled as host C++ (tests/emu), a
+logic check that works in the GPU-less authoring container."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, pat
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu import build_emulation  # noqa: E402
+from oracle import port as O  # noqa: E402
+
+from jperceiver_b200 import _lib, functional as JF  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def dev(request):
+    _lib._handle, _lib._emulated = None, False
+    if request.param == "emu":
+        _lib.use_library(build_emulation(), emulated=True)
+        yield torch.device("cpu")
+    else:
+        assert torch.cuda.is_available(), "gpu-marked test needs a CUDA device"
+        _lib.lib()
+        yield torch.device("cuda:0")
+    _lib._handle, _lib._emulated = None, False
+
+
+def D(x, dev):
+    if isinstance(x, (list, tuple)):
+        return [D(t, dev) for t in x]
+    return x.to(dev)
+
+
+def _photo_case(B=2, H=24, W=40, s=0, F=2, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    hs, ws = H >> (s + 1), W >> (s + 1)
+    base = torch.rand(B, 3, H // 4 + 2, W // 4 + 2, generator=g)
+    up = torch.nn.functional.interpolate(base, (H, W), mode="bicubic", align_corners=False).clamp(0, 1)
+    target = (0.8 * up + 0.2 * torch.rand(B, 3, H, W, generator=g)).clamp(0, 1)
+    sources = [(0.8 * torch.roll(up, (f, 2 * f), (2, 3)) + 0.2 * torch.rand(B, 3, H, W, generator=g)).clamp(0, 1)
+               for f in range(1, F + 1)]
+    disp = (0.05 + 0.9 * torch.rand(B, 1, hs, ws, generator=g))
+    K = torch.tensor([[.58 * W, 0, .5 * W, 0], [0, 1.92 * H, .5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]]).repeat(B, 1, 1)
+    invK = torch.linalg.pinv(K)
+    Ts = []
+    for f in range(F):
+        aa = 0.02 * torch.randn(B, 3, generator=g)
+        t = 0.1 * torch.randn(B, 3, generator=g)
+        Ts.append(O.pose_matrix(aa, t, invert=(f == 0)))
+    return target, sources, disp, K, invK, Ts
+
+
+def test_photometric_kat5(dev):
+    kat = np.load(os.path.join(GOLDEN, "kat.npz"))
+    H, W = 8, 12
+    K = torch.tensor([[.58 * W, 0, .5 * W, 0], [0, 1.92 * H, .5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]]).unsqueeze(0)
+    Tf, Ti = torch.from_numpy(kat["kat2_fwd"]), torch.from_numpy(kat["kat2_inv"])
+    loss, winner, idx, warped = JF.photometric_loss(
+        D(0.1 + 0.8 * pat((1, 1, 4, 6), 8), dev), D(pat((1, 3, 8, 12), 2), dev),
+        D([pat((1, 3, 8, 12), 6), pat((1, 3, 8, 12), 7)], dev), D([Ti, Tf], dev), D(K, dev), D(torch.linalg.pinv(K), dev),
+        num_scales=1, noise_scale=0.0, debug_outputs=True)
+    assert abs(loss.item() - float(kat["kat5_mean"])) < 2e-6
+    assert list(np.bincount(idx.flatten().cpu().numpy(), minlength=4)) == [0, 0, 41, 55]
+    assert np.abs(warped[0].cpu().numpy() - kat["kat5_warp_m1"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("s,H,W,automask", [(0, 24, 40, True), (1, 36, 72, True), (2, 32, 64, False), (0, 17, 33, True)])
+def test_photometric_forward_backward_vs_oracle(dev, s, H, W, automask):
+    target, sources, disp, K, invK, Ts = _photo_case(H=H, W=W, s=s)
+    B = target.shape[0]
+    g = torch.Generator().manual_seed(5)
+    noise = [1e-5 * torch.randn(B, 1, H, W, generator=g) for _ in sources]
+    d0 = disp.clone().requires_grad_(True)
+    T0 = [T.clone().requires_grad_(True) for T in Ts]
+    m, idx, warped = O.photometric_scale(d0, target, sources, T0, K, invK, automask=automask, noise=noise)
+    (m / 4).backward()
+    d1 = D(disp, dev).requires_grad_(True)
+    T1 = [D(T, dev).requires_grad_(True) for T in Ts]
+    loss, winner, idx1, warped1 = JF.photometric_loss(d1, D(target, dev), D(sources, dev), T1, D(K, dev), D(invK, dev),
+                                                      num_scales=4, automask=automask,
+                                                      noise=D([n[:, 0] for n in noise], dev), debug_outputs=True)
+    assert abs(loss.item() - m.item() / 4) <= 1e-5 * abs(m.item() / 4)
+    assert (idx1.cpu() != idx).float().mean().item() < 2e-3
+    assert (winner.cpu().long() != idx1.cpu()).sum().item() == 0
+    for w0, w1 in zip(warped, warped1):
+        # sampling coordinates are O(W) in fp32: a few ulps of coordinate error move a textured pixel by ~1e-4
+        assert (w0 - w1.cpu()).abs().max().item() < 5e-4 and (w0 - w1.cpu()).abs().mean().item() < 2e-6
+    loss.backward()
+    gd0, gd1 = d0.grad, d1.grad.cpu()
+    assert (gd0 - gd1).abs().max().item() <= 2e-3 * gd0.abs().max().item() + 1e-9
+    for a, b in zip(T0, T1):
+        assert (a.grad - b.grad.cpu()).abs().max().item() <= 2e-3 * a.grad.abs().max().item() + 1e-9
+
+
+def test_area_pyramid_and_smoothness_kat4(dev):
+    kat = np.load(os.path.join(GOLDEN, "kat.npz"))
+    img = pat((1, 3, 8, 12), 2)
+    J = JF.area_pyramid(D(img, dev), 1)[0]
+    assert (J.cpu() - torch.nn.functional.interpolate(img, (4, 6), mode="area")).abs().max().item() < 1e-6
+    v = JF.smooth_loss(D(pat((1, 1, 4, 6), 5), dev), J, 1.0, True)
+    assert abs(v.item() - float(kat["kat4"])) < 1e-5
+
+
+@pytest.mark.parametrize("disp_norm", [True, False])
+def test_smoothness_forward_backward_vs_oracle(dev, disp_norm):
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 48, 80
+    img = torch.rand(B, 3, H, W, generator=g)
+    levels = JF.area_pyramid(D(img, dev), 4)
+    for s in range(4):
+        h, w = H >> (s + 1), W >> (s + 1)
+        assert (levels[s].cpu() - torch.nn.functional.interpolate(img, (h, w), mode="area")).abs().max().item() < 1e-6
+        disp = torch.rand(B, 1, h, w, generator=g) * 0.9 + 0.05
+        d0 = disp.clone().requires_grad_(True)
+        ref = 1e-3 * O.smooth_term(d0, img, disp_norm) / (2 ** s) / 4
+        ref.backward()
+        d1 = D(disp, dev).requires_grad_(True)
+        got = JF.smooth_loss(d1, levels[s], 1e-3 / (2 ** s) / 4, disp_norm)
+        assert abs(got.item() - ref.item()) <= 2e-5 * abs(ref.item())
+        (got * 3.0).backward()
+        assert (d1.grad.cpu() / 3.0 - d0.grad).abs().max().item() <= 1e-3 * d0.grad.abs().max().item()
+
+
+def _label_case(split, B=2, occ=64, seed=0):
+    from oracle.ref_loader import default_options
+    opt = default_options(type="Argo_both", split=split, occ_map_size=occ, height=4 * occ, width=4 * occ)
+    hw = (120, 400) if split != "argo" else (200, 240)
+    inp = O.synth_inputs(opt, B, seed=seed, hw_full=hw)
+    if split == "argo":  # 4x4 intrinsics as the Argoverse loader emits
+        K4 = torch.eye(4).repeat(B, 1, 1)
+        K4[:, :3, :3] = inp[("odometry_K", 0, 0)]
+        inp[("odometry_K", 0, 0)] = K4
+    # bring the projected BEV region inside the small test image
+    inp[("odometry_K", 0, 0)][:, 0, 0] *= 0.3
+    inp[("odometry_K", 0, 0)][:, 1, 1] *= 0.3
+    inp[("odometry_K", 0, 0)][:, 0, 2] = hw[1] / 2
+    inp[("odometry_K", 0, 0)][:, 1, 2] = hw[0] / 3
+    return opt, inp, hw
+
+
+@pytest.mark.parametrize("split,align", [("odometry", True), ("argo", True), ("odometry", False)])
+def test_scale_label_both_vs_oracle(dev, split, align):
+    opt, inp, hw = _label_case(split)
+    ref = O.scale_label(opt, inp, warp_align_corners=align)
+    got = JF.scale_label(D(inp[("both_dynamic", 0, 0)], dev), D(inp[("odometry_K", 0, 0)], dev),
+                         D(inp[("Tr_cam2_velo", 0, 0)], dev), hw, split=split, mode="both", align_corners=align).cpu()
+    assert (ref > 0).float().mean().item() > 0.01, "test geometry must put the BEV map inside the image"
+    d = (got - ref).abs()
+    # near the horizon the warp is ill-conditioned: the reference's own fp32 matrix inverses move a few pixels
+    assert (d > 2e-3).float().mean().item() < 1e-3 and d.mean().item() < 2e-5 and d.max().item() < 0.05
+
+
+def test_scale_label_static_and_loss_vs_oracle(dev):
+    opt, inp, hw = _label_case("odometry")
+    opt["type"] = "static"
+    ref = O.scale_label(opt, inp)
+    occ = opt["occ_map_size"]
+    Minv = O.bev_to_image_homography(inp[("odometry_K", 0, 0)][:, :3, :3], inp[("Tr_cam2_velo", 0, 0)], "odometry", occ)
+    quad = (O.static_quad_mask(Minv[0], occ, *hw) > 0).to(torch.uint8)
+    got = JF.scale_label(D(inp[("bothS", 0, 0)], dev), D(inp[("odometry_K", 0, 0)], dev), D(inp[("Tr_cam2_velo", 0, 0)], dev),
+                         hw, split="odometry", mode="static", quad=D(quad, dev)).cpu()
+    assert (ref > 0).sum().item() > 50
+    assert ((got > 0) != (ref > 0)).float().mean().item() < 1e-3
+    both = (got > 0) & (ref > 0)
+    assert (got - ref)[both].abs().max().item() < 2e-3
+    g = torch.Generator().manual_seed(1)
+    for s, crop in ((0, False), (2, False)):
+        disp = torch.rand(2, 1, 32 >> s, 64 >> s, generator=g) * 0.9 + 0.05
+        d0 = disp.clone().requires_grad_(True)
+        r = 0.1 * O.scale_term(d0, ref, "static") / (2 ** s) / 4
+        r.backward()
+        d1 = D(disp, dev).requires_grad_(True)
+        v = JF.scale_loss(d1, D(ref, dev), 0.1 / (2 ** s) / 4, crop)
+        assert abs(v.item() - r.item()) <= 1e-5 * abs(r.item())
+        v.backward()
+        assert (d1.grad.cpu() - d0.grad).abs().max().item() <= 1e-4 * d0.grad.abs().max().item()
+
+
+def test_signed_distance_exact(dev):
+    kat = np.load(os.path.join(GOLDEN, "kat.npz"))
+    lab = torch.zeros(1, 16, 16)
+    lab[:, 4:11, 3:9] = 1
+    assert np.abs(JF.signed_distance(D(lab, dev))[0].cpu().numpy() - kat["kat6_sdf"]).max() < 1e-6
+    g = torch.Generator().manual_seed(7)
+    maps = (torch.rand(5, 48, 48, generator=g) > 0.7).float()
+    maps[3] = 0            # empty foreground -> all zeros
+    maps[4, 10:30, 5:40] = 1
+    got = JF.signed_distance(D(maps, dev)).cpu().numpy()
+    for b in range(5):
+        assert np.abs(got[b] - O.signed_distance(maps[b].numpy())).max() < 1e-5
+    assert not got[3].any()
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_bev_head_loss_forward_backward_vs_oracle(dev, channels_last):
+    kat = np.load(os.path.join(GOLDEN, "kat.npz"))
+    big = torch.cat([4 * pat((2, 1, 256, 256), 9) - 2, 4 * pat((2, 1, 256, 256), 10) - 2], 1)
+    lab = torch.zeros(2, 1, 256, 256)
+    lab[:, :, 64:176, 48:144] = 1
+    lab[1, :, 200:240, 10:250] = 1
+    sdf = JF.signed_distance(D(lab[:, 0], dev))
+    v = JF.bev_head_loss(D(big, dev), D(lab, dev), sdf, 5.0, 20.0, 20.0)
+    assert abs(v.item() - float(kat["kat7_b2_w5"])) <= 2e-6 * abs(float(kat["kat7_b2_w5"]))
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(3, 2, 32, 32, generator=g) * 2
+    labels = (torch.rand(3, 1, 32, 32, generator=g) > 0.6).float()
+    labels[2] = 0
+    l0 = logits.clone().requires_grad_(True)
+    ref = O.bev_head_loss(l0, labels, 15.0, 20.0, 20.0)
+    ref.backward()
+    l1 = D(logits, dev)
+    if channels_last:
+        l1 = l1.contiguous(memory_format=torch.channels_last)
+    l1.requires_grad_(True)
+    got = JF.bev_head_loss(l1, D(labels, dev), JF.signed_distance(D(labels[:, 0], dev)), 15.0, 20.0, 20.0)
+    assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    (2.0 * got).backward()
+    assert (l1.grad.cpu() / 2.0 - l0.grad).abs().max().item() <= 1e-4 * l0.grad.abs().max().item()
+
+
+def test_l1_mean_vs_kat8(dev):
+    kat = np.load(os.path.join(GOLDEN, "kat.npz"))
+    x = D(pat((1, 128, 8, 8), 11), dev).requires_grad_(True)
+    y = D(pat((1, 128, 8, 8), 12), dev).requires_grad_(True)
+    v = JF.l1_mean(x, y)
+    assert abs(v.item() - float(kat["kat8"])) < 1e-6
+    v.backward()
+    ref = torch.sign(x.detach() - y.detach()) / x.numel()
+    assert x.grad.device == x.device
+    assert (x.grad - ref).abs().max().item() < 1e-9 and (y.grad + ref).abs().max().item() < 1e-9
+
+
+@pytest.mark.gpu
+def test_photometric_full_size_vs_oracle_and_properties():
+    """BASELINE size (320x1024, B=4, F=2), scale 0: oracle parity, plus size-independent properties:
+    batch-permutation invariance of the mean, and linearity of the gradient in the upstream scalar."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bench_photometric import make_case
+    _lib._handle, _lib._emulated = None, False
+    dev = torch.device("cuda:0")
+    B, H, W, F = 4, 320, 1024, 2
+    target, sources, disps, K, invK, Ts = make_case(B, H, W, F, dev)
+    disp = disps[0].clone().requires_grad_(True)
+    loss, winner, _, _ = JF.photometric_loss(disp, target, sources, Ts, K, invK, num_scales=4, noise_scale=0.0)
+    m, idx, _ = O.photometric_scale(disps[0].cpu(), target.cpu(), [s.cpu() for s in sources], [T.cpu() for T in Ts],
+                                    K.cpu(), invK.cpu(), automask=True, noise=None)
+    assert abs(loss.item() - m.item() / 4) <= 1e-4 * abs(m.item() / 4)          # tolerance: 1e-4 relative (north star: 1e-3)
+    assert (winner.cpu().long() != idx).float().mean().item() < 1e-3
+    perm = torch.tensor([2, 0, 3, 1], device=dev)
+    loss_p, _, _, _ = JF.photometric_loss(disps[0][perm], target[perm], [s[perm] for s in sources], [T[perm] for T in Ts],
+                                          K[perm], invK[perm], num_scales=4, noise_scale=0.0)
+    assert abs(loss_p.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    (g1,) = torch.autograd.grad(loss, disp, retain_graph=True)
+    (g3,) = torch.autograd.grad(3.0 * loss, disp)
+    assert (g3 - 3.0 * g1).abs().max().item() <= 1e-5 * g1.abs().max().item() * 3
+    # in-kernel Philox noise: deterministic per (seed, stream), different across seeds, ~1e-5 effect
+    la = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=7, stream=1)[0].item()
+    lb = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=7, stream=1)[0].item()
+    lc = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=8, stream=1)[0].item()
+    assert la == lb and abs(la - loss.item()) < 1e-4 and abs(lc - loss.item()) < 1e-4

@@ -1,0 +1,87 @@
+"""Micro-benchmark of the fused photometric-loss kernels (forward and backward, four scales) on cuda:0.
+
+Prints one JSON line: ms per batch for the four forward launches and the four backward launches and the
+achieved algorithmic HBM bandwidth (SURVEY.md §8d bytes) against MEASURED_PEAKS.json.  Inputs are larger
+than L2 in aggregate only at B>=8, so an L2 flush (256 MiB write) runs between timed iterations."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from jperceiver_b200 import _lib, functional as JF  # noqa: E402
+
+
+def make_case(B, H, W, F, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    base = torch.rand(B, 3, H // 16 + 2, W // 16 + 2, generator=g)
+    up = torch.nn.functional.interpolate(base, (H, W), mode="bicubic", align_corners=False).clamp(0, 1)
+    target = (0.85 * up + 0.15 * torch.rand(B, 3, H, W, generator=g)).clamp(0, 1).to(dev)
+    sources = [(0.85 * torch.roll(up, (2 * f, 5 * f), (2, 3)) + 0.15 * torch.rand(B, 3, H, W, generator=g)).clamp(0, 1).to(dev)
+               for f in (-1, 1)[:F]]
+    disps = [(0.05 + 0.9 * torch.rand(B, 1, H >> (s + 1), W >> (s + 1), generator=g)).to(dev) for s in range(4)]
+    K = torch.tensor([[.58 * W, 0, .5 * W, 0], [0, 1.92 * H, .5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]]).repeat(B, 1, 1)
+    invK = torch.linalg.pinv(K)
+    Ts = []
+    for f in range(F):
+        T = torch.eye(4).repeat(B, 1, 1)
+        T[:, :3, 3] = torch.tensor([0.02, -0.01, 0.1 * (1 if f else -1)])
+        Ts.append(T.to(dev))
+    return target, sources, disps, K.to(dev), invK.to(dev), Ts
+
+
+def run(B=4, H=320, W=1024, F=2, iters=20, warmup=3):
+    dev = torch.device("cuda:0")
+    target, sources, disps, K, invK, Ts = make_case(B, H, W, F, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    disps = [d.requires_grad_(True) for d in disps]
+    Ts = [T.requires_grad_(True) for T in Ts]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    fwd_ms, bwd_ms = [], []
+    for it in range(warmup + iters):
+        flush.zero_()
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        losses = [JF.photometric_loss(disps[s], target, sources, Ts, K, invK, num_scales=4, seed=it, stream=s)[0] for s in range(4)]
+        e1.record()
+        tot = losses[0] + losses[1] + losses[2] + losses[3]
+        flush.zero_()
+        e1b = ev()
+        e1b.record()
+        tot.backward()
+        e2.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            fwd_ms.append(e0.elapsed_time(e1))
+            bwd_ms.append(e1b.elapsed_time(e2))
+        for d in disps:
+            d.grad = None
+        for T in Ts:
+            T.grad = None
+    fwd = sorted(fwd_ms)[len(fwd_ms) // 2]
+    bwd = sorted(bwd_ms)[len(bwd_ms) // 2]
+    bytes_fwd = sum(4 * H * W * (3 + 3 * F) + 4 * (H >> (s + 1)) * (W >> (s + 1)) for s in range(4)) * B
+    bytes_bwd = bytes_fwd + sum(4 * (H >> (s + 1)) * (W >> (s + 1)) for s in range(4)) * B
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    return {"metric": "fused photometric-loss ms/batch (4 scales)", "B": B, "H": H, "W": W, "F": F,
+            "fwd_ms": fwd, "bwd_ms": bwd, "fwd_alg_bytes": bytes_fwd, "bwd_alg_bytes": bytes_bwd,
+            "fwd_gbs": bytes_fwd / fwd / 1e6, "bwd_gbs": bytes_bwd / bwd / 1e6, "hbm_peak_gbs": hbm,
+            "fwd_frac": bytes_fwd / fwd / 1e6 / hbm, "bwd_frac": bytes_bwd / bwd / 1e6 / hbm,
+            "timing": "cuda events incl. python launch overhead of 4 launches; L2 flushed between iterations",
+            "peak_source": "measured" if peaks else "fallback"}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=4)
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    print(json.dumps(run(B=a.B, iters=a.iters)))
