@@ -1,0 +1,166 @@
+"""Network operators used by the model mirror (``jperceiver_b200.model``).
+
+Activations are logical ``(B, C, H, W)`` tensors stored channels-last (physically NHWC), fp32.
+Each operator below is one fused unit of the B200 design; ``BACKEND[name]`` says
+whether it currently runs as a hand-written sm_100a kernel from ``libjpb200.so`` ("jpb") or still as a
+library call ("torch": cuDNN/ATen on the same device, same memory format).  There is no CPU path: every
+operator refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+CL = torch.channels_last
+
+BACKEND = {
+    "conv2d": "torch", "batchnorm": "torch", "maxpool": "torch", "dropout": "torch", "image_prep": "torch",
+    "cvp_mlp": "torch", "cct_attention": "torch", "pose_head": "torch",
+}
+
+
+def _need_cuda(x):
+    if not x.is_cuda and not _lib.is_emulated():
+        raise _lib.JpbError("jperceiver_b200 runs on CUDA tensors only (got %s); there is no CPU fallback" % x.device)
+
+
+def _act(y, act):
+    if act == "none":
+        return y
+    if act == "relu":
+        return F.relu(y)
+    if act == "leaky":
+        return F.leaky_relu(y, 0.01)
+    if act == "sigmoid":
+        return torch.sigmoid(y)
+    raise ValueError(act)
+
+
+def conv2d(inputs, weight, bias=None, *, stride=1, pad=0, reflect=False, act="none", residual=None):
+    """Implicit-GEMM convolution with fused gather/epilogue.
+
+    ``inputs``: a tensor, or a list of ``(tensor, up2x)`` pairs that are (nearest-2x up-sampled and)
+    concatenated along channels on the fly — the ``cat(reduce(skip), upsample(x), disp)`` of
+    depth_decoder.py:76-80 never exists in memory.  ``reflect``: ReflectionPad2d(pad) instead of zeros.
+    Epilogue: ``+bias`` -> ``+residual`` -> activation.
+    """
+    if not isinstance(inputs, (list, tuple)):
+        inputs = [(inputs, False)]
+    _need_cuda(inputs[0][0])
+    xs = [F.interpolate(t, scale_factor=2, mode="nearest") if up else t for t, up in inputs]
+    x = xs[0] if len(xs) == 1 else torch.cat(xs, 1)
+    if reflect and pad:
+        x = F.pad(x, (pad,) * 4, mode="reflect")
+        pad = 0
+    y = F.conv2d(x.contiguous(memory_format=CL), weight, bias, stride=stride, padding=pad)
+    if residual is not None:
+        y = y + residual
+    return _act(y, act)
+
+
+def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1e-5):
+    """BatchNorm2d (+residual) (+ReLU).  Training mode uses per-GPU batch statistics and updates the
+    running statistics in place, as nn.BatchNorm2d does."""
+    _need_cuda(x)
+    if training:
+        bn.num_batches_tracked += 1
+    y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, momentum, eps)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+def maxpool(x, k, stride, pad):
+    _need_cuda(x)
+    return F.max_pool2d(x, k, stride, pad)
+
+
+def dropout(x, p, training, mask=None):
+    """nn.Dropout; ``mask`` (0/1 keep tensor) overrides the random draw (parity tests)."""
+    if not training or p == 0.0:
+        return x
+    if mask is None:
+        mask = (torch.rand_like(x) >= p).to(x.dtype)
+    return x * mask * (1.0 / (1.0 - p))
+
+
+def image_prep(images, out_hw=None):
+    """``(x - 0.45) / 0.225`` of one or two NCHW frames (concatenated along channels), optionally after a
+    bilinear resize (align_corners=False), emitted channels-last."""
+    if not isinstance(images, (list, tuple)):
+        images = [images]
+    _need_cuda(images[0])
+    outs = []
+    for im in images:
+        if out_hw is not None and tuple(im.shape[2:]) != tuple(out_hw):
+            im = F.interpolate(im, list(out_hw), mode="bilinear", align_corners=False)
+        outs.append((im - 0.45) / 0.225)
+    x = outs[0] if len(outs) == 1 else torch.cat(outs, 1)
+    return x.contiguous(memory_format=CL)
+
+
+def resize_bilinear(x, out_hw):
+    if tuple(x.shape[2:]) == tuple(out_hw):
+        return x
+    return F.interpolate(x, list(out_hw), mode="bilinear", align_corners=False)
+
+
+def cvp_mlp(x, fc0, fc2):
+    """Per-channel MLP over the flattened (h*w) positions: Linear+ReLU twice (CycledViewProjection.py:27-67)."""
+    _need_cuda(x)
+    B, C, h, w = x.shape
+    y = x.reshape(B, C, h * w)  # logical NCHW order, as the reference's .view does
+    y = F.relu(F.linear(y, fc0.weight, fc0.bias))
+    y = F.relu(F.linear(y, fc2.weight, fc2.bias))
+    return y.reshape(B, C, h, w).contiguous(memory_format=CL)
+
+
+def cct_attention(front, cross, front_hat, dfeat, p):
+    """Cross-view transformer core (CrossViewTransformer.py:45-92) after the depth-feature convs.
+    Returns (out, S, attn).  Quirks kept: hard max/arg-max over keys; ``attn @ value_d`` is a batched
+    (h x w) matrix product broadcast over channels."""
+    _need_cuda(front)
+    B, C, a, b = front.shape
+    n = a * b
+    q = conv2d(cross, p.query_conv.weight, p.query_conv.bias).reshape(B, -1, n)
+    k = conv2d(front, p.key_conv.weight, p.key_conv.bias).reshape(B, -1, n).permute(0, 2, 1)
+    energy = torch.bmm(k, q)
+    star, arg = energy.max(dim=1)
+    v = conv2d(front_hat, p.value_conv.weight, p.value_conv.bias).reshape(B, -1, n)
+    T = torch.gather(v, 2, arg.view(B, 1, n).expand(-1, v.shape[1], -1)).reshape(B, -1, a, b)
+    S = star.view(B, 1, a, b)
+    fused = conv2d([(front, False), (T, False)], p.f_conv.weight, p.f_conv.bias, pad=1)
+    out = front + fused * S
+    qd = conv2d(cross, p.query_conv_depth.weight, p.query_conv_depth.bias).reshape(B, -1, n)
+    kd = conv2d(front, p.key_conv_depth.weight, p.key_conv_depth.bias).reshape(B, -1, n).permute(0, 2, 1)
+    vd = conv2d(dfeat, p.value_conv_depth.weight, p.value_conv_depth.bias)
+    attn = torch.bmm(kd, qd).max(dim=1)[0].view(B, 1, a, b)
+    return (out + attn @ vd).contiguous(memory_format=CL), S, attn
+
+
+def pose_head(x, invert):
+    """Spatial mean of the 6-channel PoseDecoder output, x0.01, Rodrigues, 4x4 assembly
+    (pose_decoder.py:22-26, net.py:704-756)."""
+    _need_cuda(x)
+    v = 0.01 * x.mean(3).mean(2)
+    aa, t = v[:, :3], v[:, 3:]
+    B = aa.shape[0]
+    ang = aa.norm(dim=1, keepdim=True)
+    ax = aa / (ang + 1e-7)
+    ca, sa = torch.cos(ang)[:, 0], torch.sin(ang)[:, 0]
+    Cc = 1 - ca
+    x_, y_, z_ = ax[:, 0], ax[:, 1], ax[:, 2]
+    R3 = torch.stack([x_ * x_ * Cc + ca, x_ * y_ * Cc - z_ * sa, z_ * x_ * Cc + y_ * sa,
+                      x_ * y_ * Cc + z_ * sa, y_ * y_ * Cc + ca, y_ * z_ * Cc - x_ * sa,
+                      z_ * x_ * Cc - y_ * sa, y_ * z_ * Cc + x_ * sa, z_ * z_ * Cc + ca], 1).view(B, 3, 3)
+    R = torch.zeros(B, 4, 4, dtype=x.dtype, device=x.device)
+    R[:, :3, :3] = R3
+    R[:, 3, 3] = 1
+    T = torch.eye(4, dtype=x.dtype, device=x.device).repeat(B, 1, 1)
+    if invert:
+        T[:, :3, 3] = -t
+        return R.transpose(1, 2) @ T
+    T[:, :3, 3] = t
+    return T @ R
