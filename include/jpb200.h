@@ -134,6 +134,21 @@ int jpb_bev_loss_bwd(const JpbBevArgs* args, const float* grad_out, float* grad_
 int jpb_l1_mean_fwd(const float* x, const float* y, long long n, double* acc /* [1] += */, void* stream);
 int jpb_l1_mean_bwd(const float* x, const float* y, long long n, const float* grad_out, float* gx, float* gy, void* stream);
 
+/* ---- flat-buffer optimizer step (mono/core/utils/dist_utils.py:34-60 + torch.optim.Adam) ---------
+ * jpb_sumsq: acc[0] += sum g^2 (run on the all-reduced SUM of gradients).
+ * jpb_adam_step: g_eff = g * grad_scale (1/world) * min(1, max_norm / (sqrt(normsq)*grad_scale + 1e-6));
+ *                Adam(lr, beta1, beta2, eps, L2 weight_decay) with bias correction from the device-side
+ *                step counter, which the call increments (CUDA-graph replayable).                    */
+typedef struct JpbAdamArgs {
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;        /* 1 / world_size */
+  float max_norm;          /* <= 0 disables clipping */
+  const double* normsq;    /* [1] from jpb_sumsq, or NULL */
+  long long* step;         /* [1] device step counter (starts at 0) */
+} JpbAdamArgs;
+int jpb_sumsq(const float* g, long long n, double* acc, void* stream);
+int jpb_adam_step(float* p, const float* g, float* m, float* v, long long n, const JpbAdamArgs* args, void* stream);
+
 /* ---- accumulator finalisation: out[i] = (float)(acc[i] / (den ? den[i] : 1) * scale) --------------
  * (the `.mean()` / weight scalings of net.py:175-190, done on device so no loss term syncs the host) */
 int jpb_finalize(const double* acc, const double* den, float scale, float* out, int n, void* stream);

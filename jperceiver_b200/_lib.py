@@ -71,6 +71,11 @@ class BevArgs(C.Structure):
     ]
 
 
+class AdamArgs(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("grad_scale", C.c_float), ("max_norm", C.c_float), ("normsq", C.c_void_p), ("step", C.c_void_p)]
+
+
 def _declare(h):
     h.jpb_abi_version.restype = C.c_int
     h.jpb_build_info.restype = C.c_char_p
@@ -98,6 +103,8 @@ class _Signatures:
     jpb_bev_loss_bwd = [C.POINTER(BevArgs), P, P, V]
     jpb_l1_mean_fwd = [P, P, C.c_longlong, P, V]
     jpb_l1_mean_bwd = [P, P, C.c_longlong, P, P, P, V]
+    jpb_sumsq = [P, C.c_longlong, P, V]
+    jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
 
 
 def exported_symbols():

@@ -1,0 +1,262 @@
+"""``Baseline`` — the joint depth / pose / BEV-layout model with the reference's public surface
+(reference mono/model/mono_baseline/net.py:32-82: constructor takes ``cfg.model``; ``forward(inputs)``
+returns ``(outputs, loss_dict)`` in training mode and ``outputs`` in eval mode; same dict keys).
+
+What differs from the reference is everything underneath: sub-networks run on fused channels-last
+operators (``netops``) and ``compute_losses`` is a handful of fused sm_100a kernels
+(``functional``) with no host round-trips — no ``.cpu()``/cv2/scipy calls inside the step, no
+per-scale full-resolution temporaries.
+
+Pinned semantics where the reference is defective or undefined (the oracle
+applies the same rules):
+  * loss selection per ``type`` follows the alternate copy /net.py:114-159; ``Argo_both`` follows net.py:94-138;
+  * ``loss_weightS``/``loss2_weightS`` default to ``loss_weight``/``loss2_weight`` (only the Argo config defines them);
+  * ``static_eigen``: depth + pose only (photometric + smoothness);
+  * non-square inputs: the layout branch sees the frame bilinearly resized to (4*occ)^2 and the CCT depth
+    feature is l4 resized to (occ/8)^2 — identities at the reference's 1024^2;
+  * the road head is evaluated once, not twice (net.py:73-74 evaluates it twice and discards one result);
+    ``bn_double_update=True`` re-applies the running-statistics update so BatchNorm buffers still match;
+  * torchgeometry's warp convention is the explicit option ``warp_align_corners`` (default True).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import functional as JF
+from ... import netops as ops
+from ..registry import MONO
+from .networks import (CrossViewTransformer, CycledViewProjection, Decoder, DepthDecoder, DepthEncoder, Encoder,
+                       PoseDecoder, PoseEncoder)
+from .params import BNP
+
+ROAD_TYPES = ("static", "static_raw", "Argo_static", "Argo_both")
+CAR_TYPES = ("dynamic", "Argo_dynamic", "Argo_both")
+LABEL_TYPES = ("static", "static_raw", "Argo_static", "Argo_both")
+
+
+class _Opt(dict):
+    """``cfg.model`` is read both as ``opt.x`` and ``opt["x"]`` by the reference."""
+    __getattr__ = dict.__getitem__
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def static_quad_points(occ):
+    """BEV-pixel corners of the 'assumption region' rectangle (net.py:235-248)."""
+    r1 = occ / 40
+    pr = [(round(18 * r1), round(31 * r1)), (round(22 * r1), round(31 * r1)), (round(18 * r1), round(33 * r1)),
+          (round(22 * r1), round(33 * r1))]
+    return [[occ - pr[3][1] - 1, pr[0][0] - 1], [occ - pr[3][1] + (pr[2][1] - pr[1][1]) - 1, pr[0][0] - 1],
+            [occ - pr[3][1] - 1, pr[1][0] - 1], [occ - pr[3][1] + (pr[2][1] - pr[1][1]) - 1, pr[1][0] - 1]]
+
+
+def static_quad_mask_host(K3, Tr, split, occ, height, width):
+    """The cv2-filled projection of that rectangle through sample 0's homography (net.py:292-306).
+
+    Host-side by design: it depends only on the calibration of sample 0 (dataset constants), so the data
+    side computes it once per calibration and caches it; the reference recomputes it every step behind a
+    ``.cpu()`` sync.  Uses the reference's own rasteriser (cv2.fillConvexPoly) for bit-equal masks.
+    """
+    import cv2
+
+    K3 = np.asarray(K3, dtype=np.float32)[:3, :3]
+    Tr = np.asarray(Tr, dtype=np.float32)
+    h = np.float32(0.33 if split == "argo" else 1.73)
+    tcol = Tr[:3, 2] * (-h) + Tr[:3, 3]
+    img_H_ground = (K3 @ np.stack([Tr[:3, 0], Tr[:3, 1], tcol], 1)).astype(np.float32)
+    s = np.float32(occ / 40.0)
+    shift = np.array([[s, 0, 0], [0, s, float(int(occ) // 2)], [0, 0, 1]], dtype=np.float32)
+    Minv = np.linalg.inv((shift @ np.linalg.inv(img_H_ground)).astype(np.float32)).astype(np.float32)
+    pts = np.asarray(static_quad_points(occ), dtype=np.float32)
+    ph = np.concatenate([pts, np.ones((4, 1), np.float32)], 1) @ Minv.T
+    proj = np.round(ph[:, :2] / ph[:, 2:3]).astype(np.int32)
+    poly = np.array([proj[0], proj[2], proj[3], proj[1]], dtype=np.int32).reshape(-1, 1, 2)
+    canvas = np.zeros((height, width, 3), dtype=np.uint8)
+    canvas = cv2.fillConvexPoly(canvas, poly, (0, 255, 255), 1)
+    return (cv2.cvtColor(canvas, cv2.COLOR_RGB2GRAY) > 0).astype(np.uint8)
+
+
+@MONO.register_module
+class Baseline(nn.Module):
+    def __init__(self, options):
+        super().__init__()
+        self.opt = _Opt(options)
+        o = self.opt
+        self.num_input_frames = len(o.frame_ids)
+        self.DepthEncoder = DepthEncoder(o.depth_num_layers, o.get("depth_pretrained_path"))
+        self.DepthDecoder = DepthDecoder(self.DepthEncoder.num_ch_enc)
+        self.PoseEncoder = PoseEncoder(o.pose_num_layers, o.get("pose_pretrained_path"), num_input_images=2)
+        self.PoseDecoder = PoseDecoder(self.PoseEncoder.num_ch_enc)
+        self.LayoutEncoder = Encoder(o.depth_num_layers, True)
+        enc_ch = self.LayoutEncoder.resnet_encoder.num_ch_enc
+        self.CycledViewProjection = CycledViewProjection(in_dim=o.occ_map_size // 32)
+        self.CrossViewTransformer = CrossViewTransformer(128)
+        self.LayoutDecoder = Decoder(enc_ch, o.num_class)
+        self.LayoutTransformDecoder = Decoder(enc_ch, o.num_class, "transform_decoder")
+        self.CycledViewProjectionB = CycledViewProjection(in_dim=o.occ_map_size // 32)
+        self.CrossViewTransformerB = CrossViewTransformer(128)
+        self.LayoutDecoderB = Decoder(enc_ch, o.num_class)
+        self.LayoutTransformDecoderB = Decoder(enc_ch, o.num_class, "transform_decoder")
+        self.weight = {"static": o.static_weight, "dynamic": o.dynamic_weight}
+        # knobs that do not exist in the reference configs (defaults reproduce the reference)
+        self.warp_align_corners = bool(o.get("warp_align_corners", True))
+        self.bn_double_update = bool(o.get("bn_double_update", True))
+        self.debug_outputs = bool(o.get("debug_outputs", True))   # ("color",f,s) / ("min_index",s) in outputs
+        self.noise_scale = float(o.get("automask_noise", 1e-5))
+        self.noise_override = None   # tests: {scale: [B,H,W tensors]}
+        self.scale_label_override = None   # tests: inject a label (the Argo_both label is ill-conditioned)
+        self._step = 0
+        self._quad_cache = {}
+        if self.bn_double_update:   # second running-stat update of the reference's duplicated road-head pass
+            for m in (self.LayoutEncoder, self.LayoutDecoder, self.LayoutTransformDecoder):
+                for bn in m.modules():
+                    if isinstance(bn, BNP):
+                        bn.stat_updates = 2
+
+    # ------------------------------------------------------------------------------------ forward
+    def forward(self, inputs):
+        o = self.opt
+        if not inputs[("color_aug", 0, 0)].is_cuda and not JF._lib.is_emulated():
+            raise JF._lib.JpbError("Baseline.forward needs CUDA tensors: jperceiver_b200 has no CPU path")
+        JF._lib.lib()  # fail loudly if the CUDA library is missing
+        depth_feature = self.DepthEncoder(inputs[("color_aug", 0, 0)])
+        outputs = dict(self.DepthDecoder(depth_feature))
+        if o["type"] != "static_eigen":
+            outputs.update(self.predict_layouts(inputs, depth_feature))
+        if self.training:
+            outputs.update(self.predict_poses(inputs))
+            loss_dict = self.compute_losses(inputs, outputs)
+            self._step += 1
+            return outputs, loss_dict
+        return outputs
+
+    def predict_poses(self, inputs):
+        outputs = {}
+        fids = list(self.opt.frame_ids)
+        for f in fids[1:]:
+            if f == "s":
+                continue
+            pair = [inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]] if f < 0 else \
+                   [inputs[("color_aug", 0, 0)], inputs[("color_aug", f, 0)]]
+            feats = self.PoseEncoder(pair, (192, 640))
+            raw = self.PoseDecoder.features(feats)
+            outputs[("cam_T_cam", 0, f)] = ops.pose_head(raw, invert=(f < 0))
+        return outputs
+
+    def _head(self, feat, l4, sfx, car):
+        cvp = getattr(self, "CycledViewProjection" + sfx)
+        cvt = getattr(self, "CrossViewTransformer" + sfx)
+        tf, rtf = cvp(feat)
+        fused, S, attn = cvt(feat, tf, rtf, l4)
+        out = {"topview" + sfx: getattr(self, "LayoutDecoder" + sfx)(fused),
+               "transform_topview" + sfx: getattr(self, "LayoutTransformDecoder" + sfx)(tf)}
+        out["features" + sfx] = out["features_" + car] = fused
+        out["transform_feature_" + car] = tf
+        out["retransform_features" + sfx] = out["retransform_features_" + car] = rtf
+        out["cv_attn_" + car] = S
+        out["cm_attn_" + car] = attn
+        return out
+
+    def predict_layouts(self, inputs, depth_feature):
+        occ = self.opt.occ_map_size
+        l4 = ops.resize_bilinear(depth_feature[-1], (occ // 8, occ // 8))
+        feat = self.LayoutEncoder(inputs[("color_aug", 0, 0)], (4 * occ, 4 * occ))
+        outputs = {"origin_features": feat}
+        outputs.update(self._head(feat, l4, "", "road"))
+        outputs.update(self._head(feat, l4, "B", "car"))
+        return outputs
+
+    # ------------------------------------------------------------------------------------ losses
+    def _quad_mask(self, inputs, height, width):
+        o = self.opt
+        quad = inputs.get(("scale_quad_mask", 0, 0))
+        if quad is not None:
+            return quad
+        K, Tr = inputs[("odometry_K", 0, 0)], inputs[("Tr_cam2_velo", 0, 0)]
+        hK, hT = inputs.get(("_host", "odometry_K")), inputs.get(("_host", "Tr_cam2_velo"))
+        if hK is None or hT is None:   # device-only inputs: one small D2H of sample 0's calibration
+            hK, hT = K[0].detach().cpu(), Tr[0].detach().cpu()
+        else:
+            hK, hT = hK[0], hT[0]
+        key = (hK.numpy().tobytes(), hT.numpy().tobytes(), height, width)
+        if key not in self._quad_cache:
+            m = static_quad_mask_host(hK.numpy(), hT.numpy(), o.split, o.occ_map_size, height, width)
+            self._quad_cache = {key: torch.from_numpy(m).to(K.device)}
+        return self._quad_cache[key]
+
+    def get_scale_label(self, inputs):
+        o = self.opt
+        height, width = inputs[("color", 0, -1)].shape[2:4]
+        if o["type"] == "Argo_both":
+            return JF.scale_label(inputs[("both_dynamic", 0, 0)], inputs[("odometry_K", 0, 0)], inputs[("Tr_cam2_velo", 0, 0)],
+                                  (height, width), split=o.split, mode="both", align_corners=self.warp_align_corners)
+        return JF.scale_label(inputs[("bothS", 0, 0)], inputs[("odometry_K", 0, 0)], inputs[("Tr_cam2_velo", 0, 0)],
+                              (height, width), split=o.split, mode="static", quad=self._quad_mask(inputs, height, width),
+                              align_corners=self.warp_align_corners)
+
+    def compute_losses(self, inputs, outputs):
+        o = self.opt
+        typ = o["type"]
+        L = {}
+        lw, l2w = o.loss_weight, o.loss2_weight
+        lwS, l2wS = o.get("loss_weightS", lw), o.get("loss2_weightS", l2w)
+        if o.get("loss_type", "iou") != "iou" or o.get("loss2_type", "boundary") != "boundary" or o.get("loss_sum", 3) != 3:
+            if typ != "static_eigen":
+                raise NotImplementedError("BEV loss variant (%s, %s, loss_sum=%s) is not implemented yet; the B200 path covers "
+                                          "iou + CE + boundary (loss_sum=3), which all five target configs use"
+                                          % (o.get("loss_type"), o.get("loss2_type"), o.get("loss_sum")))
+        if typ in ROAD_TYPES:
+            y = inputs[("bothS", 0, 0)]
+            sdf = JF.signed_distance(y.reshape(y.shape[0], y.shape[-2], y.shape[-1]))
+            L["topview_loss"] = JF.bev_head_loss(outputs["topview"], y, sdf, o.static_weight, lwS, l2wS)
+            L["transform_topview_loss"] = JF.bev_head_loss(outputs["transform_topview"], y, sdf, o.static_weight, lwS, l2wS)
+            L["transform_loss"] = JF.l1_mean(outputs["features"], outputs["retransform_features"])
+            L["layout_loss"] = L["topview_loss"] + 0.001 * L["transform_loss"] + L["transform_topview_loss"]
+        if typ in CAR_TYPES:
+            y = inputs[("bothD", 0, 0)]
+            sdf = JF.signed_distance(y.reshape(y.shape[0], y.shape[-2], y.shape[-1]))
+            L["topview_lossB"] = JF.bev_head_loss(outputs["topviewB"], y, sdf, o.dynamic_weight, lw, l2w)
+            L["transform_topview_lossB"] = JF.bev_head_loss(outputs["transform_topviewB"], y, sdf, o.dynamic_weight, lw, l2w)
+            L["transform_lossB"] = JF.l1_mean(outputs["featuresB"], outputs["retransform_featuresB"])
+            L["layout_lossB"] = L["topview_lossB"] + 0.001 * L["transform_lossB"] + L["transform_topview_lossB"]
+        label = None
+        if typ in LABEL_TYPES:
+            label = self.get_scale_label(inputs) if self.scale_label_override is None else self.scale_label_override
+            outputs["scale_label"] = label
+        fids = [f for f in o.frame_ids[1:] if f != "s"]
+        scales = list(o.scales)
+        nsc = len(scales)
+        target = inputs[("color", 0, 0)]
+        sources = [inputs[("color", f, 0)] for f in fids]
+        poses = [outputs[("cam_T_cam", 0, f)] for f in fids]
+        pyramid = JF.area_pyramid(target, max(scales) + 1)
+        for s in scales:
+            disp = outputs[("disp", 0, s)]
+            noise = self.noise_override[s] if self.noise_override is not None else None
+            loss, winner, min_index, warped = JF.photometric_loss(
+                disp, target, sources, poses, inputs[("K", 0)], inputs[("inv_K", 0)], num_scales=nsc, automask=o.automask,
+                min_depth=o.min_depth, max_depth=o.max_depth, noise=noise, noise_scale=self.noise_scale,
+                seed=int(o.get("seed", 1024)), stream=self._step * 16 + 4 * s, debug_outputs=self.debug_outputs)
+            L[("min_reconstruct_loss", s)] = loss
+            if self.debug_outputs:
+                lo, hi = 1.0 / o.max_depth, 1.0 / o.min_depth
+                outputs[("depth", 0, s)] = 1.0 / (lo + (hi - lo) * disp.detach())
+                outputs[("min_index", s)] = min_index
+                for f, wimg in zip(fids, warped):
+                    outputs[("color", f, s)] = wimg
+            if label is not None:
+                L[("scale_loss", s)] = JF.scale_loss(disp, label, o.scale_weight / (2 ** s) / nsc, crop=(typ == "static_raw"),
+                                                     min_depth=o.min_depth, max_depth=o.max_depth)
+            L[("smooth_loss", s)] = JF.smooth_loss(disp, pyramid[s], o.smoothness_weight / (2 ** s) / nsc, o.disp_norm)
+        return L
+
+    def depth_outputs(self, outputs):
+        """``outputs[("depth",0,s)]`` on demand (the reference materialises them inside compute_losses)."""
+        for s in self.opt.scales:
+            d = outputs[("disp", 0, s)]
+            lo, hi = 1.0 / self.opt.max_depth, 1.0 / self.opt.min_depth
+            outputs[("depth", 0, s)] = 1.0 / (lo + (hi - lo) * d)
+        return outputs

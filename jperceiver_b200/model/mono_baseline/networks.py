@@ -88,28 +88,24 @@ class _CRP(nn.Module):
             setattr(self, "%d_pointwise" % (i + 1), Wrap(ConvP(planes, planes, 1, bias=False)))
         self.n_stages = stages
 
-    def forward(self, x):
-        top = x
-        for i in range(self.n_stages):
-            top = ops.maxpool(top, 5, 1, 2)
-            top = x = ops.conv2d(top, getattr(self, "%d_pointwise" % (i + 1)).conv.weight, residual=x)
-            # note: ``x = top + x`` and the next stage pools ``top`` (the conv output *before* the add)
-            top = None
-        return x
-
 
 class DepthDecoder(nn.Module):
     def __init__(self, num_ch_enc):
         super().__init__()
         bott = 256
+        # attribute order = the reference's registration order (depth_decoder.py:15-41): it fixes the
+        # parameter order, hence the optimizer-state layout of interchangeable checkpoints
         self.reduce4 = Wrap(ConvP(int(num_ch_enc[4]), 512, 1, bias=False))
-        self.iconv4 = Wrap(ConvP(512, bott, 3))
         for lvl in (3, 2, 1):
             setattr(self, "reduce%d" % lvl, Wrap(ConvP(int(num_ch_enc[lvl]), bott, 1, bias=False)))
+        self.iconv4 = Wrap(ConvP(512, bott, 3))
+        for lvl in (3, 2, 1):
             setattr(self, "iconv%d" % lvl, Wrap(ConvP(2 * bott + 1, bott, 3)))
         for lvl in (4, 3, 2, 1):
             setattr(self, "crp%d" % lvl, nn.ModuleList([_CRP(bott)]))
+        for lvl in (4, 3, 2, 1):
             setattr(self, "merge%d" % lvl, Wrap(ConvP(bott, bott, 3)))
+        for lvl in (4, 3, 2, 1):
             setattr(self, "disp%d" % lvl, nn.ModuleList([Wrap(ConvP(bott, 1, 3))]))
         self.drop_p = 0.5
         self.drop_masks = None  # tests may inject (mask_l4, mask_l3)

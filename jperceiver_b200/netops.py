@@ -65,7 +65,11 @@ def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1
     running statistics in place, as nn.BatchNorm2d does."""
     _need_cuda(x)
     if training:
-        bn.num_batches_tracked += 1
+        # ``stat_updates`` = 2 on the road-head BNs reproduces the reference's duplicated forward pass
+        # (net.py:73-74): two momentum updates with the same batch statistics == one with 1-(1-m)^2.
+        k = getattr(bn, "stat_updates", 1)
+        bn.num_batches_tracked += k
+        momentum = 1.0 - (1.0 - momentum) ** k
     y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, momentum, eps)
     if residual is not None:
         y = y + residual

@@ -1,0 +1,142 @@
+"""Whole-model parity: ``jperceiver_b200.model.Baseline`` (forward + losses + backward through the C ABI)
+against the oracle port on identical weights, inputs, dropout masks and automask noise.
+
+``[emu]`` runs at a reduced size with the host emulation of the CUDA-core kernels (logic check, CPU);
+``[gpu]`` is the parity test proper at 320x1024 (the BASELINE.json shape) on cuda:0."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu import build_emulation  # noqa: E402
+from oracle import port as O  # noqa: E402
+from oracle.ref_loader import default_options  # noqa: E402
+
+from jperceiver_b200 import _lib  # noqa: E402
+from jperceiver_b200.model import MONO  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def dev(request):
+    _lib._handle, _lib._emulated = None, False
+    if request.param == "emu":
+        _lib.use_library(build_emulation(), emulated=True)
+        yield torch.device("cpu")
+    else:
+        assert torch.cuda.is_available()
+        _lib.lib()
+        yield torch.device("cuda:0")
+    _lib._handle, _lib._emulated = None, False
+
+
+def test_state_dict_layout_matches_reference():
+    model = MONO.module_dict["Baseline"](default_options())
+    shapes = json.load(open(os.path.join(GOLDEN, "state_dict_shapes.json")))
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())      # same keys in the same order
+    assert all(list(sd[k].shape) == shapes[k] for k in shapes)
+    assert sum(p.numel() for p in model.parameters()) == 53737194
+
+
+def run_case(dev, typ, H, W, occ, B, hw_full, fids=(0, -1, 1), rel=1e-3):
+    torch.set_num_threads(os.cpu_count() or 1)
+    split = "argo" if typ.startswith("Argo") else "odometry"
+    opt = default_options(type=typ, split=split, height=H, width=W, occ_map_size=occ, frame_ids=list(fids), imgs_per_gpu=B)
+    model = MONO.module_dict["Baseline"](opt)
+    P = O.synth_params(model.state_dict(), seed=5)
+    model.load_state_dict(P)
+    model.to(dev).train()
+    inp = O.synth_inputs(opt, B, seed=2, hw_full=hw_full)
+    if hw_full[0] < 300:   # reduced-size case: bring the projected BEV region inside the small full-res frame
+        oK = inp[("odometry_K", 0, 0)]
+        oK[:, 0, 0] *= 0.3
+        oK[:, 1, 1] *= 0.3
+        oK[:, 0, 2] = hw_full[1] / 2
+        oK[:, 1, 2] = hw_full[0] / 3
+    g = torch.Generator().manual_seed(9)
+    l4hw, l3hw = (H // 32, W // 32), (H // 16, W // 16)
+    masks = ((torch.rand(B, 512, *l4hw, generator=g) >= 0.5).float(), (torch.rand(B, 256, *l3hw, generator=g) >= 0.5).float())
+    nsrc = len(fids) - 1
+    noise = {s: [1e-5 * torch.randn(B, 1, H, W, generator=g) for _ in range(nsrc)] for s in range(4)}
+    # oracle
+    Po = {k: v.clone() for k, v in P.items()}
+    for k, v in Po.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    oo, ol = O.forward(Po, opt, {k: v.clone() for k, v in inp.items()}, training=True, drop_masks=masks, noise=noise)
+    ot = O.total_loss(ol)
+    ot.backward()
+    # product
+    model.DepthDecoder.drop_masks = tuple(m.to(dev) for m in masks)
+    model.noise_override = {s: [n[:, 0].to(dev) for n in noise[s]] for s in noise}
+    if typ == "Argo_both":
+        # ``mean(|g-p|/g)`` over ``g > 0`` divides by bilinear-blended label values as small as 1e-5 at the mask
+        # edge: the reference's own loss moves by ~1e-2 under fp32 re-association of the warp matrices.  The label is
+        # compared on its own (robust metrics) and then shared so that everything downstream is compared tightly.
+        mine = model.get_scale_label({k: v.to(dev) for k, v in inp.items()}).cpu()
+        ref = oo["scale_label"]
+        d = (mine - ref).abs()
+        assert (d > 2e-3).float().mean().item() < 2e-3 and d.mean().item() < 5e-5
+        model.scale_label_override = ref.to(dev)
+    po, pl = model({k: v.to(dev) for k, v in inp.items()})
+    pt = sum(v for v in pl.values())
+    pt.backward()
+    assert set(map(str, pl.keys())) == set(map(str, ol.keys()))
+    for k in ol:
+        a, b = float(pl[k]), float(ol[k])
+        assert abs(a - b) <= rel * max(abs(b), 1e-6), (k, a, b)
+    for k in oo:
+        if not torch.is_tensor(oo[k]) or k == "scale_label":
+            continue
+        a, b = po[k].detach().cpu(), oo[k].detach()
+        assert a.shape == b.shape, k
+        if b.dtype == torch.int64:
+            assert (a != b).float().mean().item() < 5e-3, k
+        else:
+            assert (a - b).abs().max().item() <= rel * max(b.abs().max().item(), 1e-6) * 5, k
+    named = dict(model.named_parameters())
+    worst = 0.0
+    gtot = float(torch.sqrt(sum((v.grad.double() ** 2).sum() for v in Po.values() if v.requires_grad and v.grad is not None)))
+    for k, p in named.items():
+        go = Po[k].grad
+        if go is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+            continue
+        # conv biases in front of a BatchNorm have an exactly-zero true gradient (pure rounding noise): absolute floor
+        diff = (p.grad.detach().cpu() - go).norm().item()
+        worst = max(worst, diff / (go.norm().item() + 1e-30))
+        assert diff <= max(20 * rel, 1e-2) * go.norm().item() + 2e-5 * gtot, (k, diff, go.norm().item(), gtot)   # arg-min / sign flips at near-ties move a few pixels' gradients
+    sd = model.state_dict()
+    for k in sd:
+        if "running" in k or "tracked" in k:
+            assert (sd[k].cpu().double() - Po[k].double()).abs().max().item() <= 1e-4 * max(1.0, Po[k].double().abs().max().item()), k
+    return worst
+
+
+def test_argo_both_small(dev):
+    if dev.type == "cuda":
+        pytest.skip("covered at full size in test_full_size_gpu")
+    run_case(dev, "Argo_both", 256, 256, 64, 2, (120, 400), rel=2e-4)
+
+
+def test_static_nonsquare_small(dev):
+    if dev.type == "cuda":
+        pytest.skip("covered at full size in test_full_size_gpu")
+    run_case(dev, "static", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("typ", ["static", "Argo_both", "static_raw"])
+def test_full_size_gpu(typ):
+    """BASELINE.json shape 320x1024 (non-square rule a-8), B=2, frames [0,-1,1]; tolerance 1e-3 relative on
+    every loss scalar (north star), 5e-3 of max-abs on output maps, 2e-2 relative L2 on parameter gradients
+    (conv math runs in TF32 on the GPU, the oracle in fp32)."""
+    _lib._handle, _lib._emulated = None, False
+    hw = (2056, 2464) if typ == "Argo_both" else (375, 1242)
+    run_case(torch.device("cuda:0"), typ, 320, 1024, 256, 2, hw, rel=1e-3)
