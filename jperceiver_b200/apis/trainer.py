@@ -1,0 +1,212 @@
+"""The training step: ``batch_processor`` (mono/apis/trainer.py:30-56) plus the optimizer hook
+(mono/core/utils/dist_utils.py:34-60) re-hosted on flat device buffers.
+
+Reference per iteration: every input ``.float().cuda()`` -> model -> sum of *all* loss_dict entries ->
+``.item()`` on each entry (~20 syncs) -> zero_grad -> backward (DDP bucket all-reduce) -> a second flat
+all-reduce of all gradients -> clip_grad_norm_(35) over 466 tensors -> Adam over 466 tensors.
+
+Here: parameters and gradients live in two flat fp32 buffers (views keep the per-tensor shapes and the
+channels-last weight layout); one NCCL all-reduce of the gradient buffer, one ``jpb_sumsq`` and one
+``jpb_adam_step`` launch (1/world scaling + clipping + Adam fused); all loss scalars travel to the host
+in one copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from .env import get_dist_info
+
+HOST_KEYS = ("odometry_K", "Tr_cam2_velo")
+
+
+def change_input_variable(data, device=None, non_blocking=True):
+    """Move a batch dict to the GPU as float32 (trainer.py:20-27).  Small calibration tensors keep a host
+    copy under ``("_host", name)`` so host-side caches (the static scale-label quad) need no D2H."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    out = {}
+    for k, v in data.items():
+        if isinstance(k, tuple) and k and k[0] == "bev_path":
+            out[k] = v
+            continue
+        if isinstance(k, tuple) and "kp" in k:
+            out[k] = v
+            continue
+        t = torch.as_tensor(v)
+        if isinstance(k, tuple) and k and k[0] in HOST_KEYS and not t.is_cuda:
+            out[("_host", k[0])] = t.float()
+        out[k] = t.to(device=device, dtype=torch.float32, non_blocking=non_blocking)
+    return out
+
+
+def loss_scalars(losses):
+    """Ordered names + one stacked device tensor [each entry..., total]; total = sum of ALL entries
+    (the layout terms are double-counted, exactly as trainer.py:44 does)."""
+    names, vals = [], []
+    for name, v in losses.items():
+        if isinstance(v, torch.Tensor):
+            vals.append(v.mean() if v.dim() else v)
+        elif isinstance(v, list):
+            vals.append(sum(x.mean() for x in v))
+        else:
+            raise TypeError("{} is not a tensor or list of tensors".format(name))
+        names.append(str(name))
+    total = vals[0]
+    for v in vals[1:]:
+        total = total + v
+    return names, vals, total
+
+
+def batch_processor(model, data, train_mode):
+    """Reference contract: returns dict(loss=tensor, log_vars=OrderedDict of floats, num_samples=int)."""
+    data = change_input_variable(data)
+    model_out, losses = model(data)
+    names, vals, total = loss_scalars(losses)
+    host = torch.stack([v.detach() for v in vals] + [total.detach()]).tolist()   # ONE device->host copy
+    log_vars = OrderedDict(zip(names + ["loss"], host))
+    return dict(loss=total, log_vars=log_vars, num_samples=len(data[("color", 0, 0)]))
+
+
+class FlatParameters:
+    """Re-home every parameter (and its gradient) of ``model`` as a view into one flat fp32 buffer."""
+
+    def __init__(self, model):
+        params = [p for p in model.parameters() if p.requires_grad]
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.numel = n
+        self.param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in params:
+            pv, gv = self._view(self.param, off, p), self._view(self.grad, off, p)
+            pv.copy_(p.data)
+            p.data = pv
+            p.grad = gv
+            self.views.append((off, p.numel()))
+            off += p.numel()
+        self.params = params
+
+    @staticmethod
+    def _view(flat, off, p):
+        sl = flat[off:off + p.numel()]
+        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+            o, i, h, w = p.shape
+            return sl.view(o, h, w, i).permute(0, 3, 1, 2)
+        return sl.view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, (off, n) in zip(self.params, self.views):   # autograd may have been told to drop .grad
+            if p.grad is None:
+                p.grad = self._view(self.grad, off, p)
+
+
+class FusedAdam:
+    """Adam on the flat buffers via ``jpb_sumsq`` + ``jpb_adam_step`` (clip + 1/world + update fused)."""
+
+    def __init__(self, flat, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=None):
+        self.flat = flat
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_norm = max_norm
+        dev = flat.param.device
+        self.exp_avg = torch.zeros_like(flat.param)
+        self.exp_avg_sq = torch.zeros_like(flat.param)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.normsq = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step(self, world_size=1):
+        f = self.flat
+        lib = _lib.lib()
+        st = _lib.stream_of(f.param)
+        a = _lib.AdamArgs()
+        a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay
+        a.grad_scale = 1.0 / world_size
+        a.max_norm = float(self.max_norm) if self.max_norm else 0.0
+        a.step = _lib.ptr(self.step_count)
+        if self.max_norm:
+            self.normsq.zero_()
+            _lib.check(lib.jpb_sumsq(_lib.ptr(f.grad), f.numel, _lib.ptr(self.normsq), st), "jpb_sumsq")
+            a.normsq = _lib.ptr(self.normsq)
+        _lib.check(lib.jpb_adam_step(_lib.ptr(f.param), _lib.ptr(f.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                     f.numel, C.byref(a), st), "jpb_adam_step")
+
+    def grad_norm(self, world_size=1):
+        """Host float of the (averaged) gradient norm of the last step — a sync; for logging/tests only."""
+        return float(self.normsq.sqrt().item()) / world_size
+
+
+def build_optimizer(model, optimizer_cfg, grad_clip=None):
+    """``build_optimizer`` of trainer.py:76-143 for the configs' ``dict(type='Adam', lr=..., weight_decay=0)``."""
+    cfg = dict(optimizer_cfg)
+    if cfg.pop("type", "Adam") != "Adam":
+        raise NotImplementedError("the B200 path implements the optimizer the reference configs use (Adam)")
+    if cfg.pop("paramwise_options", None) is not None:
+        raise NotImplementedError("paramwise_options are not used by the reference configs")
+    flat = getattr(model, "_jpb_flat", None)
+    if flat is None:
+        flat = model._jpb_flat = FlatParameters(model)
+    max_norm = None
+    if grad_clip:
+        if grad_clip.get("norm_type", 2) != 2:
+            raise NotImplementedError("only the L2 gradient-norm clip of the reference configs is implemented")
+        max_norm = grad_clip.get("max_norm")
+    return FusedAdam(flat, lr=cfg.get("lr", 1e-3), betas=tuple(cfg.get("betas", (0.9, 0.999))), eps=cfg.get("eps", 1e-8),
+                     weight_decay=cfg.get("weight_decay", 0.0), max_norm=max_norm)
+
+
+class TrainEngine:
+    """One object per process (= per GPU): forward, backward, gradient exchange, optimizer step."""
+
+    def __init__(self, model, optimizer_cfg=None, grad_clip=None):
+        self.model = model
+        self.optimizer = build_optimizer(model, optimizer_cfg or dict(type="Adam", lr=1e-4, weight_decay=0),
+                                         grad_clip if grad_clip is not None else dict(max_norm=35, norm_type=2))
+        self.flat = model._jpb_flat
+        self.rank, self.world = get_dist_info()
+        self.last_names = None
+
+    def exchange_gradients(self):
+        """The path's only collective: all-reduce(sum) of the flat gradient buffer (dist_utils.py:27);
+        the division by world size is fused into the optimizer kernel."""
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad)
+
+    def step(self, data, need_log=True):
+        """data: dict of device tensors (see ``change_input_variable``).  Returns the stacked loss tensor
+        ``[entries..., total]`` on the device (names in ``self.last_names``)."""
+        self.flat.zero_grad()
+        _, losses = self.model(data)
+        names, vals, total = loss_scalars(losses)
+        total.backward()
+        self.exchange_gradients()
+        self.optimizer.step(self.world)
+        self.last_names = names + ["loss"]
+        if need_log:
+            return torch.stack([v.detach() for v in vals] + [total.detach()])
+        return total.detach()
+
+
+def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=False, validate=False, logger=None):
+    """Training loop over an iterable of batch dicts (the reference drives mmcv's Runner here; the runner,
+    checkpoint and eval hooks are SURVEY.md §8(f) 'next').  ``dataset_train`` must yield collated batch dicts."""
+    import logging
+    logger = logger or logging.getLogger()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    model.to(dev).train()
+    engine = TrainEngine(model, cfg.optimizer, cfg.get("optimizer_config", {}).get("grad_clip"))
+    interval = cfg.get("log_config", {}).get("interval", 50)
+    it = 0
+    for epoch in range(cfg.get("total_epochs", 1)):
+        for batch in dataset_train:
+            out = engine.step(change_input_variable(batch, dev), need_log=(it % interval == 0))
+            if it % interval == 0:
+                vals = out.tolist()
+                logger.info("epoch %d iter %d %s", epoch, it, ", ".join("%s: %.5f" % kv for kv in zip(engine.last_names, vals)))
+            it += 1
+    return engine

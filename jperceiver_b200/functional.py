@@ -11,6 +11,32 @@ from . import _lib
 from ._lib import PhotoArgs, PhotoGrad, check, ptr, stream_of
 
 
+# ---- optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline figures) ----
+PROFILE_ON = False
+PROFILE: dict = {}
+
+
+def _launch(name, tensor, call):
+    """Run one C-ABI launch; when profiling, bracket it with CUDA events on the tensor's current stream."""
+    if PROFILE_ON and tensor.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = call()
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+        return status
+    return call()
+
+
+def profile_summary():
+    """{kernel: {launches, ms_per_launch, ms_total}} — call after a device synchronize."""
+    out = {}
+    for name, evs in PROFILE.items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        out[name] = {"launches": len(ms), "ms_per_launch": sum(ms) / len(ms), "ms_total": sum(ms)}
+    return out
+
+
 def _f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
@@ -70,7 +96,8 @@ class _Photometric(torch.autograd.Function):
                 w = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
                 warped.append(w)
                 a.warped[i] = ptr(w)
-        check(_lib.lib().jpb_photometric_fwd(C.byref(a), stream_of(target)), "jpb_photometric_fwd")
+        check(_launch("photometric_fwd", target, lambda: _lib.lib().jpb_photometric_fwd(C.byref(a), stream_of(target))),
+              "jpb_photometric_fwd")
         loss = finalize(acc, 1.0 / (B * H * W * cfg["num_scales"])).reshape(())
         ctx.cfg = cfg
         ctx.noises = noises
@@ -98,7 +125,8 @@ class _Photometric(torch.autograd.Function):
         g.grad_out, g.inv_count, g.winner, g.grad_disp = ptr(gl), 1.0 / (B * H * W * cfg["num_scales"]), ptr(winner), ptr(gdisp)
         for i in range(F):
             g.grad_T[i] = ptr(gT[i])
-        check(_lib.lib().jpb_photometric_bwd(C.byref(a), C.byref(g), stream_of(target)), "jpb_photometric_bwd")
+        check(_launch("photometric_bwd", target, lambda: _lib.lib().jpb_photometric_bwd(C.byref(a), C.byref(g), stream_of(target))),
+              "jpb_photometric_bwd")
         n_extra = len(ctx.noises) if ctx.noises is not None else 0
         return (gdisp, None, None, None, None) + (None,) * F + tuple(gT) + (None,) * n_extra
 

@@ -1,0 +1,139 @@
+"""Host-side training logic: flat parameter/gradient buffers, the fused clip+Adam step against
+torch.optim.Adam + clip_grad_norm_, the reference's loss-summing contract, config loading, and the
+data-parallel gradient exchange on a 2-process gloo group (CPU, host emulation of the kernels)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu import build_emulation  # noqa: E402
+
+from jperceiver_b200 import _lib  # noqa: E402
+from jperceiver_b200.apis import Config, TrainEngine, build_optimizer  # noqa: E402
+from jperceiver_b200.apis.trainer import FlatParameters, loss_scalars  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulation():
+    _lib.use_library(build_emulation(), emulated=True)
+    yield
+    _lib._handle, _lib._emulated = None, False
+
+
+class Tiny(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 8, 3, padding=1, bias=False)   # a bias in front of BN has a pure-noise gradient, which Adam amplifies
+        self.conv.weight.data = self.conv.weight.data.contiguous(memory_format=torch.channels_last)
+        self.bn = nn.BatchNorm2d(8)
+        self.fc = nn.Linear(8, 4)
+        self.unused = nn.Linear(4, 4)   # never receives a gradient (like the ResNet fc / res_conv of the real model)
+
+    def forward(self, data):
+        x = data["x"]
+        y = self.fc(torch.relu(self.bn(self.conv(x))).mean((2, 3)))
+        return {"y": y}, {"a": (y ** 2).mean(), ("b", 0): y.abs().mean() * 0.5}
+
+
+def test_loss_sum_counts_every_entry():
+    names, vals, total = loss_scalars({"topview_loss": torch.tensor(2.0), "layout_loss": torch.tensor(3.0), ("smooth_loss", 0): torch.tensor(0.5)})
+    assert names == ["topview_loss", "layout_loss", "('smooth_loss', 0)"] and total.item() == 5.5
+    with pytest.raises(TypeError):
+        loss_scalars({"bad": 1.0})
+
+
+def test_flat_views_keep_layout_and_values():
+    m = Tiny()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = FlatParameters(m)
+    assert flat.numel == sum(p.numel() for p in m.parameters())
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])
+    assert m.conv.weight.is_contiguous(memory_format=torch.channels_last)
+    assert m.conv.weight.data_ptr() == flat.param.data_ptr()
+    flat.param.zero_()
+    assert m.fc.weight.abs().sum().item() == 0.0
+
+
+@pytest.mark.parametrize("max_norm", [None, 0.05])
+def test_fused_adam_matches_torch(max_norm):
+    torch.manual_seed(0)
+    a, b = Tiny(), Tiny()
+    b.load_state_dict(a.state_dict())
+    opt_ref = torch.optim.Adam(a.parameters(), lr=1e-2, weight_decay=0)
+    eng = TrainEngine(b, dict(type="Adam", lr=1e-2, weight_decay=0), dict(max_norm=max_norm, norm_type=2) if max_norm else {})
+    for it in range(4):
+        x = torch.randn(4, 3, 8, 8, generator=torch.Generator().manual_seed(it))
+        opt_ref.zero_grad()
+        _, la = a({"x": x})
+        sum(la.values()).backward()
+        if max_norm:
+            torch.nn.utils.clip_grad_norm_(a.parameters(), max_norm)
+        opt_ref.step()
+        eng.step({"x": x})
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert (pa - pb).abs().max().item() <= 2e-6 + 1e-5 * pa.abs().max().item(), k
+    assert int(eng.optimizer.step_count.item()) == 4
+
+
+def test_reference_configs_load_unchanged():
+    cfg_dir = "/root/reference/config"
+    if not os.path.isdir(cfg_dir):
+        pytest.skip("reference tree not present")
+    for name in ("cfg_kitti_baseline_odometry_boundary_ce_iou_1024_20_B1", "cfg_kitti_baseline_odometry_boundary_ce_iou_1024_20",
+                 "cfg_kitti_baseline_raw_boundary_ce_iou_1024_20", "cfg_kitti_baseline_argo_both_boundary_ce_iou_1024_20_B1",
+                 "cfg_kitti_baseline_kitti_odom_8pugsB24_lr1e-4_ce_eigen"):
+        cfg = Config.fromfile(os.path.join(cfg_dir, name + ".py"))
+        assert cfg.model.name == "Baseline" and cfg.model["type"] == cfg.model.type
+        assert cfg.optimizer.type == "Adam" and cfg.optimizer_config.grad_clip.max_norm == 35
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import build_emulation as be
+    _lib.use_library(be(), emulated=True)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = Tiny()
+    eng = TrainEngine(m, dict(type="Adam", lr=1e-2, weight_decay=0), dict(max_norm=35, norm_type=2))
+    x = torch.randn(4, 3, 8, 8, generator=torch.Generator().manual_seed(100 + rank))
+    # expected: average over ranks of the single-process gradients (BN statistics stay per-rank)
+    eng.flat.zero_grad()
+    _, l = m({"x": x})
+    sum(l.values()).backward()
+    local = eng.flat.grad.clone()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    expect = sum(gathered) / world
+    eng.exchange_gradients()
+    got = eng.flat.grad / world
+    ok_grad = bool((got - expect).abs().max().item() < 1e-6)
+    eng.step({"x": x})
+    params = eng.flat.param.clone()
+    allp = [torch.zeros_like(params) for _ in range(world)]
+    dist.all_gather(allp, params)
+    ok_sync = bool(all(torch.equal(allp[0], p) for p in allp))
+    q.put((rank, ok_grad, ok_sync))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] for r in res), res
