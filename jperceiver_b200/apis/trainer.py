@@ -77,9 +77,10 @@ class FlatParameters:
     def __init__(self, model):
         params = [p for p in model.parameters() if p.requires_grad]
         dev = params[0].device
-        n = sum(p.numel() for p in params)
+        # every tensor starts on a 256-byte boundary: TMA / cp.async / vectorised loads need >= 16-byte alignment
+        n = sum(self._padded(p.numel()) for p in params)
         self.numel = n
-        self.param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views = []
         off = 0
@@ -89,8 +90,14 @@ class FlatParameters:
             p.data = pv
             p.grad = gv
             self.views.append((off, p.numel()))
-            off += p.numel()
+            off += self._padded(p.numel())
         self.params = params
+
+    ALIGN = 64  # floats
+
+    @classmethod
+    def _padded(cls, n):
+        return (n + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
 
     @staticmethod
     def _view(flat, off, p):

@@ -139,4 +139,14 @@ def test_full_size_gpu(typ):
     (conv math runs in TF32 on the GPU, the oracle in fp32)."""
     _lib._handle, _lib._emulated = None, False
     hw = (2056, 2464) if typ == "Argo_both" else (375, 1242)
-    run_case(torch.device("cuda:0"), typ, 320, 1024, 256, 2, hw, rel=1e-3)
+    # The network contains hard arg-max selections (CrossViewTransformer) and batch-statistics BatchNorm over as
+    # few as 128 values: TF32 rounding in a convolution can flip a selection, which is a discontinuous change of
+    # every downstream value (the reference's own GPU run differs from its CPU run the same way).  Whole-model
+    # parity is therefore taken with library convolutions held to true fp32; the tensor-core convolution kernels
+    # are compared layer by layer (tests/test_conv.py) at a TF32-appropriate tolerance.
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        run_case(torch.device("cuda:0"), typ, 320, 1024, 256, 2, hw, rel=1e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
