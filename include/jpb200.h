@@ -134,6 +134,35 @@ int jpb_bev_loss_bwd(const JpbBevArgs* args, const float* grad_out, float* grad_
 int jpb_l1_mean_fwd(const float* x, const float* y, long long n, double* acc /* [1] += */, void* stream);
 int jpb_l1_mean_bwd(const float* x, const float* y, long long n, const float* grad_out, float* gx, float* gy, void* stream);
 
+/* ---- implicit-GEMM convolution on tcgen05 tensor cores (TF32 in, FP32 accumulate in TMEM) ------------
+ * Replaces nn.Conv2d plus the passes the reference runs in front of / behind it as separate kernels:
+ * ReflectionPad2d/ZeroPad2d (layers.py:156-167), nearest 2x up-sampling (layers.py:110), torch.cat of up to
+ * three sources (depth_decoder.py:76,96,115), bias, residual add (layers.py:197) and the activation
+ * (F.leaky_relu depth_decoder.py:60, ReLU, sigmoid depth_decoder.py:35-38).
+ * Activations are NHWC fp32.  K is walked in 16-byte chunks described by `table` (4 ints per chunk:
+ * {source index or -1, dy<<16 | (dx & 0xffff), channel offset, valid bytes}); 8 chunks = one 32-float K block.
+ * `weight` is the K-major matrix [N][w_row] whose first w_cols columns follow the same chunk order.      */
+#define JPB_CONV_MAX_SRC 3
+typedef struct JpbConvArgs {
+  const float* src[JPB_CONV_MAX_SRC];   /* [B, H_i, W_i, C_i] */
+  int src_C[JPB_CONV_MAX_SRC], src_H[JPB_CONV_MAX_SRC], src_W[JPB_CONV_MAX_SRC];
+  int src_up[JPB_CONV_MAX_SRC];         /* 1: source is read through a nearest 2x up-sampling */
+  int nsrc;
+  int B, Hin, Win;                      /* logical input extent (after up-sampling) */
+  int Ho, Wo, N;                        /* output extent and channels */
+  int stride, pad, reflect;
+  const float* weight;                  /* [N][w_row], 16-byte aligned, w_row % 4 == 0 */
+  long long w_row;
+  int w_cols;
+  const int* table;                     /* [nkb*8][4] */
+  int nkb;                              /* number of 32-float K blocks */
+  const float* bias;                    /* [N] or NULL */
+  const float* residual;                /* [B,Ho,Wo,N] or NULL, added before the activation */
+  int act;                              /* 0 none, 1 ReLU, 2 LeakyReLU(0.01), 3 sigmoid */
+  float* out;                           /* [B,Ho,Wo,N] */
+} JpbConvArgs;
+int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
+
 /* ---- flat-buffer optimizer step (mono/core/utils/dist_utils.py:34-60 + torch.optim.Adam) ---------
  * jpb_sumsq: acc[0] += sum g^2 (run on the all-reduced SUM of gradients).
  * jpb_adam_step: g_eff = g * grad_scale (1/world) * min(1, max_norm / (sqrt(normsq)*grad_scale + 1e-6));

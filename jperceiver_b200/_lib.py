@@ -71,9 +71,22 @@ class BevArgs(C.Structure):
     ]
 
 
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 3), ("src_C", C.c_int * 3), ("src_H", C.c_int * 3), ("src_W", C.c_int * 3), ("src_up", C.c_int * 3),
+        ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
+        ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("weight", C.c_void_p), ("w_row", C.c_longlong),
+        ("w_cols", C.c_int), ("table", C.c_void_p), ("nkb", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("act", C.c_int), ("out", C.c_void_p),
+    ]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("grad_scale", C.c_float), ("max_norm", C.c_float), ("normsq", C.c_void_p), ("step", C.c_void_p)]
+
+
+EMU_MISSING = ("jpb_conv2d_fwd",)   # tcgen05/TMA entry points do not exist in the host-emulation build
 
 
 def _declare(h):
@@ -81,6 +94,8 @@ def _declare(h):
     h.jpb_build_info.restype = C.c_char_p
     for name in dir(_Signatures):
         if name.startswith("jpb_"):
+            if not hasattr(h, name) and name in EMU_MISSING:
+                continue
             fn = getattr(h, name)
             fn.restype = C.c_int
             fn.argtypes = getattr(_Signatures, name)
@@ -104,6 +119,7 @@ class _Signatures:
     jpb_l1_mean_fwd = [P, P, C.c_longlong, P, V]
     jpb_l1_mean_bwd = [P, P, C.c_longlong, P, P, P, V]
     jpb_sumsq = [P, C.c_longlong, P, V]
+    jpb_conv2d_fwd = [C.POINTER(ConvArgs), V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
 
 

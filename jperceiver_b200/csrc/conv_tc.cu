@@ -1,0 +1,356 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05, TF32 x TF32 -> FP32 in TMEM).
+//
+//   D[M = B*Ho*Wo, N = Cout] = A[M, K] * W[N, K]^T,   K = taps x (padded) input channels
+//
+// A is never materialised: 128 producer threads gather it 16 bytes (4 channels) at a time with
+// cp.async straight into the 128-byte-swizzled K-major shared-memory layout that tcgen05.mma reads.
+// The gather folds everything the reference does as separate full-tensor passes in front of a conv:
+//   * ReflectionPad2d / zero padding                      (layers.py:156-167, layout_model.py:31-47)
+//   * nearest 2x up-sampling  F.interpolate(scale_factor=2) (layers.py:110, layout_model.py:50-53)
+//   * channel concatenation   torch.cat((reduce, up, disp),1) (depth_decoder.py:76,96,115)
+//   * stride-2 sampling
+// through a small per-convolution chunk table (one int4 per 16-byte chunk of K: source tensor, tap
+// offset, channel offset, valid bytes).  W tiles arrive by TMA (cp.async.bulk.tensor, 128B swizzle)
+// from the K-major weight matrix (the channels-last nn.Conv2d weight as it sits in the flat parameter
+// buffer, or a packed copy when Cin is not a multiple of 4).  One elected thread issues
+// tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8 per instruction, 4 per 32-float K block) into
+// a TMEM accumulator; stages are recycled with tcgen05.commit -> mbarrier.  The epilogue reads TMEM with
+// tcgen05.ld (32 lanes x 32 columns per warp) and fuses bias, residual add and LeakyReLU/ReLU/sigmoid
+// before the only global write of the layer.
+//
+// Warp roles (192 threads): warps 0-3 gather A, then run the epilogue (warp w owns TMEM lanes 32w..32w+31);
+// warp 4 allocates TMEM and drives the weight TMA; warp 5 issues the MMAs.
+#include "jpb_common.cuh"
+#include "../../include/jpb200.h"
+
+#ifndef JPB_HOST_EMU
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128;          // output pixels per CTA (UMMA M)
+constexpr int BK = 32;           // floats per K block = one 128-byte swizzle row
+constexpr int A_STAGE = BM * BK * 4;   // 16 KB
+constexpr int NPROD = 128;       // A producer threads (warps 0-3)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct SrcDev {
+  const float* ptr;
+  int C, H, W, up;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return v > 0.f ? v : 0.f;
+  if (act == 2) return v > 0.f ? v : 0.01f * v;
+  if (act == 3) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+// NT: N tile (UMMA N), multiple of 16 in [16,256].  STAGES: smem pipeline depth.
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap wmap, JpbConvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [STAGES][A 16KB][B NT*128] | barriers | tmem ptr | src table
+  constexpr int B_STAGE = NT * BK * 4;
+  constexpr int STAGE = A_STAGE + B_STAGE;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  SrcDev* srcs = reinterpret_cast<SrcDev*>(tmem_slot + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = a.B * a.Ho * a.Wo;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT;
+  const int nkb = a.nkb;
+
+  if (tid < a.nsrc) {
+    srcs[tid].ptr = a.src[tid];
+    srcs[tid].C = a.src_C[tid]; srcs[tid].H = a.src_H[tid]; srcs[tid].W = a.src_W[tid]; srcs[tid].up = a.src_up[tid];
+  }
+  if (tid == 160) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD + 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {   // TMEM allocation (power of two >= 32 columns), owned by warp 4
+    constexpr uint32_t cols = NT < 32 ? 32 : NT;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================================================== A gather (producers)
+    const int c = tid & 7;           // 16-byte chunk column inside the 128-byte K row
+    const int rbase = tid >> 3;      // rows rbase + 16*i
+    int iy0[8], ix0[8], bb[8];
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rbase + 16 * i;
+      if (m < M) {
+        const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
+        const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
+        bb[i] = b; iy0[i] = oy * a.stride - a.pad; ix0[i] = ox * a.stride - a.pad;
+      } else {
+        bb[i] = -1; iy0[i] = 0; ix0[i] = 0;
+      }
+    }
+    const uint32_t swz = (uint32_t)((c ^ (rbase & 7)) << 4) + (uint32_t)(rbase & 7) * 128u + (uint32_t)(rbase >> 3) * 1024u;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + kb * 8 + c);   // x: source (-1 none), y: dy<<16 | (dx & 0xffff), z: channel offset, w: valid bytes
+      const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
+      if (e.x < 0 || e.w == 16) {
+        const SrcDev sd = srcs[e.x < 0 ? 0 : e.x];
+        const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
+        for (int i = 0; i < 8; ++i) {
+          int iy = iy0[i] + dy, ix = ix0[i] + dx;
+          bool ok = bb[i] >= 0 && e.x >= 0;
+          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+          else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+          if (!ok) { iy = 0; ix = 0; }
+          if (sd.up) { iy >>= 1; ix >>= 1; }
+          const float* g = sd.ptr + ((size_t)((ok ? bb[i] : 0) * sd.H + iy) * sd.W + ix) * sd.C + e.z;
+          cp_async16(sbase + (uint32_t)i * 2048u, g, ok ? 16u : 0u);
+        }
+      } else {
+        // partial chunk (a source whose channel count is not a multiple of 4, e.g. the 1-channel disparity):
+        // synchronous scalar loads, zero padded
+        const SrcDev sd = srcs[e.x];
+        const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
+        const int nval = e.w >> 2;
+        for (int i = 0; i < 8; ++i) {
+          int iy = iy0[i] + dy, ix = ix0[i] + dx;
+          bool ok = bb[i] >= 0;
+          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+          else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            if (sd.up) { iy >>= 1; ix >>= 1; }
+            const float* g = sd.ptr + ((size_t)(bb[i] * sd.H + iy) * sd.W + ix) * sd.C + e.z;
+            v.x = g[0];
+            if (nval > 1) v.y = g[1];
+            if (nval > 2) v.z = g[2];
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + (uint32_t)i * 2048u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+      }
+      cp_async_commit();
+      // keep up to 2 K blocks of copies in flight per thread; publish the one before the previous
+      if (kb >= 2) {
+        cp_async_wait<2>();
+        fence_async_proxy();
+        mbar_arrive(&full_bar[(kb - 2) % STAGES]);
+      }
+    }
+    for (int kb = (nkb >= 2 ? nkb - 2 : 0); kb < nkb; ++kb) {
+      if (kb == nkb - 2) cp_async_wait<1>(); else cp_async_wait<0>();
+      fence_async_proxy();
+      mbar_arrive(&full_bar[kb % STAGES]);
+    }
+
+    // ===================================================== epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* out = a.out + (size_t)m * a.N + n0;
+    const float* res = a.residual ? a.residual + (size_t)m * a.N + n0 : nullptr;
+    for (int j = 0; j < NT; j += 16) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)j, v);   // warp-collective: every lane executes it, even for rows >= M
+      if (m < M) {
+        const int nleft = a.N - n0 - j;
+        if (nleft >= 16 && (a.N & 3) == 0) {
+          for (int q = 0; q < 16; q += 4) {
+            float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            if (a.bias) { const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + j + q); o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w; }
+            if (res) { const float4 rq = *reinterpret_cast<const float4*>(res + j + q); o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w; }
+            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+            *reinterpret_cast<float4*>(out + j + q) = o;
+          }
+        } else {
+          for (int q = 0; q < 16 && q < nleft; ++q) {
+            float o = v[q];
+            if (a.bias) o += a.bias[n0 + j + q];
+            if (res) o += res[j + q];
+            out[j + q] = apply_act(o, a.act);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================================================== weight TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
+        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else {
+    // ===================================================== MMA issuer
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
+    // both K-major, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t ad = umma_desc_sw128(smem_u32(smem + s * STAGE));
+        const uint64_t bd = umma_desc_sw128(smem_u32(smem + s * STAGE + A_STAGE));
+        for (int k = 0; k < BK / 8; ++k)   // 8 TF32 (32 bytes) per instruction: advance the start address by 2 x 16 B
+          umma_tf32(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (kb == nkb - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    constexpr uint32_t cols = NT < 32 ? 32 : NT;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <int NT, int STAGES>
+int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = true;
+  }
+  const int M = a->B * a->Ho * a->Wo;
+  dim3 grid((M + BM - 1) / BM, (a->N + NT - 1) / NT);
+  conv_tc_fwd_kernel<NT, STAGES><<<grid, 192, smem, st>>>(map, *a);
+  return jpb_status();
+}
+
+}  // namespace
+
+extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
+  if (!a || !a->weight || !a->table || !a->out || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nkb < 1) return JPB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(a->weight) & 15) || (a->w_row & 3)) return JPB_ERR_ARG;   // TMA: 16-byte aligned base and row pitch
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return JPB_ERR_UNSUPPORTED;
+  int nt = 16;
+  while (nt < a->N && nt < 256) nt <<= 1;
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a->w_cols, (cuuint64_t)a->N};
+  const cuuint64_t gstr[1] = {(cuuint64_t)a->w_row * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)nt};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->weight), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return JPB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nt) {
+    case 16: return launch_fwd<16, 6>(a, map, st);
+    case 32: return launch_fwd<32, 6>(a, map, st);
+    case 64: return launch_fwd<64, 6>(a, map, st);
+    case 128: return launch_fwd<128, 5>(a, map, st);
+    default: return launch_fwd<256, 4>(a, map, st);
+  }
+}
+
+#endif  // JPB_HOST_EMU

@@ -12,11 +12,12 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from . import conv as _conv
 
 CL = torch.channels_last
 
 BACKEND = {
-    "conv2d": "torch", "batchnorm": "torch", "maxpool": "torch", "dropout": "torch", "image_prep": "torch",
+    "conv2d": "jpb",   # forward: tcgen05 implicit GEMM (csrc/conv_tc.cu); backward: library (interim) "batchnorm": "torch", "maxpool": "torch", "dropout": "torch", "image_prep": "torch",
     "cvp_mlp": "torch", "cct_attention": "torch", "pose_head": "torch",
 }
 
@@ -49,15 +50,10 @@ def conv2d(inputs, weight, bias=None, *, stride=1, pad=0, reflect=False, act="no
     if not isinstance(inputs, (list, tuple)):
         inputs = [(inputs, False)]
     _need_cuda(inputs[0][0])
-    xs = [F.interpolate(t, scale_factor=2, mode="nearest") if up else t for t, up in inputs]
-    x = xs[0] if len(xs) == 1 else torch.cat(xs, 1)
-    if reflect and pad:
-        x = F.pad(x, (pad,) * 4, mode="reflect")
-        pad = 0
-    y = F.conv2d(x.contiguous(memory_format=CL), weight, bias, stride=stride, padding=pad)
-    if residual is not None:
-        y = y + residual
-    return _act(y, act)
+    xs, ups = [t for t, _ in inputs], [u for _, u in inputs]
+    if inputs[0][0].is_cuda and BACKEND["conv2d"] == "jpb":
+        return _conv.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual)
+    return _conv._torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual)   # host emulation (tests) / library mode
 
 
 def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1e-5):
@@ -102,6 +98,8 @@ def image_prep(images, out_hw=None):
             im = F.interpolate(im, list(out_hw), mode="bilinear", align_corners=False)
         outs.append((im - 0.45) / 0.225)
     x = outs[0] if len(outs) == 1 else torch.cat(outs, 1)
+    if x.shape[1] % 4:   # 3 -> 4 / 6 -> 8 zero channels: every pixel is a whole number of 16-byte gather chunks
+        x = F.pad(x, (0, 0, 0, 0, 0, 4 - x.shape[1] % 4))
     return x.contiguous(memory_format=CL)
 
 

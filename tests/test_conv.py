@@ -1,0 +1,67 @@
+"""Layer-by-layer parity of the tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu) with the fp32 library
+convolution on the shapes of SURVEY.md Appendix A (scaled down in batch/extent, same K/N structure).
+Tolerance: TF32 operands (10-bit mantissa, truncated) with fp32 accumulation -> 3e-3 of max|y|."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from jperceiver_b200 import _lib
+from jperceiver_b200 import conv as JC
+
+pytestmark = pytest.mark.gpu
+CL = torch.channels_last
+
+CASES = [
+    # name, sources [(C, H, W, up)], Cout, k, stride, pad, reflect, act, bias, residual
+    ("layer1 3x3 64->64", [(64, 40, 64, 0)], 64, 3, 1, 1, 0, "none", 0, 0),
+    ("layer2.0 3x3 s2 64->128", [(64, 40, 64, 0)], 128, 3, 2, 1, 0, "none", 0, 0),
+    ("downsample 1x1 s2 64->128", [(64, 40, 64, 0)], 128, 1, 2, 0, 0, "none", 0, 0),
+    ("layer3 3x3 256->256", [(256, 20, 32, 0)], 256, 3, 1, 1, 0, "none", 0, 0),
+    ("layer4 3x3 512->512 (two N tiles)", [(512, 10, 16, 0)], 512, 3, 1, 1, 0, "none", 0, 0),
+    ("stem 7x7 s2 (3->pad4)->64", [(4, 64, 96, 0)], 64, 7, 2, 3, 0, "none", 0, 0),
+    ("pose stem 7x7 s2 (6->pad8)->64", [(8, 48, 80, 0)], 64, 7, 2, 3, 0, "none", 0, 0),
+    ("reduce 1x1 128->256 no bias", [(128, 20, 64, 0)], 256, 1, 1, 0, 0, "none", 0, 0),
+    ("crp 1x1 256->256 + residual", [(256, 20, 64, 0)], 256, 1, 1, 0, 0, "none", 0, 1),
+    ("iconv4 refl 3x3 512->256 leaky", [(512, 10, 32, 0)], 256, 3, 1, 1, 1, "leaky", 1, 0),
+    ("iconv3 refl 3x3 cat(256, up256, 1)->256 leaky", [(256, 20, 64, 0), (256, 10, 32, 1), (1, 20, 64, 0)], 256, 3, 1, 1, 1, "leaky", 1, 0),
+    ("disp refl 3x3 up(256)->1 sigmoid", [(256, 20, 64, 1)], 1, 3, 1, 1, 1, "sigmoid", 1, 0),
+    ("pose conv3 1x1 256->6", [(256, 6, 20, 0)], 6, 1, 1, 0, 0, "none", 1, 0),
+    ("pose conv1 3x3 256->256 relu", [(256, 6, 20, 0)], 256, 3, 1, 1, 0, "relu", 1, 0),
+    ("layout dec 3x3 up(32)->32", [(32, 32, 32, 1)], 32, 3, 1, 1, 0, "none", 1, 0),
+    ("layout dec 3x3 16->16", [(16, 64, 64, 0)], 16, 3, 1, 1, 0, "none", 1, 0),
+    ("topview refl 3x3 16->2", [(16, 64, 64, 0)], 2, 3, 1, 1, 1, "none", 1, 0),
+    ("cvt f_conv 3x3 cat(128,128)->128", [(128, 8, 8, 0), (128, 8, 8, 0)], 128, 3, 1, 1, 0, "none", 1, 0),
+    ("query 1x1 128->16", [(128, 8, 8, 0)], 16, 1, 1, 0, 0, "none", 1, 0),
+    ("odd extent 3x3 64->64 (M not a multiple of 128)", [(64, 13, 19, 0)], 64, 3, 1, 1, 1, "none", 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_forward_matches_fp32_library(case):
+    name, srcs, cout, k, stride, pad, reflect, act, has_bias, has_res = case
+    _lib._handle, _lib._emulated = None, False
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(hash(name) % 1000)
+    B = 2
+    xs = [torch.randn(B, c, h, w, generator=g).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
+    ups = [bool(up) for *_, up in srcs]
+    cin_t = sum(c for c, *_ in srcs)
+    cin_w = {4: 3, 8: 6}.get(cin_t, cin_t) if k == 7 else cin_t
+    if k == 7:
+        xs[0][:, cin_w:] = 0
+    weight = (torch.randn(cout, cin_w, k, k, generator=g) / (cin_w * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
+    bias = torch.randn(cout, generator=g).to(dev) if has_bias else None
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref0 = JC._torch_conv(xs, ups, weight, bias, stride, pad, reflect, "none", None)
+        res = torch.randn(ref0.shape, generator=g).to(dev).contiguous(memory_format=CL) if has_res else None
+        ref = JC._torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, res)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    got = JC.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, res)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=CL)
+    err = (got - ref).abs().max().item()
+    scale = max(ref0.abs().max().item(), 1e-6)
+    assert err <= 3e-3 * scale, (name, err, scale)
