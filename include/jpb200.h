@@ -159,9 +159,40 @@ typedef struct JpbConvArgs {
   const float* bias;                    /* [N] or NULL */
   const float* residual;                /* [B,Ho,Wo,N] or NULL, added before the activation */
   int act;                              /* 0 none, 1 ReLU, 2 LeakyReLU(0.01), 3 sigmoid */
-  float* out;                           /* [B,Ho,Wo,N] */
+  float* out;                           /* [B,Ho,Wo,N] (scatter == 0) */
+  /* -- data-gradient use of the same kernel: sources = dY, weight = flipped/transposed W, N = Cin of the forward -- */
+  int in_div;                           /* 2: gather coordinate must be even and is halved (dgrad of a stride-2 conv) */
+  int nt;                               /* N tile override (0 = auto); scatter tiles must not straddle a destination */
+  int scatter;                          /* 1: fold the result back into the forward convolution's sources */
+  float* dst[JPB_CONV_MAX_SRC];         /* [B, H_j, W_j, C_j] gradient of forward source j (+=, zero-filled by the caller) */
+  int dst_C[JPB_CONV_MAX_SRC], dst_H[JPB_CONV_MAX_SRC], dst_W[JPB_CONV_MAX_SRC], dst_up[JPB_CONV_MAX_SRC];
+  int ndst;
+  int fold_pad, fold_reflect, fold_H, fold_W; /* output pixel (py,px) -> (py-fold_pad, px-fold_pad), reflected into fold_H x fold_W */
 } JpbConvArgs;
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
+
+/* weight gradient of the same operator: dw[n][k] (+)= sum_p im2col[p][k] * dy[p][n], k in the chunk order of `table`.
+ * dy is the gradient w.r.t. the pre-activation output, [B*Ho*Wo][N] with N % 4 == 0.  The pixel range is split over
+ * `splits` CTAs per tile; with splits > 1 results are accumulated atomically into a zero-filled dw.            */
+typedef struct JpbConvWgradArgs {
+  const float* src[JPB_CONV_MAX_SRC];
+  int src_C[JPB_CONV_MAX_SRC], src_H[JPB_CONV_MAX_SRC], src_W[JPB_CONV_MAX_SRC], src_up[JPB_CONV_MAX_SRC];
+  int nsrc;
+  int B, Hin, Win, Ho, Wo, N;
+  int stride, pad, reflect;
+  const int* table;
+  int nchunks;               /* rows of the table (multiple of 8) */
+  const float* dy;
+  float* dw;                 /* [N][w_row] */
+  long long w_row;
+  int w_cols;
+  int splits;
+} JpbConvWgradArgs;
+int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
+
+/* ---- backward of the convolution epilogue: dz = dy * act'(y) (act as in JpbConvArgs, from the OUTPUT y) and
+ * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */
+int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int C, int act, float* dbias, void* stream);
 
 /* ---- flat-buffer optimizer step (mono/core/utils/dist_utils.py:34-60 + torch.optim.Adam) ---------
  * jpb_sumsq: acc[0] += sum g^2 (run on the all-reduced SUM of gradients).

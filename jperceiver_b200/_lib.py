@@ -77,7 +77,18 @@ class ConvArgs(C.Structure):
         ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
         ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("weight", C.c_void_p), ("w_row", C.c_longlong),
         ("w_cols", C.c_int), ("table", C.c_void_p), ("nkb", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
-        ("act", C.c_int), ("out", C.c_void_p),
+        ("act", C.c_int), ("out", C.c_void_p), ("in_div", C.c_int), ("nt", C.c_int), ("scatter", C.c_int),
+        ("dst", C.c_void_p * 3), ("dst_C", C.c_int * 3), ("dst_H", C.c_int * 3), ("dst_W", C.c_int * 3), ("dst_up", C.c_int * 3),
+        ("ndst", C.c_int), ("fold_pad", C.c_int), ("fold_reflect", C.c_int), ("fold_H", C.c_int), ("fold_W", C.c_int),
+    ]
+
+
+class ConvWgradArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 3), ("src_C", C.c_int * 3), ("src_H", C.c_int * 3), ("src_W", C.c_int * 3), ("src_up", C.c_int * 3),
+        ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
+        ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("table", C.c_void_p), ("nchunks", C.c_int),
+        ("dy", C.c_void_p), ("dw", C.c_void_p), ("w_row", C.c_longlong), ("w_cols", C.c_int), ("splits", C.c_int),
     ]
 
 
@@ -86,7 +97,7 @@ class AdamArgs(C.Structure):
                 ("grad_scale", C.c_float), ("max_norm", C.c_float), ("normsq", C.c_void_p), ("step", C.c_void_p)]
 
 
-EMU_MISSING = ("jpb_conv2d_fwd",)   # tcgen05/TMA entry points do not exist in the host-emulation build
+EMU_MISSING = ("jpb_conv2d_fwd", "jpb_conv2d_wgrad")   # tcgen05/TMA entry points do not exist in the host-emulation build
 
 
 def _declare(h):
@@ -120,6 +131,8 @@ class _Signatures:
     jpb_l1_mean_bwd = [P, P, C.c_longlong, P, P, P, V]
     jpb_sumsq = [P, C.c_longlong, P, V]
     jpb_conv2d_fwd = [C.POINTER(ConvArgs), V]
+    jpb_conv2d_wgrad = [C.POINTER(ConvWgradArgs), V]
+    jpb_act_bwd = [P, P, P, C.c_longlong, I, I, P, V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
 
 

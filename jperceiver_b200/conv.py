@@ -1,9 +1,9 @@
 """Host side of the tcgen05 implicit-GEMM convolution (``csrc/conv_tc.cu``): the per-layer K-chunk table,
 weight packing for ragged channel counts, and the autograd binding.
 
-Backward status (round 1): the forward runs on the hand-written kernel; the backward of each convolution still
-calls the library (cuDNN through autograd on a re-materialised input).  dgrad / wgrad kernels are the next step
-(DESIGN.md §roadmap)."""
+Backward: ``jpb_act_bwd`` (epilogue backward + bias gradient) -> data gradient = the forward kernel run on dz with
+flipped/transposed weights and a scatter epilogue that undoes reflection padding / up-sampling / concatenation ->
+weight gradient = ``jpb_conv2d_wgrad`` (pixels are the GEMM reduction, MN-major operands, split over CTAs)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -16,6 +16,7 @@ from ._lib import check, ptr, stream_of
 
 CL = torch.channels_last
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3}
+BACKWARD = "jpb"   # "jpb": tcgen05 dgrad/wgrad kernels; "torch": library backward on a re-materialised input (debug)
 _TABLES: dict = {}
 
 
@@ -79,6 +80,134 @@ def _torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual):
     return y
 
 
+def _fill_sources(a, xs, ups):
+    for i, x in enumerate(xs):
+        a.src[i] = ptr(x)
+        a.src_C[i], a.src_H[i], a.src_W[i], a.src_up[i] = x.shape[1], x.shape[2], x.shape[3], int(ups[i])
+    a.nsrc = len(xs)
+
+
+def _cl(x):
+    return x if x.is_contiguous(memory_format=CL) else x.contiguous(memory_format=CL)
+
+
+def _launch(name, t, call):
+    from .functional import _launch as L
+    return L(name, t, call)
+
+
+def act_bwd(gy, y, act, want_bias):
+    """dz = gy * act'(y) [+ bias gradient] in one pass over NHWC data."""
+    gy = _cl(gy)
+    B, N, Ho, Wo = gy.shape
+    rows = B * Ho * Wo
+    need_dz = act != "none"
+    if not need_dz and not want_bias:
+        return gy, None
+    dz = torch.empty_like(gy, memory_format=CL) if need_dz else None
+    gb = torch.zeros(N, dtype=torch.float32, device=gy.device) if want_bias else None
+    check(_launch("act_bwd", gy, lambda: _lib.lib().jpb_act_bwd(ptr(gy), ptr(y) if need_dz else None, ptr(dz), rows, N, ACT[act],
+                                                                 ptr(gb), stream_of(gy))), "jpb_act_bwd")
+    return (dz if need_dz else gy), gb
+
+
+def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
+    """Gradients w.r.t. the forward sources, through the forward kernel run on dz with the flipped/transposed weights."""
+    N, Cin, kh, kw = weight.shape
+    B, _, Ho, Wo = dz.shape
+    H = xs[0].shape[2] * (2 if ups[0] else 1)
+    W = xs[0].shape[3] * (2 if ups[0] else 1)
+    dev = dz.device
+    Nc = dz.shape[1]                                   # possibly channel-padded dz
+    wT = weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=CL)   # [Cin][kh][kw][Cout]
+    wmat, wcols = gemm_weight(wT, [Nc], [N])
+    table = chunk_table([Nc], kh, kw, dev)
+    src_C = [x.shape[1] for x in xs]
+    if len(xs) == 1 and src_C[0] != Cin:                # zero-padded stem input: gradient not needed (images)
+        return [None]
+    grads = []
+    simple = len(xs) == 1 and not ups[0] and not reflect
+    for x, up in zip(xs, ups):
+        grads.append(torch.empty_like(x, memory_format=CL) if simple else torch.zeros_like(x, memory_format=CL))
+    a = _lib.ConvArgs()
+    a.src[0] = ptr(dz)
+    a.src_C[0], a.src_H[0], a.src_W[0], a.src_up[0] = Nc, Ho, Wo, 0
+    a.nsrc = 1
+    a.B, a.Hin, a.Win = B, Ho, Wo
+    a.N = Cin
+    a.stride, a.reflect = 1, 0
+    a.in_div = 2 if stride == 2 else 0
+    assert stride in (1, 2)
+    if reflect:
+        a.Ho, a.Wo, a.pad = H + 2 * pad, W + 2 * pad, kh - 1
+        a.fold_pad, a.fold_reflect = pad, 1
+    else:
+        a.Ho, a.Wo, a.pad = H, W, kh - 1 - pad
+        a.fold_pad, a.fold_reflect = 0, 0
+    a.fold_H, a.fold_W = H, W
+    a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
+    a.table, a.nkb = ptr(table), table.shape[0] // 8
+    a.act = 0
+    if simple:
+        a.out = ptr(grads[0])
+    else:
+        a.scatter = 1
+        a.ndst = len(xs)
+        nt = 256
+        for g, up in zip(grads, ups):
+            pass
+        for i, (g, up) in enumerate(zip(grads, ups)):
+            a.dst[i] = ptr(g)
+            a.dst_C[i], a.dst_H[i], a.dst_W[i], a.dst_up[i] = g.shape[1], g.shape[2], g.shape[3], int(up)
+            if i + 1 < len(grads):
+                while g.shape[1] % nt:
+                    nt //= 2
+        if len(grads) == 1:
+            nt = 0
+        assert nt == 0 or nt >= 16
+        a.nt = nt
+    check(_launch("conv_dgrad", dz, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(dz))), "jpb_conv2d_fwd(dgrad)")
+    return grads
+
+
+def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect):
+    N, Cin, kh, kw = weight.shape
+    B, Nc, Ho, Wo = dz.shape
+    dev = dz.device
+    src_C = [x.shape[1] for x in xs]
+    w_C = [Cin] if (len(xs) == 1 and src_C[0] != Cin) else src_C
+    table = chunk_table(src_C, kh, kw, dev)
+    raw = all(c % 4 == 0 for c in src_C) and src_C == w_C
+    Cpad = sum(_pad4(c) for c in src_C)
+    wcols = kh * kw * (Cin if raw else Cpad)
+    dw = torch.zeros(Nc, wcols, dtype=torch.float32, device=dev)
+    a = _lib.ConvWgradArgs()
+    _fill_sources(a, xs, ups)
+    a.B = B
+    a.Hin = xs[0].shape[2] * (2 if ups[0] else 1)
+    a.Win = xs[0].shape[3] * (2 if ups[0] else 1)
+    a.Ho, a.Wo, a.N = Ho, Wo, Nc
+    a.stride, a.pad, a.reflect = stride, pad, int(reflect)
+    a.table, a.nchunks = ptr(table), table.shape[0]
+    a.dy, a.dw, a.w_row, a.w_cols = ptr(dz), ptr(dw), wcols, wcols
+    nt = 32
+    while nt < Nc and nt < 256:
+        nt *= 2
+    tiles = ((table.shape[0] + 31) // 32) * ((Nc + nt - 1) // nt)
+    steps = (B * Ho * Wo + 31) // 32
+    a.splits = max(1, min(steps, (2 * 148 + tiles - 1) // tiles))
+    check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz))), "jpb_conv2d_wgrad")
+    dw = dw[:N]
+    if raw:
+        return dw.view(N, kh, kw, Cin).permute(0, 3, 1, 2)
+    parts, off = [], 0
+    dw = dw.view(N, kh, kw, Cpad)
+    for c_t, c_w in zip(src_C, w_C):
+        parts.append(dw[..., off:off + c_w])
+        off += _pad4(c_t)
+    return torch.cat(parts, -1).permute(0, 3, 1, 2)
+
+
 class _ConvTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, weight, bias, residual, *xs):
@@ -101,10 +230,7 @@ class _ConvTC(torch.autograd.Function):
         wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=dev, memory_format=CL)
         a = _lib.ConvArgs()
-        for i, x in enumerate(xs):
-            a.src[i] = ptr(x)
-            a.src_C[i], a.src_H[i], a.src_W[i], a.src_up[i] = x.shape[1], x.shape[2], x.shape[3], int(ups[i])
-        a.nsrc = len(xs)
+        _fill_sources(a, xs, ups)
         a.B, a.Hin, a.Win, a.Ho, a.Wo, a.N = B, Hin, Win, Ho, Wo, N
         a.stride, a.pad, a.reflect = stride, pad, int(reflect)
         a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
@@ -115,17 +241,35 @@ class _ConvTC(torch.autograd.Function):
             a.residual = ptr(residual)
         a.act = ACT[act]
         a.out = ptr(out)
-        from .functional import _launch
         check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out))), "jpb_conv2d_fwd")
         ctx.cfg = cfg
         ctx.has = (bias is not None, residual is not None)
-        ctx.save_for_backward(weight, bias, residual, *xs)
+        ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)
         return out
 
     @staticmethod
     def backward(ctx, gy):
         cfg = ctx.cfg
-        weight, bias, residual, *xs = ctx.saved_tensors
+        weight, bias, residual, out, *xs = ctx.saved_tensors
+        if BACKWARD == "torch":
+            return _ConvTC._backward_library(ctx, gy)
+        ups, stride, pad, reflect, act = cfg["ups"], cfg["stride"], cfg["pad"], cfg["reflect"], cfg["act"]
+        N = weight.shape[0]
+        dz, gb = act_bwd(gy, out, act, bias is not None)
+        gr = dz if residual is not None else None
+        dzp = dz
+        if N % 4:                                    # 1/2/6 output channels: pad dz so rows are whole 16-byte chunks
+            dzp = F.pad(dz, (0, 0, 0, 0, 0, _pad4(N) - N)).contiguous(memory_format=CL)
+        gxs = [None] * len(xs)
+        if any(ctx.needs_input_grad[4:]):
+            gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
+        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect) if ctx.needs_input_grad[1] else None
+        return (None, gw, gb, gr) + tuple(gxs)
+
+    @staticmethod
+    def _backward_library(ctx, gy):
+        cfg = ctx.cfg
+        weight, bias, residual, out, *xs = ctx.saved_tensors
         with torch.enable_grad():
             xs_ = [x.detach().requires_grad_(True) for x in xs]
             w_ = weight.detach().requires_grad_(True)

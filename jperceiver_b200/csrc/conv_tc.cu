@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
         for (int i = 0; i < 8; ++i) {
           int iy = iy0[i] + dy, ix = ix0[i] + dx;
           bool ok = bb[i] >= 0 && e.x >= 0;
+          if (a.in_div == 2) { ok = ok && !((iy | ix) & 1); iy >>= 1; ix >>= 1; }   // dgrad of a stride-2 convolution
           if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
           else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
           if (!ok) { iy = 0; ix = 0; }
@@ -231,27 +232,48 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
     const int row = warp * 32 + lane;
     const int m = m0 + row;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float* out = a.out + (size_t)m * a.N + n0;
-    const float* res = a.residual ? a.residual + (size_t)m * a.N + n0 : nullptr;
+    float* out = nullptr;
+    const float* res = nullptr;
+    bool atomic = false, vec_ok = (a.N & 3) == 0;
+    int nvalid = a.N - n0;                    // channels of this N tile that exist
+    if (!a.scatter) {
+      out = a.out + (size_t)m * a.N + n0;
+      res = a.residual ? a.residual + (size_t)m * a.N + n0 : nullptr;
+    } else if (m < M) {
+      // dgrad scatter: this launch's output pixel (py,px) lives in the (padded) gradient domain; fold it back through
+      // the reflection padding and the nearest up-sampling of the forward gather, into the source that owns channels n0..
+      int j = 0, cbase = 0;
+      while (j + 1 < a.ndst && n0 >= cbase + a.dst_C[j]) { cbase += a.dst_C[j]; ++j; }
+      const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
+      int ty = rem / a.Wo - a.fold_pad, tx = rem % a.Wo - a.fold_pad;
+      if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
+      atomic = a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
+      if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
+      out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
+      vec_ok = (a.dst_C[j] & 3) == 0;
+      nvalid = cbase + a.dst_C[j] - n0;
+    }
     for (int j = 0; j < NT; j += 16) {
       float v[16];
       tmem_ld16(taddr + (uint32_t)j, v);   // warp-collective: every lane executes it, even for rows >= M
       if (m < M) {
-        const int nleft = a.N - n0 - j;
-        if (nleft >= 16 && (a.N & 3) == 0) {
+        const int nleft = nvalid - j;
+        if (nleft >= 16 && vec_ok) {
           for (int q = 0; q < 16; q += 4) {
             float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
             if (a.bias) { const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + j + q); o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w; }
             if (res) { const float4 rq = *reinterpret_cast<const float4*>(res + j + q); o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w; }
             o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-            *reinterpret_cast<float4*>(out + j + q) = o;
+            if (atomic) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out + j + q), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            else *reinterpret_cast<float4*>(out + j + q) = o;
           }
         } else {
           for (int q = 0; q < 16 && q < nleft; ++q) {
             float o = v[q];
             if (a.bias) o += a.bias[n0 + j + q];
             if (res) o += res[j + q];
-            out[j + q] = apply_act(o, a.act);
+            o = apply_act(o, a.act);
+            if (atomic) atomicAdd(out + j + q, o); else out[j + q] = o;
           }
         }
       }
@@ -297,6 +319,170 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
   }
 }
 
+
+// ======================================================================================== weight gradient
+//   dW^T[k, co] = sum_p  im2col[p, k] * dZ[p, co]      (p = output pixel, k = position in the K-chunk order)
+// GEMM with the reduction over pixels: both operands are "MN-major" (the gathered channels / the dZ channels are the
+// contiguous dimension), 128-byte swizzled: shared memory holds 1 KB atoms of 8 pixels x 32 channels.
+//   M tile = 128 consecutive K positions (32 chunks of the table), N tile = NT output channels,
+//   each pipeline stage = 32 pixels = 4 tcgen05.mma (K = 8 pixels each).
+// The pixel range is split over gridDim.z CTAs; partial tiles are accumulated with red.global.add.
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, JpbConvWgradArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int B_STAGE = NT * BK * 4;
+  constexpr int STAGE = A_STAGE + B_STAGE;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = a.B * a.Ho * a.Wo;
+  const int mt = blockIdx.x, n0 = blockIdx.y * NT;
+  // pixel range of this split, in 32-pixel steps
+  const int steps_total = (P + 31) / 32;
+  const int steps_per = (steps_total + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int step0 = blockIdx.z * steps_per;
+  int nsteps = steps_total - step0;
+  if (nsteps > steps_per) nsteps = steps_per;
+  if (nsteps < 0) nsteps = 0;
+
+  if (tid == 160) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD + 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    constexpr uint32_t cols = NT < 32 ? 32 : NT;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nsteps > 0) {
+  if (warp < 4) {
+    // ------------------------------------------------ im2col^T gather: thread owns chunk q of the K tile, 8 pixel slots
+    const int q = tid & 31, prow = tid >> 5;
+    const int gq = mt * 32 + q;
+    int4 e = make_int4(-1, 0, 0, 0);
+    if (gq < a.nchunks) e = __ldg(reinterpret_cast<const int4*>(a.table) + gq);
+    const float* sptr = a.src[e.x < 0 ? 0 : e.x];
+    const int sC = a.src_C[e.x < 0 ? 0 : e.x], sH = a.src_H[e.x < 0 ? 0 : e.x], sW = a.src_W[e.x < 0 ? 0 : e.x];
+    const int sup = a.src_up[e.x < 0 ? 0 : e.x];
+    const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
+    const int nval = e.w >> 2;
+    const int HoWo = a.Ho * a.Wo;
+    for (int st = 0; st < nsteps; ++st) {
+      const int s = st % STAGES;
+      const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const uint32_t abase = smem_u32(smem + s * STAGE);
+      const int p0 = (step0 + st) * 32;
+      for (int i = 0; i < 8; ++i) {
+        const int slot = prow + 4 * i;            // pixel slot 0..31 of this step
+        const int p = p0 + slot;
+        // atom (mngroup = q>>3, kgroup = slot>>3), row = slot&7, 16-byte column (q&7) ^ row
+        const uint32_t dst = abase + (uint32_t)(((q >> 3) * 4 + (slot >> 3)) * 1024 + (slot & 7) * 128 + (((q & 7) ^ (slot & 7)) << 4));
+        bool ok = p < P && e.x >= 0;
+        int iy = 0, ix = 0, b = 0;
+        if (ok) {
+          b = p / HoWo;
+          const int rem = p - b * HoWo;
+          const int oy = rem / a.Wo;
+          iy = oy * a.stride - a.pad + dy;
+          ix = (rem - oy * a.Wo) * a.stride - a.pad + dx;
+          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+          else ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+          if (sup) { iy >>= 1; ix >>= 1; }
+        }
+        if (!ok) { iy = 0; ix = 0; b = 0; }
+        const float* g = sptr + ((size_t)(b * sH + iy) * sW + ix) * sC + e.z;
+        if (e.w == 16 || !ok) cp_async16(dst, g, ok ? 16u : 0u);
+        else {
+          float4 v = make_float4(g[0], nval > 1 ? g[1] : 0.f, nval > 2 ? g[2] : 0.f, 0.f);
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+      }
+      cp_async_commit();
+      if (st >= 2) {
+        cp_async_wait<2>();
+        fence_async_proxy();
+        mbar_arrive(&full_bar[(st - 2) % STAGES]);
+      }
+    }
+    for (int st = (nsteps >= 2 ? nsteps - 2 : 0); st < nsteps; ++st) {
+      if (st == nsteps - 2) cp_async_wait<1>(); else cp_async_wait<0>();
+      fence_async_proxy();
+      mbar_arrive(&full_bar[st % STAGES]);
+    }
+    // ------------------------------------------------ epilogue: dW[n0 + j][k] (+)= D[k, j]
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int k = mt * 128 + warp * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool use_atomic = gridDim.z > 1;
+    for (int j = 0; j < NT; j += 16) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)j, v);
+      if (k < a.w_cols) {
+        for (int c = 0; c < 16; ++c) {
+          const int n = n0 + j + c;
+          if (n < a.N) {
+            float* d = a.dw + (size_t)n * a.w_row + k;
+            if (use_atomic) atomicAdd(d, v[c]); else *d = v[c];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (int st = 0; st < nsteps; ++st) {
+        const int s = st % STAGES;
+        const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
+        const int p0 = (step0 + st) * 32;
+        for (int h = 0; h < NT / 32; ++h)     // one {32 channels x 32 pixels} box per MN group: lands as 4 atoms of 8 pixels
+          tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE + h * 4096), &dymap, &full_bar[s], n0 + 32 * h, p0);
+      }
+    }
+  } else {
+    // MN-major x MN-major: a_major = b_major = 1 (bits 15, 16)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int st = 0; st < nsteps; ++st) {
+      const int s = st % STAGES;
+      const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        // descriptor: leading byte offset = distance between 32-channel MN groups (4096 B), stride byte offset = distance
+        // between 8-pixel K groups (1024 B); one MMA consumes one K group
+        const uint64_t hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        const uint64_t ad = (uint64_t)((smem_u32(smem + s * STAGE) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | hi;
+        const uint64_t bd = (uint64_t)((smem_u32(smem + s * STAGE + A_STAGE) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | hi;
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32(tmem_base, ad + (uint64_t)(64 * kk), bd + (uint64_t)(64 * kk), idesc, (st | kk) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (st == nsteps - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    constexpr uint32_t cols = NT < 32 ? 32 : NT;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -329,12 +515,15 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
 }  // namespace
 
 extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
-  if (!a || !a->weight || !a->table || !a->out || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nkb < 1) return JPB_ERR_ARG;
+  if (!a || !a->weight || !a->table || (!a->out && !a->scatter) || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nkb < 1) return JPB_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(a->weight) & 15) || (a->w_row & 3)) return JPB_ERR_ARG;   // TMA: 16-byte aligned base and row pitch
   EncodeTiledFn enc = get_encode();
   if (!enc) return JPB_ERR_UNSUPPORTED;
   int nt = 16;
   while (nt < a->N && nt < 256) nt <<= 1;
+  if (a->nt) nt = a->nt;
+  if (nt != 16 && nt != 32 && nt != 64 && nt != 128 && nt != 256) return JPB_ERR_ARG;
+  if (a->scatter && (a->ndst < 1 || a->ndst > JPB_CONV_MAX_SRC)) return JPB_ERR_ARG;
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)a->w_cols, (cuuint64_t)a->N};
   const cuuint64_t gstr[1] = {(cuuint64_t)a->w_row * 4};
@@ -350,6 +539,46 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
     case 64: return launch_fwd<64, 6>(a, map, st);
     case 128: return launch_fwd<128, 5>(a, map, st);
     default: return launch_fwd<256, 4>(a, map, st);
+  }
+}
+
+namespace {
+template <int NT, int STAGES>
+int launch_wgrad(const JpbConvWgradArgs* a, const CUtensorMap& map, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = true;
+  }
+  dim3 grid((a->nchunks + 31) / 32, (a->N + NT - 1) / NT, a->splits);
+  conv_tc_wgrad_kernel<NT, STAGES><<<grid, 192, smem, st>>>(map, *a);
+  return jpb_status();
+}
+}  // namespace
+
+extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
+  if (!a || !a->dy || !a->dw || !a->table || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nchunks < 1 || a->splits < 1) return JPB_ERR_ARG;
+  if ((a->N & 3) || (reinterpret_cast<uintptr_t>(a->dy) & 15)) return JPB_ERR_UNSUPPORTED;   // TMA row pitch of dZ must be 16-byte aligned
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return JPB_ERR_UNSUPPORTED;
+  int nt = 32;
+  while (nt < a->N && nt < 256) nt <<= 1;
+  const long long P = (long long)a->B * a->Ho * a->Wo;
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a->N, (cuuint64_t)P};
+  const cuuint64_t gstr[1] = {(cuuint64_t)a->N * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return JPB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nt) {
+    case 32: return launch_wgrad<32, 6>(a, map, st);
+    case 64: return launch_wgrad<64, 6>(a, map, st);
+    case 128: return launch_wgrad<128, 5>(a, map, st);
+    default: return launch_wgrad<256, 4>(a, map, st);
   }
 }
 

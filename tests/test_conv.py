@@ -65,3 +65,58 @@ def test_conv_forward_matches_fp32_library(case):
     err = (got - ref).abs().max().item()
     scale = max(ref0.abs().max().item(), 1e-6)
     assert err <= 3e-3 * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_backward_matches_fp32_library(case):
+    """dgrad (incl. reflection / up-sampling / concat scatter, stride-2 gather division), wgrad (MN-major tcgen05,
+    split over pixels, packed K layouts) and the fused epilogue backward against fp32 autograd of the library form."""
+    name, srcs, cout, k, stride, pad, reflect, act, has_bias, has_res = case
+    _lib._handle, _lib._emulated = None, False
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(hash(name) % 1000 + 7)
+    B = 2
+    xs = [torch.randn(B, c, h, w, generator=g).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
+    ups = [bool(up) for *_, up in srcs]
+    cin_t = sum(c for c, *_ in srcs)
+    cin_w = {4: 3, 8: 6}.get(cin_t, cin_t) if k == 7 else cin_t
+    stem = k == 7
+    if stem:
+        xs[0][:, cin_w:] = 0
+    weight = (torch.randn(cout, cin_w, k, k, generator=g) / (cin_w * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
+    bias = torch.randn(cout, generator=g).to(dev) if has_bias else None
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr = [x.clone().requires_grad_(not stem) for x in xs]
+        wr = weight.clone().requires_grad_(True)
+        br = bias.clone().requires_grad_(True) if has_bias else None
+        y0 = JC._torch_conv(xr, ups, wr, br, stride, pad, reflect, "none", None)
+        res = torch.randn(y0.shape, generator=g).to(dev).contiguous(memory_format=CL) if has_res else None
+        rr = res.clone().requires_grad_(True) if has_res else None
+        ref = JC._torch_conv(xr, ups, wr, br, stride, pad, reflect, act, rr)
+        gy = torch.randn(ref.shape, generator=g).to(dev).contiguous(memory_format=CL)
+        ref.backward(gy)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    xm = [x.clone().requires_grad_(not stem) for x in xs]
+    wm = weight.clone().requires_grad_(True)
+    bm = bias.clone().requires_grad_(True) if has_bias else None
+    rm = res.clone().requires_grad_(True) if has_res else None
+    got = JC.conv2d_tc(xm, ups, wm, bm, stride, pad, reflect, act, rm)
+    got.backward(gy)
+    torch.cuda.synchronize()
+
+    def close(a, b, what):
+        assert a is not None and a.shape == b.shape, (name, what)
+        err = (a - b).abs().max().item()
+        assert err <= 5e-3 * max(b.abs().max().item(), 1e-6), (name, what, err, b.abs().max().item())
+
+    close(wm.grad, wr.grad, "weight")
+    if has_bias:
+        close(bm.grad, br.grad, "bias")
+    if has_res:
+        close(rm.grad, rr.grad, "residual")
+    if not stem:
+        for i, (a, b) in enumerate(zip(xm, xr)):
+            close(a.grad, b.grad, "input%d" % i)
