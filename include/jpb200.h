@@ -187,6 +187,7 @@ typedef struct JpbConvWgradArgs {
   long long w_row;
   int w_cols;
   int splits;
+  float* dbg;                /* debug only: first pipeline stage (A then B tile) is copied here when non-NULL */
 } JpbConvWgradArgs;
 int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
 

@@ -89,6 +89,7 @@ class ConvWgradArgs(C.Structure):
         ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
         ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("table", C.c_void_p), ("nchunks", C.c_int),
         ("dy", C.c_void_p), ("dw", C.c_void_p), ("w_row", C.c_longlong), ("w_cols", C.c_int), ("splits", C.c_int),
+        ("dbg", C.c_void_p),
     ]
 
 

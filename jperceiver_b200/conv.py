@@ -170,7 +170,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     return grads
 
 
-def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect):
+def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
     N, Cin, kh, kw = weight.shape
     B, Nc, Ho, Wo = dz.shape
     dev = dz.device
@@ -196,6 +196,8 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect):
     tiles = ((table.shape[0] + 31) // 32) * ((Nc + nt - 1) // nt)
     steps = (B * Ho * Wo + 31) // 32
     a.splits = max(1, min(steps, (2 * 148 + tiles - 1) // tiles))
+    if dbg is not None:
+        a.dbg = ptr(dbg)
     check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz))), "jpb_conv2d_wgrad")
     dw = dw[:N]
     if raw:

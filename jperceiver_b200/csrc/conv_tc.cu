@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
 // ======================================================================================== weight gradient
 //   dW^T[k, co] = sum_p  im2col[p, k] * dZ[p, co]      (p = output pixel, k = position in the K-chunk order)
 // GEMM with the reduction over pixels: both operands are "MN-major" (the gathered channels / the dZ channels are the
-// contiguous dimension), 128-byte swizzled: shared memory holds 1 KB atoms of 8 pixels x 32 channels.
+// contiguous dimension).  MN-major TF32 operands must use the SWIZZLE_128B_BASE32B layout (cute Swizzle<2,5,2>): shared
+// memory holds 512-byte atoms of 4 pixels x 32 channels, 32-byte chunks XOR-ed with the pixel index mod 4.
 //   M tile = 128 consecutive K positions (32 chunks of the table), N tile = NT output channels,
 //   each pipeline stage = 32 pixels = 4 tcgen05.mma (K = 8 pixels each).
 // The pixel range is split over gridDim.z CTAs; partial tiles are accumulated with red.global.add.
@@ -386,8 +387,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
       for (int i = 0; i < 8; ++i) {
         const int slot = prow + 4 * i;            // pixel slot 0..31 of this step
         const int p = p0 + slot;
-        // atom (mngroup = q>>3, kgroup = slot>>3), row = slot&7, 16-byte column (q&7) ^ row
-        const uint32_t dst = abase + (uint32_t)(((q >> 3) * 4 + (slot >> 3)) * 1024 + (slot & 7) * 128 + (((q & 7) ^ (slot & 7)) << 4));
+        // MN group (q>>3) of 4096 B = 8 K-groups of 4 pixels (512 B); row = slot&3; 32-byte chunk ((q&7)>>1) ^ row, 16-byte half q&1
+        const uint32_t dst = abase + (uint32_t)((q >> 3) * 4096 + (slot >> 2) * 512 + (slot & 3) * 128 +
+                                                 (((((q & 7) >> 1) ^ (slot & 3)) << 5) | ((q & 1) << 4)));
         bool ok = p < P && e.x >= 0;
         int iy = 0, ix = 0, b = 0;
         if (ok) {
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
         const int p0 = (step0 + st) * 32;
-        for (int h = 0; h < NT / 32; ++h)     // one {32 channels x 32 pixels} box per MN group: lands as 4 atoms of 8 pixels
+        for (int h = 0; h < NT / 32; ++h)     // one {32 channels x 32 pixels} box per MN group: lands as 8 atoms of 4 pixels
           tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE + h * 4096), &dymap, &full_bar[s], n0 + 32 * h, p0);
       }
     }
@@ -460,10 +462,15 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
       const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
+      if (a.dbg && st == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {   // debug: dump stage 0 (A then B)
+        const float* sa = reinterpret_cast<const float*>(smem);
+        for (int i = lane; i < (A_STAGE + B_STAGE) / 4; i += 32) a.dbg[i] = sa[i];
+        __syncwarp();
+      }
       if (lane == 0) {
         // descriptor: leading byte offset = distance between 32-channel MN groups (4096 B), stride byte offset = distance
-        // between 8-pixel K groups (1024 B); one MMA consumes one K group
-        const uint64_t hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        // between 4-pixel K groups (512 B), layout type 1 = SWIZZLE_128B_BASE32B; one MMA (K = 8 pixels) spans two K groups
+        const uint64_t hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
         const uint64_t ad = (uint64_t)((smem_u32(smem + s * STAGE) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | hi;
         const uint64_t bd = (uint64_t)((smem_u32(smem + s * STAGE + A_STAGE) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | hi;
         for (int kk = 0; kk < 4; ++kk)
@@ -571,7 +578,7 @@ extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
   const cuuint32_t box[2] = {32, 32};
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   switch (nt) {

@@ -1,6 +1,10 @@
 """Layer-by-layer parity of the tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu) with the fp32 library
 convolution on the shapes of SURVEY.md Appendix A (scaled down in batch/extent, same K/N structure).
-Tolerance: TF32 operands (10-bit mantissa, truncated) with fp32 accumulation -> 3e-3 of max|y|."""
+
+Operands are drawn TF32-representable (low 13 mantissa bits zero), so the tensor-core products are exact and the only
+difference from the fp32 library result is the fp32 summation order: forward tolerance 5e-5 of max|y| — a much sharper
+check of indexing (gather table, swizzles, descriptors, scatter) than a TF32-noise tolerance would be, and activation
+masks cannot flip between the two implementations.  A second forward test uses unrounded operands at 3e-3 (TF32)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -10,6 +14,11 @@ from jperceiver_b200 import conv as JC
 
 pytestmark = pytest.mark.gpu
 CL = torch.channels_last
+
+
+def tf32(t):
+    """Truncate to TF32 (keep sign, 8 exponent and 10 mantissa bits)."""
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32).view(t.shape)
 
 CASES = [
     # name, sources [(C, H, W, up)], Cout, k, stride, pad, reflect, act, bias, residual
@@ -36,20 +45,22 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("exact", [True, False], ids=["tf32-exact-operands", "fp32-operands"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_conv_forward_matches_fp32_library(case):
+def test_conv_forward_matches_fp32_library(case, exact):
     name, srcs, cout, k, stride, pad, reflect, act, has_bias, has_res = case
     _lib._handle, _lib._emulated = None, False
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(hash(name) % 1000)
     B = 2
-    xs = [torch.randn(B, c, h, w, generator=g).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
+    rnd = tf32 if exact else (lambda t: t)
+    xs = [rnd(torch.randn(B, c, h, w, generator=g)).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
     ups = [bool(up) for *_, up in srcs]
     cin_t = sum(c for c, *_ in srcs)
     cin_w = {4: 3, 8: 6}.get(cin_t, cin_t) if k == 7 else cin_t
     if k == 7:
         xs[0][:, cin_w:] = 0
-    weight = (torch.randn(cout, cin_w, k, k, generator=g) / (cin_w * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
+    weight = rnd(torch.randn(cout, cin_w, k, k, generator=g) / (cin_w * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
     bias = torch.randn(cout, generator=g).to(dev) if has_bias else None
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
@@ -64,7 +75,7 @@ def test_conv_forward_matches_fp32_library(case):
     assert got.shape == ref.shape and got.is_contiguous(memory_format=CL)
     err = (got - ref).abs().max().item()
     scale = max(ref0.abs().max().item(), 1e-6)
-    assert err <= 3e-3 * scale, (name, err, scale)
+    assert err <= (5e-5 if exact else 3e-3) * scale, (name, err, scale)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
@@ -76,41 +87,53 @@ def test_conv_backward_matches_fp32_library(case):
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(hash(name) % 1000 + 7)
     B = 2
-    xs = [torch.randn(B, c, h, w, generator=g).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
+    xs = [tf32(torch.randn(B, c, h, w, generator=g)).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
     ups = [bool(up) for *_, up in srcs]
     cin_t = sum(c for c, *_ in srcs)
     cin_w = {4: 3, 8: 6}.get(cin_t, cin_t) if k == 7 else cin_t
     stem = k == 7
     if stem:
         xs[0][:, cin_w:] = 0
-    weight = (torch.randn(cout, cin_w, k, k, generator=g) / (cin_w * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
+    weight = tf32(torch.randn(cout, cin_w, k, k, generator=g) / (cin_w * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
     bias = torch.randn(cout, generator=g).to(dev) if has_bias else None
+    xm = [x.clone().requires_grad_(not stem) for x in xs]
+    wm = weight.clone().requires_grad_(True)
+    bm = bias.clone().requires_grad_(True) if has_bias else None
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
         xr = [x.clone().requires_grad_(not stem) for x in xs]
         wr = weight.clone().requires_grad_(True)
         br = bias.clone().requires_grad_(True) if has_bias else None
-        y0 = JC._torch_conv(xr, ups, wr, br, stride, pad, reflect, "none", None)
-        res = torch.randn(y0.shape, generator=g).to(dev).contiguous(memory_format=CL) if has_res else None
+        z = JC._torch_conv(xr, ups, wr, br, stride, pad, reflect, "none", None)
+        res = torch.randn(z.shape, generator=g).to(dev).contiguous(memory_format=CL) if has_res else None
         rr = res.clone().requires_grad_(True) if has_res else None
-        ref = JC._torch_conv(xr, ups, wr, br, stride, pad, reflect, act, rr)
-        gy = torch.randn(ref.shape, generator=g).to(dev).contiguous(memory_format=CL)
+        rm = res.clone().requires_grad_(True) if has_res else None
+        got = JC.conv2d_tc(xm, ups, wm, bm, stride, pad, reflect, act, rm)
+        if has_res:
+            z = z + rr
+        # ReLU / LeakyReLU masks are taken from the kernel's own output: the two summation orders differ by ~1e-5, so a
+        # handful of |z| ~ 0 elements would otherwise take different branches and dominate a max-abs comparison
+        if act == "relu":
+            ref = torch.where(got.detach() > 0, z, torch.zeros_like(z))
+        elif act == "leaky":
+            ref = torch.where(got.detach() > 0, z, 0.01 * z)
+        elif act == "sigmoid":
+            ref = torch.sigmoid(z)
+        else:
+            ref = z
+        gy = tf32(torch.randn(ref.shape, generator=g)).to(dev).contiguous(memory_format=CL)
         ref.backward(gy)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    xm = [x.clone().requires_grad_(not stem) for x in xs]
-    wm = weight.clone().requires_grad_(True)
-    bm = bias.clone().requires_grad_(True) if has_bias else None
-    rm = res.clone().requires_grad_(True) if has_res else None
-    got = JC.conv2d_tc(xm, ups, wm, bm, stride, pad, reflect, act, rm)
     got.backward(gy)
     torch.cuda.synchronize()
 
     def close(a, b, what):
         assert a is not None and a.shape == b.shape, (name, what)
         err = (a - b).abs().max().item()
-        assert err <= 5e-3 * max(b.abs().max().item(), 1e-6), (name, what, err, b.abs().max().item())
+        # dz = gy * act'(y) is not TF32-representable after a leaky / sigmoid derivative: TF32 tolerance
+        assert err <= 3e-3 * max(b.abs().max().item(), 1e-6), (name, what, err, b.abs().max().item())
 
     close(wm.grad, wr.grad, "weight")
     if has_bias:
