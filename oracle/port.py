@@ -608,6 +608,6 @@ def synth_inputs(opt, B, seed=1, hw_full=(375, 1242)):
             ry, rx = (torch.rand(2, generator=g) * 0.5 + 0.5) * frac * occ
             m[b, 0] = ((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) <= 1).float()
             if name != "bothD":   # the road always covers the strip ahead of the ego car (so the CGT "assumption region" is labelled)
-                m[b, 0, int(0.3 * occ):int(0.7 * occ), int(0.1 * occ):int(0.55 * occ)] = 1
+                m[b, 0, int(0.5 * occ):, int(0.3 * occ):int(0.7 * occ)] = 1   # ego car sits at the bottom centre of the BEV map
         inp[(name, 0, 0)] = m
     return inp
