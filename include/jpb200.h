@@ -195,6 +195,11 @@ int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */
 int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int C, int act, float* dbias, void* stream);
 
+/* ---- NHWC max pooling (nn.MaxPool2d(k, s, p); layers.py:191, resnet.py:91, layout_model.py:84) --------------
+ * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.               */
+int jpb_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, int k, int s, int p, void* stream);
+int jpb_maxpool_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, int k, int s, int p, void* stream);
+
 /* ---- flat-buffer optimizer step (mono/core/utils/dist_utils.py:34-60 + torch.optim.Adam) ---------
  * jpb_sumsq: acc[0] += sum g^2 (run on the all-reduced SUM of gradients).
  * jpb_adam_step: g_eff = g * grad_scale (1/world) * min(1, max_norm / (sqrt(normsq)*grad_scale + 1e-6));

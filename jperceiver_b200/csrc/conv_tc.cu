@@ -378,36 +378,42 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
     const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
     const int nval = e.w >> 2;
     const int HoWo = a.Ho * a.Wo;
+    // pixel coordinates of this thread's 8 slots, advanced incrementally (32 pixels per step): no divisions in the loop
+    int pb[8], poy[8], pox[8];
+    for (int i = 0; i < 8; ++i) {
+      const long long p = (long long)step0 * 32 + prow + 4 * i;
+      pb[i] = (int)(p / HoWo);
+      const int rem = (int)(p - (long long)pb[i] * HoWo);
+      poy[i] = rem / a.Wo;
+      pox[i] = rem - poy[i] * a.Wo;
+    }
     for (int st = 0; st < nsteps; ++st) {
       const int s = st % STAGES;
       const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
       const uint32_t abase = smem_u32(smem + s * STAGE);
-      const int p0 = (step0 + st) * 32;
       for (int i = 0; i < 8; ++i) {
         const int slot = prow + 4 * i;            // pixel slot 0..31 of this step
-        const int p = p0 + slot;
         // MN group (q>>3) of 4096 B = 8 K-groups of 4 pixels (512 B); row = slot&3; 32-byte chunk ((q&7)>>1) ^ row, 16-byte half q&1
         const uint32_t dst = abase + (uint32_t)((q >> 3) * 4096 + (slot >> 2) * 512 + (slot & 3) * 128 +
                                                  (((((q & 7) >> 1) ^ (slot & 3)) << 5) | ((q & 1) << 4)));
-        bool ok = p < P && e.x >= 0;
-        int iy = 0, ix = 0, b = 0;
-        if (ok) {
-          b = p / HoWo;
-          const int rem = p - b * HoWo;
-          const int oy = rem / a.Wo;
-          iy = oy * a.stride - a.pad + dy;
-          ix = (rem - oy * a.Wo) * a.stride - a.pad + dx;
-          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
-          else ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-          if (sup) { iy >>= 1; ix >>= 1; }
-        }
+        bool ok = pb[i] < a.B && e.x >= 0;
+        int iy = poy[i] * a.stride - a.pad + dy, ix = pox[i] * a.stride - a.pad + dx, b = pb[i];
+        if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+        else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+        if (sup) { iy >>= 1; ix >>= 1; }
         if (!ok) { iy = 0; ix = 0; b = 0; }
         const float* g = sptr + ((size_t)(b * sH + iy) * sW + ix) * sC + e.z;
         if (e.w == 16 || !ok) cp_async16(dst, g, ok ? 16u : 0u);
         else {
           float4 v = make_float4(g[0], nval > 1 ? g[1] : 0.f, nval > 2 ? g[2] : 0.f, 0.f);
           asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+        // advance this slot by 32 pixels
+        pox[i] += 32;
+        while (pox[i] >= a.Wo) {
+          pox[i] -= a.Wo;
+          if (++poy[i] >= a.Ho) { poy[i] = 0; ++pb[i]; }
         }
       }
       cp_async_commit();

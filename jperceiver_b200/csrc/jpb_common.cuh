@@ -22,6 +22,8 @@ struct jpb_dim3 { unsigned x, y, z; jpb_dim3(unsigned a = 1, unsigned b = 1, uns
 typedef jpb_dim3 dim3;
 static jpb_dim3 threadIdx(0, 0, 0), blockIdx(0, 0, 0), blockDim(1, 1, 1), gridDim(1, 1, 1);
 typedef void* cudaStream_t;
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
 #define __global__
 #define __device__
 #define __host__

@@ -329,3 +329,36 @@ class _L1Mean(torch.autograd.Function):
 def l1_mean(x, y):
     """``nn.L1Loss()(x, y)`` (compute_transform_losses).  x and y must share a memory layout."""
     return _L1Mean.apply(x, y)
+
+
+# --------------------------------------------------------------------------------------------------
+# NHWC max pooling
+# --------------------------------------------------------------------------------------------------
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, s, p):
+        x = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+        B, Cc, H, W = x.shape
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        y = torch.empty((B, Cc, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty((B, Ho, Wo, Cc), dtype=torch.uint8, device=x.device)
+        check(_launch("maxpool_fwd", x, lambda: _lib.lib().jpb_maxpool_fwd(ptr(x), ptr(y), ptr(idx), B, H, W, Cc, k, s, p, stream_of(x))),
+              "jpb_maxpool_fwd")
+        ctx.save_for_backward(idx)
+        ctx.geom = (B, H, W, Cc, k, s, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        B, H, W, Cc, k, s, p = ctx.geom
+        gy = gy if gy.is_contiguous(memory_format=torch.channels_last) else gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=gy.device, memory_format=torch.channels_last)
+        check(_launch("maxpool_bwd", gy, lambda: _lib.lib().jpb_maxpool_bwd(ptr(gy), ptr(idx), ptr(gx), B, H, W, Cc, k, s, p, stream_of(gy))),
+              "jpb_maxpool_bwd")
+        return gx, None, None, None
+
+
+def maxpool(x, k, s, p):
+    """nn.MaxPool2d(k, s, p) on a channels-last tensor (C % 4 == 0)."""
+    return _MaxPool.apply(x, k, s, p)

@@ -17,8 +17,10 @@ from . import conv as _conv
 CL = torch.channels_last
 
 BACKEND = {
-    "conv2d": "jpb",   # forward: tcgen05 implicit GEMM (csrc/conv_tc.cu); backward: library (interim) "batchnorm": "torch", "maxpool": "torch", "dropout": "torch", "image_prep": "torch",
-    "cvp_mlp": "torch", "cct_attention": "torch", "pose_head": "torch",
+    "conv2d": "jpb",        # tcgen05 implicit GEMM: forward, dgrad, wgrad (csrc/conv_tc.cu) + epilogue backward (elementwise.cu)
+    "maxpool": "jpb",       # csrc/pool.cu
+    "batchnorm": "torch",   # cuDNN batch-norm (NHWC) — next kernel to replace
+    "dropout": "torch", "image_prep": "torch", "cvp_mlp": "torch", "cct_attention": "torch", "pose_head": "torch",
 }
 
 
@@ -74,6 +76,9 @@ def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1
 
 def maxpool(x, k, stride, pad):
     _need_cuda(x)
+    if BACKEND["maxpool"] == "jpb" and x.shape[1] % 4 == 0:
+        from . import functional as JF
+        return JF.maxpool(x, k, stride, pad)
     return F.max_pool2d(x, k, stride, pad)
 
 

@@ -265,3 +265,19 @@ def test_photometric_full_size_vs_oracle_and_properties():
     lb = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=7, stream=1)[0].item()
     lc = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=8, stream=1)[0].item()
     assert la == lb and abs(la - loss.item()) < 1e-4 and abs(lc - loss.item()) < 1e-4
+
+
+@pytest.mark.parametrize("k,s,p,H,W,C", [(5, 1, 2, 12, 20, 8), (3, 2, 1, 16, 24, 16), (2, 2, 0, 8, 8, 128), (3, 2, 1, 15, 21, 4)])
+def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, C, H, W, generator=g)
+    x[0, :, 3:6, 3:6] = 1.5      # plateaus: ties must resolve to the first maximum, like ATen
+    x0 = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.max_pool2d(x0, k, s, p)
+    gy = torch.randn(ref.shape, generator=g)
+    ref.backward(gy)
+    x1 = D(x, dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got = JF.maxpool(x1, k, s, p)
+    assert torch.equal(got.cpu(), ref.detach())
+    got.backward(D(gy, dev))
+    assert (x1.grad.cpu() - x0.grad).abs().max().item() < 1e-6
