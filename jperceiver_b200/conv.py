@@ -16,6 +16,7 @@ from ._lib import check, ptr, stream_of
 
 CL = torch.channels_last
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3}
+SMALLN = True      # route 3x3 convolutions with <= 4 output channels to the CUDA-core kernels (csrc/conv_smalln.cu)
 BACKWARD = "jpb"   # "jpb": tcgen05 dgrad/wgrad kernels; "torch": library backward on a re-materialised input (debug)
 _TABLES: dict = {}
 
@@ -210,11 +211,44 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
     return torch.cat(parts, -1).permute(0, 3, 1, 2)
 
 
+def _is_smalln(weight, xs, stride, pad, residual):
+    N, Cin, kh, kw = weight.shape
+    return (N <= 4 and kh == 3 and kw == 3 and stride == 1 and pad == 1 and len(xs) == 1 and residual is None
+            and xs[0].shape[1] == Cin and Cin % 4 == 0 and N * 9 * Cin * 4 <= 48 * 1024)
+
+
+def smalln_fwd(x, up, weight, bias, reflect, act):
+    B, Cin, Hs, Ws = x.shape
+    N = weight.shape[0]
+    Ho, Wo = (2 * Hs, 2 * Ws) if up else (Hs, Ws)
+    out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=CL)
+    w = weight.detach().permute(0, 2, 3, 1)
+    w = w if w.is_contiguous() else w.contiguous()
+    check(_launch("conv_smalln_fwd", x, lambda: _lib.lib().jpb_conv3x3_smalln_fwd(
+        ptr(x), ptr(w), ptr(bias.detach()) if bias is not None else None, ptr(out), B, Hs, Ws, Cin, int(up), N, int(reflect), ACT[act],
+        stream_of(x))), "jpb_conv3x3_smalln_fwd")
+    return out
+
+
+def smalln_wgrad(x, up, dz, weight, reflect):
+    B, Cin, Hs, Ws = x.shape
+    N = weight.shape[0]
+    dw = torch.zeros(N, 3, 3, Cin, dtype=torch.float32, device=x.device)
+    check(_launch("conv_smalln_wgrad", x, lambda: _lib.lib().jpb_conv3x3_smalln_wgrad(
+        ptr(x), ptr(dz), ptr(dw), B, Hs, Ws, Cin, int(up), N, int(reflect), stream_of(x))), "jpb_conv3x3_smalln_wgrad")
+    return dw.permute(0, 3, 1, 2)
+
+
 class _ConvTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, weight, bias, residual, *xs):
         ups, stride, pad, reflect, act = cfg["ups"], cfg["stride"], cfg["pad"], cfg["reflect"], cfg["act"]
         xs = [x if x.is_contiguous(memory_format=CL) else x.contiguous(memory_format=CL) for x in xs]
+        if SMALLN and _is_smalln(weight, xs, stride, pad, residual):
+            out = smalln_fwd(xs[0], ups[0], weight, bias, reflect, act)
+            ctx.cfg = cfg
+            ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)
+            return out
         B = xs[0].shape[0]
         Hin = xs[0].shape[2] * (2 if ups[0] else 1)
         Win = xs[0].shape[3] * (2 if ups[0] else 1)
@@ -265,7 +299,12 @@ class _ConvTC(torch.autograd.Function):
         gxs = [None] * len(xs)
         if any(ctx.needs_input_grad[4:]):
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
-        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect) if ctx.needs_input_grad[1] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            if SMALLN and _is_smalln(weight, xs, stride, pad, residual):
+                gw = smalln_wgrad(xs[0], ups[0], _cl(dz), weight, reflect)
+            else:
+                gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect)
         return (None, gw, gb, gr) + tuple(gxs)
 
     @staticmethod
