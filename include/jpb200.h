@@ -191,13 +191,15 @@ typedef struct JpbConvWgradArgs {
 } JpbConvWgradArgs;
 int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
 
-/* ---- 3x3 stride-1 pad-1 convolutions with 1..4 output channels on the CUDA cores (disparity heads
- * depth_decoder.py:35-38, BEV topview heads layout_model.py:158).  x: [B,Hs,Ws,C] NHWC (read through a nearest 2x
- * up-sampling when up != 0), w / dw: [N][3][3][C], y / dz: [B,Ho,Wo,N].  dw is accumulated (+=).               */
-int jpb_conv3x3_smalln_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hs, int Ws, int C, int up,
-                           int N, int reflect, int act, void* stream);
-int jpb_conv3x3_smalln_wgrad(const float* x, const float* dz, float* dw, int B, int Hs, int Ws, int C, int up, int N, int reflect,
-                             void* stream);
+/* ---- 3x3 stride-1 pad-1 convolutions with 1..2 output channels on the CUDA cores (disparity heads
+ * depth_decoder.py:35-38, BEV topview heads layout_model.py:158), as nine 1x1 projections + a shift-and-add gather.
+ * x: [B,Hs,Ws,C] NHWC (read through a nearest 2x up-sampling when up != 0), w / dw: [N][3][3][C], y / dz: [B,Ho,Wo,N].
+ * work: [B*Hs*Ws][N*9] floats (forward: scratch; backward: ZERO-FILLED by the caller).  dw is accumulated (+=), dx is
+ * overwritten; either may be NULL.                                                                          */
+int jpb_conv3x3_smalln_fwd(const float* x, const float* w, const float* bias, float* y, float* work, int B, int Hs, int Ws, int C,
+                           int up, int N, int reflect, int act, void* stream);
+int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const float* dz, float* work, float* dw, float* dx, int B, int Hs, int Ws,
+                           int C, int up, int N, int reflect, void* stream);
 
 /* ---- backward of the convolution epilogue: dz = dy * act'(y) (act as in JpbConvArgs, from the OUTPUT y) and
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */

@@ -134,8 +134,8 @@ class _Signatures:
     jpb_conv2d_fwd = [C.POINTER(ConvArgs), V]
     jpb_conv2d_wgrad = [C.POINTER(ConvWgradArgs), V]
     jpb_act_bwd = [P, P, P, C.c_longlong, I, I, P, V]
-    jpb_conv3x3_smalln_fwd = [P, P, P, P, I, I, I, I, I, I, I, I, V]
-    jpb_conv3x3_smalln_wgrad = [P, P, P, I, I, I, I, I, I, I, V]
+    jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
+    jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]

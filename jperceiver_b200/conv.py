@@ -16,7 +16,7 @@ from ._lib import check, ptr, stream_of
 
 CL = torch.channels_last
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3}
-SMALLN = True      # route 3x3 convolutions with <= 4 output channels to the CUDA-core kernels (csrc/conv_smalln.cu)
+SMALLN = True      # route 3x3 convolutions with <= 2 output channels to the CUDA-core kernels (csrc/conv_smalln.cu)
 BACKWARD = "jpb"   # "jpb": tcgen05 dgrad/wgrad kernels; "torch": library backward on a re-materialised input (debug)
 _TABLES: dict = {}
 
@@ -213,8 +213,13 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
 
 def _is_smalln(weight, xs, stride, pad, residual):
     N, Cin, kh, kw = weight.shape
-    return (N <= 4 and kh == 3 and kw == 3 and stride == 1 and pad == 1 and len(xs) == 1 and residual is None
+    return (N <= 2 and kh == 3 and kw == 3 and stride == 1 and pad == 1 and len(xs) == 1 and residual is None
             and xs[0].shape[1] == Cin and Cin % 4 == 0 and N * 9 * Cin * 4 <= 48 * 1024)
+
+
+def _w_nhwc(weight):
+    w = weight.detach().permute(0, 2, 3, 1)
+    return w if w.is_contiguous() else w.contiguous()
 
 
 def smalln_fwd(x, up, weight, bias, reflect, act):
@@ -222,21 +227,26 @@ def smalln_fwd(x, up, weight, bias, reflect, act):
     N = weight.shape[0]
     Ho, Wo = (2 * Hs, 2 * Ws) if up else (Hs, Ws)
     out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=CL)
-    w = weight.detach().permute(0, 2, 3, 1)
-    w = w if w.is_contiguous() else w.contiguous()
+    work = torch.empty(B * Hs * Ws * N * 9, dtype=torch.float32, device=x.device)
+    w = _w_nhwc(weight)
     check(_launch("conv_smalln_fwd", x, lambda: _lib.lib().jpb_conv3x3_smalln_fwd(
-        ptr(x), ptr(w), ptr(bias.detach()) if bias is not None else None, ptr(out), B, Hs, Ws, Cin, int(up), N, int(reflect), ACT[act],
-        stream_of(x))), "jpb_conv3x3_smalln_fwd")
+        ptr(x), ptr(w), ptr(bias.detach()) if bias is not None else None, ptr(out), ptr(work), B, Hs, Ws, Cin, int(up), N, int(reflect),
+        ACT[act], stream_of(x))), "jpb_conv3x3_smalln_fwd")
     return out
 
 
-def smalln_wgrad(x, up, dz, weight, reflect):
+def smalln_bwd(x, up, dz, weight, reflect, want_dw=True, want_dx=True):
+    """(dw, dx) of the small-N convolution from dz (gradient w.r.t. the pre-activation output)."""
     B, Cin, Hs, Ws = x.shape
     N = weight.shape[0]
-    dw = torch.zeros(N, 3, 3, Cin, dtype=torch.float32, device=x.device)
-    check(_launch("conv_smalln_wgrad", x, lambda: _lib.lib().jpb_conv3x3_smalln_wgrad(
-        ptr(x), ptr(dz), ptr(dw), B, Hs, Ws, Cin, int(up), N, int(reflect), stream_of(x))), "jpb_conv3x3_smalln_wgrad")
-    return dw.permute(0, 3, 1, 2)
+    work = torch.zeros(B * Hs * Ws * N * 9, dtype=torch.float32, device=x.device)
+    dw = torch.zeros(N, 3, 3, Cin, dtype=torch.float32, device=x.device) if want_dw else None
+    dx = torch.empty_like(x, memory_format=CL) if want_dx else None
+    w = _w_nhwc(weight)
+    check(_launch("conv_smalln_bwd", x, lambda: _lib.lib().jpb_conv3x3_smalln_bwd(
+        ptr(x), ptr(w), ptr(dz), ptr(work), ptr(dw), ptr(dx), B, Hs, Ws, Cin, int(up), N, int(reflect), stream_of(x))),
+        "jpb_conv3x3_smalln_bwd")
+    return (dw.permute(0, 3, 1, 2) if want_dw else None), dx
 
 
 class _ConvTC(torch.autograd.Function):
@@ -293,18 +303,16 @@ class _ConvTC(torch.autograd.Function):
         N = weight.shape[0]
         dz, gb = act_bwd(gy, out, act, bias is not None)
         gr = dz if residual is not None else None
+        if SMALLN and _is_smalln(weight, xs, stride, pad, residual):
+            gw, gx = smalln_bwd(xs[0], ups[0], _cl(dz), weight, reflect, ctx.needs_input_grad[1], ctx.needs_input_grad[4])
+            return (None, gw, gb, gr, gx)
         dzp = dz
-        if N % 4:                                    # 1/2/6 output channels: pad dz so rows are whole 16-byte chunks
+        if N % 4:                                    # e.g. the 6-channel pose head: pad dz so rows are whole 16-byte chunks
             dzp = F.pad(dz, (0, 0, 0, 0, 0, _pad4(N) - N)).contiguous(memory_format=CL)
         gxs = [None] * len(xs)
         if any(ctx.needs_input_grad[4:]):
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
-        gw = None
-        if ctx.needs_input_grad[1]:
-            if SMALLN and _is_smalln(weight, xs, stride, pad, residual):
-                gw = smalln_wgrad(xs[0], ups[0], _cl(dz), weight, reflect)
-            else:
-                gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect)
+        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect) if ctx.needs_input_grad[1] else None
         return (None, gw, gb, gr) + tuple(gxs)
 
     @staticmethod

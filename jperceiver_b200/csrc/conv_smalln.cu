@@ -1,15 +1,22 @@
-// 3x3 convolutions with 1..4 output channels (the four disparity heads `dispL`, Cin = 256 read through a nearest 2x
-// up-sampling, sigmoid — depth_decoder.py:35-38,68; the four BEV `topview` heads, Cin = 16 -> 2 — layout_model.py:158)
-// on the CUDA cores.  As GEMMs these layers waste >= 94 % of the tensor-core N dimension and are bound by re-reading
-// the im2col matrix; here one warp owns an output pixel (forward) / one thread owns a channel (weight gradient), the
-// input is read through L1 once per tap and the weights sit in shared memory.
-//   forward : y[p][n] = act(bias[n] + sum_{tap,c} x[src(p,tap)][c] * w[n][tap][c])
-//   wgrad   : dw[n][tap][c] += sum_p dz[p][n] * x[src(p,tap)][c]
-// src() folds ReflectionPad2d(1) / zero padding and the nearest 2x up-sampling, as the tensor-core gather does.
+// 3x3 stride-1 pad-1 convolutions with 1..2 output channels (the four disparity heads `dispL`: Cin = 256 read
+// through a nearest 2x up-sampling, sigmoid — depth_decoder.py:35-38,68; the four BEV `topview` heads: Cin = 16 -> 2 —
+// layout_model.py:158) on the CUDA cores, in "project, then shift-and-add" form.
+//
+// As GEMMs these layers waste >= 94 % of the tensor-core N dimension and are bound by re-reading the im2col matrix
+// (9 x the input, at 4 x the pixel count when the input is up-sampled).  Because N is tiny, the 3x3 convolution is
+// re-associated as nine 1x1 projections of the SOURCE pixels followed by a gather over taps:
+//   forward : D[s][n,t] = sum_c x[s][c] w[n][t][c]              (reads x exactly once)
+//             y[p][n]   = act(bias[n] + sum_t D[src(p,t)][n,t])  (tiny)
+//   backward: G[s][n,t] = sum_{p : src(p,t) = s} dz[p][n]        (tiny, adjoint of the gather)
+//             dw[n][t][c] += sum_s x[s][c] G[s][n,t]             (reads x exactly once)
+//             dx[s][c]   = sum_{n,t} G[s][n,t] w[n][t][c]        (writes dx exactly once)
+// src(p,t) folds ReflectionPad2d(1) / zero padding and the nearest 2x up-sampling.
 #include "jpb_common.cuh"
 #include "../../include/jpb200.h"
 
 namespace {
+
+constexpr int MAXNT = 18;   // N * 9 with N <= 2
 
 struct SmallGeom {
   int B, Hs, Ws, C, up, Ho, Wo, N, reflect, act;
@@ -31,101 +38,164 @@ __device__ __forceinline__ float small_act(float v, int act) {
   return v;
 }
 
-// one "warp" (32 consecutive threads; a single emulated thread covers all lanes) per output pixel
-__global__ void __launch_bounds__(256) smalln_fwd_kernel(const float* x, const float* w, const float* bias, float* y, SmallGeom g) {
-  JPB_DYN_SMEM(float, sw);   // [N][9][C]
-  const int KW = 9 * g.C;
-  for (int i = JPB_TID; i < g.N * KW; i += JPB_NT) sw[i] = w[i];
-  __syncthreads();
 #ifdef JPB_HOST_EMU
-  const int lanes = 1, lane = 0, warps_per_block = 1, warp = 0;
+#define SM_LANES 1
+#define SM_LANE 0
+#define SM_WARPS 1
+#define SM_WARP 0
 #else
-  const int lanes = 32, lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5;
+#define SM_LANES 32
+#define SM_LANE (threadIdx.x & 31)
+#define SM_WARPS (blockDim.x >> 5)
+#define SM_WARP (threadIdx.x >> 5)
 #endif
+
+// D[s][n*9+t] = sum_c x[s][c] * w[n][t][c]; one warp per source pixel, lanes stride the channels in float4s
+__global__ void __launch_bounds__(256) smalln_project_kernel(const float* x, const float* w, float* D, long long S, int C, int NT) {
+  JPB_DYN_SMEM(float, sw);   // [NT][C]
+  for (int i = JPB_TID; i < NT * C; i += JPB_NT) sw[i] = w[i];
+  __syncthreads();
+  for (long long s = (long long)blockIdx.x * SM_WARPS + SM_WARP; s < S; s += (long long)gridDim.x * SM_WARPS) {
+    float acc[MAXNT];
+    for (int j = 0; j < MAXNT; ++j) acc[j] = 0.f;
+    const float* xp = x + (size_t)s * C;
+    for (int c = SM_LANE * 4; c < C; c += SM_LANES * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + c);
+      for (int j = 0; j < NT; ++j) {
+        const float* wj = sw + j * C + c;
+        acc[j] += v.x * wj[0] + v.y * wj[1] + v.z * wj[2] + v.w * wj[3];
+      }
+    }
+#ifndef JPB_HOST_EMU
+    for (int j = 0; j < NT; ++j)
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+#endif
+    if (SM_LANE == 0)
+      for (int j = 0; j < NT; ++j) D[s * NT + j] = acc[j];
+  }
+}
+
+// y[p][n] = act(bias[n] + sum_t D[src(p,t)][n*9+t])
+__global__ void __launch_bounds__(256) smalln_gather_kernel(const float* D, const float* bias, float* y, SmallGeom g) {
   const long long P = (long long)g.B * g.Ho * g.Wo;
-  for (long long p = (long long)blockIdx.x * warps_per_block + warp; p < P; p += (long long)gridDim.x * warps_per_block) {
+  const int NT = g.N * 9;
+  for (long long p = (long long)blockIdx.x * JPB_NT + JPB_TID; p < P; p += (long long)gridDim.x * JPB_NT) {
     const int b = (int)(p / (g.Ho * g.Wo));
     const int rem = (int)(p - (long long)b * g.Ho * g.Wo);
     const int oy = rem / g.Wo, ox = rem - oy * g.Wo;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[2] = {0.f, 0.f};
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
         int sy, sx;
         if (!small_src(g, oy, ox, ky, kx, sy, sx)) continue;
-        const float* xp = x + ((size_t)(b * g.Hs + sy) * g.Ws + sx) * g.C;
-        const float* wp = sw + (ky * 3 + kx) * g.C;
-        for (int c = lane * 4; c < g.C; c += lanes * 4) {
-          const float4 v = *reinterpret_cast<const float4*>(xp + c);
-          for (int n = 0; n < g.N; ++n) {
-            const float* wn = wp + n * KW + c;
-            acc[n] += v.x * wn[0] + v.y * wn[1] + v.z * wn[2] + v.w * wn[3];
-          }
-        }
+        const float* d = D + ((size_t)(b * g.Hs + sy) * g.Ws + sx) * NT + ky * 3 + kx;
+        for (int n = 0; n < g.N; ++n) acc[n] += d[n * 9];
       }
-#ifndef JPB_HOST_EMU
-    for (int n = 0; n < g.N; ++n)
-      for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-#endif
-    if (lane == 0)
-      for (int n = 0; n < g.N; ++n) y[p * g.N + n] = small_act(acc[n] + (bias ? bias[n] : 0.f), g.act);
+    for (int n = 0; n < g.N; ++n) y[p * g.N + n] = small_act(acc[n] + (bias ? bias[n] : 0.f), g.act);
   }
 }
 
-// one thread per channel (blockDim.x == C rounded up to 32); each block reduces a slab of pixels
-__global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* x, const float* dz, float* dw, SmallGeom g) {
+// G[src(p,t)][n*9+t] += dz[p][n]   (G zero-filled by the caller)
+__global__ void __launch_bounds__(256) smalln_adjoint_kernel(const float* dz, float* G, SmallGeom g) {
   const long long P = (long long)g.B * g.Ho * g.Wo;
-  const long long per = (P + gridDim.x - 1) / gridDim.x;
-  const long long p0 = (long long)blockIdx.x * per;
-  long long p1 = p0 + per;
-  if (p1 > P) p1 = P;
-  for (int c = JPB_TID; c < g.C; c += JPB_NT) {
-    float acc[4][9];
-    for (int n = 0; n < 4; ++n)
-      for (int t = 0; t < 9; ++t) acc[n][t] = 0.f;
-    for (long long p = p0; p < p1; ++p) {
-      const int b = (int)(p / (g.Ho * g.Wo));
-      const int rem = (int)(p - (long long)b * g.Ho * g.Wo);
-      const int oy = rem / g.Wo, ox = rem - oy * g.Wo;
-      float d[4];
-      for (int n = 0; n < g.N; ++n) d[n] = dz[p * g.N + n];
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) {
-          int sy, sx;
-          if (!small_src(g, oy, ox, ky, kx, sy, sx)) continue;
-          const float xv = x[((size_t)(b * g.Hs + sy) * g.Ws + sx) * g.C + c];
-          for (int n = 0; n < g.N; ++n) acc[n][ky * 3 + kx] += d[n] * xv;
-        }
-    }
-    if (p1 > p0)
-      for (int n = 0; n < g.N; ++n)
-        for (int t = 0; t < 9; ++t) atomicAdd(&dw[(size_t)(n * 9 + t) * g.C + c], acc[n][t]);
+  const int NT = g.N * 9;
+  for (long long p = (long long)blockIdx.x * JPB_NT + JPB_TID; p < P; p += (long long)gridDim.x * JPB_NT) {
+    const int b = (int)(p / (g.Ho * g.Wo));
+    const int rem = (int)(p - (long long)b * g.Ho * g.Wo);
+    const int oy = rem / g.Wo, ox = rem - oy * g.Wo;
+    float d[2];
+    for (int n = 0; n < g.N; ++n) d[n] = dz[p * g.N + n];
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        int sy, sx;
+        if (!small_src(g, oy, ox, ky, kx, sy, sx)) continue;
+        float* t = G + ((size_t)(b * g.Hs + sy) * g.Ws + sx) * NT + ky * 3 + kx;
+        for (int n = 0; n < g.N; ++n) atomicAdd(t + n * 9, d[n]);
+      }
   }
 }
+
+// dw[j][c] += sum_s x[s][c] * G[s][j]; thread owns 4 channels, threadIdx.y strides the block's slab of source pixels
+__global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* x, const float* G, float* dw, long long S, int C, int NT) {
+  const int C4 = C >> 2;
+  const int lanes_s = JPB_NT / C4 > 0 ? JPB_NT / C4 : 1;   // threads striding the pixel dimension
+  const long long per = (S + gridDim.x - 1) / gridDim.x;
+  const long long s0 = (long long)blockIdx.x * per;
+  long long s1 = s0 + per;
+  if (s1 > S) s1 = S;
+  for (int u = JPB_TID; u < C4 * lanes_s; u += JPB_NT) {
+    const int cg = u % C4, ls = u / C4;           // channel group / pixel lane of this thread
+    for (int j0 = 0; j0 < NT; j0 += 9) {          // one output channel (9 taps) at a time: 36 accumulators
+      float acc[9][4];
+      for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+      for (long long s = s0 + ls; s < s1; s += lanes_s) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)s * C + cg * 4);
+        const float* gp = G + s * NT + j0;
+        for (int t = 0; t < 9; ++t) {
+          const float gv = gp[t];
+          acc[t][0] += gv * v.x; acc[t][1] += gv * v.y; acc[t][2] += gv * v.z; acc[t][3] += gv * v.w;
+        }
+      }
+      if (s1 > s0)
+        for (int t = 0; t < 9; ++t)
+          for (int q = 0; q < 4; ++q) atomicAdd(&dw[(size_t)(j0 + t) * C + cg * 4 + q], acc[t][q]);
+    }
+  }
+}
+
+// dx[s][c] = sum_j G[s][j] * w[j][c]
+__global__ void __launch_bounds__(256) smalln_dgrad_kernel(const float* G, const float* w, float* dx, long long S, int C, int NT) {
+  JPB_DYN_SMEM(float, sw);   // [NT][C]
+  for (int i = JPB_TID; i < NT * C; i += JPB_NT) sw[i] = w[i];
+  __syncthreads();
+  const int C4 = C >> 2;
+  const long long total = S * C4;
+  for (long long e = (long long)blockIdx.x * JPB_NT + JPB_TID; e < total; e += (long long)gridDim.x * JPB_NT) {
+    const long long s = e / C4;
+    const int c = (int)(e - s * C4) * 4;
+    const float* gp = G + s * NT;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NT; ++j) {
+      const float gv = gp[j];
+      const float* wj = sw + j * C + c;
+      o.x += gv * wj[0]; o.y += gv * wj[1]; o.z += gv * wj[2]; o.w += gv * wj[3];
+    }
+    *reinterpret_cast<float4*>(dx + (size_t)s * C + c) = o;
+  }
+}
+
+inline unsigned sm_grid(long long work, int per_block, int cap = 148 * 8) {
+  long long g = (work + per_block - 1) / per_block;
+  if (g > cap) g = cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+inline bool small_ok(int N, int C) { return N >= 1 && N <= 2 && C >= 4 && (C & 3) == 0 && (size_t)N * 9 * C * 4 <= 48 * 1024; }
 
 }  // namespace
 
-extern "C" int jpb_conv3x3_smalln_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hs, int Ws, int C, int up,
-                                      int N, int reflect, int act, void* stream) {
-  if (!x || !w || !y || N < 1 || N > 4 || (C & 3) || C < 4) return JPB_ERR_ARG;
+extern "C" int jpb_conv3x3_smalln_fwd(const float* x, const float* w, const float* bias, float* y, float* work, int B, int Hs, int Ws,
+                                      int C, int up, int N, int reflect, int act, void* stream) {
+  if (!x || !w || !y || !work || !small_ok(N, C)) return JPB_ERR_ARG;
   SmallGeom g{B, Hs, Ws, C, up, up ? 2 * Hs : Hs, up ? 2 * Ws : Ws, N, reflect, act};
-  const size_t smem = (size_t)N * 9 * C * sizeof(float);
-  if (smem > 48 * 1024) return JPB_ERR_UNSUPPORTED;
-  const long long P = (long long)B * g.Ho * g.Wo;
-  long long blocks = (P + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  JPB_LAUNCH(smalln_fwd_kernel, dim3((unsigned)blocks), dim3(256), smem, (cudaStream_t)stream, x, w, bias, y, g);
+  const long long S = (long long)B * Hs * Ws;
+  JPB_LAUNCH(smalln_project_kernel, dim3(sm_grid(S, 8)), dim3(256), (size_t)N * 9 * C * 4, (cudaStream_t)stream, x, w, work, S, C, N * 9);
+  JPB_LAUNCH(smalln_gather_kernel, dim3(sm_grid((long long)B * g.Ho * g.Wo, 256)), dim3(256), 0, (cudaStream_t)stream, work, bias, y, g);
   return jpb_status();
 }
 
-extern "C" int jpb_conv3x3_smalln_wgrad(const float* x, const float* dz, float* dw, int B, int Hs, int Ws, int C, int up, int N, int reflect,
-                                        void* stream) {
-  if (!x || !dz || !dw || N < 1 || N > 4 || C < 1) return JPB_ERR_ARG;
+extern "C" int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const float* dz, float* work, float* dw, float* dx, int B, int Hs,
+                                      int Ws, int C, int up, int N, int reflect, void* stream) {
+  if (!x || !w || !dz || !work || !small_ok(N, C) || (!dw && !dx)) return JPB_ERR_ARG;
   SmallGeom g{B, Hs, Ws, C, up, up ? 2 * Hs : Hs, up ? 2 * Ws : Ws, N, reflect, 0};
-  const long long P = (long long)B * g.Ho * g.Wo;
-  long long blocks = P / 256 + 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  int threads = ((C + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  JPB_LAUNCH(smalln_wgrad_kernel, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream, x, dz, dw, g);
+  const long long S = (long long)B * Hs * Ws;
+  JPB_LAUNCH(smalln_adjoint_kernel, dim3(sm_grid((long long)B * g.Ho * g.Wo, 256)), dim3(256), 0, (cudaStream_t)stream, dz, work, g);
+  if (dw) {
+    int threads = 256;
+    if (C / 4 > 256) return JPB_ERR_UNSUPPORTED;
+    JPB_LAUNCH(smalln_wgrad_kernel, dim3(sm_grid(S, 64, 148 * 4)), dim3(threads), 0, (cudaStream_t)stream, x, work, dw, S, C, N * 9);
+  }
+  if (dx)
+    JPB_LAUNCH(smalln_dgrad_kernel, dim3(sm_grid(S * (C / 4), 256)), dim3(256), (size_t)N * 9 * C * 4, (cudaStream_t)stream, work, w, dx, S, C, N * 9);
   return jpb_status();
 }

@@ -283,17 +283,17 @@ def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
     assert (x1.grad.cpu() - x0.grad).abs().max().item() < 1e-6
 
 
-@pytest.mark.parametrize("C,N,up,reflect,act", [(256, 1, 1, 1, "sigmoid"), (16, 2, 0, 1, "none"), (32, 4, 0, 0, "leaky"), (64, 1, 1, 0, "none")])
-def test_small_n_conv_forward_and_wgrad_vs_torch(dev, C, N, up, reflect, act):
-    """The CUDA-core 3x3 kernels for the 1-/2-channel heads (disparity, topview) against the library convolution."""
-    import ctypes as Cc
+@pytest.mark.parametrize("C,N,up,reflect,act", [(256, 1, 1, 1, "sigmoid"), (16, 2, 0, 1, "none"), (32, 2, 0, 0, "leaky"), (64, 1, 1, 0, "none")])
+def test_small_n_conv_forward_backward_vs_torch(dev, C, N, up, reflect, act):
+    """The CUDA-core project / shift-and-add kernels for the 1-/2-channel heads (disparity, topview) against the
+    library convolution: forward, weight gradient and data gradient."""
     from jperceiver_b200 import conv as JC
     g = torch.Generator().manual_seed(6)
     B, Hs, Ws = 2, 6, 10
     x = torch.randn(B, C, Hs, Ws, generator=g)
     w = torch.randn(N, C, 3, 3, generator=g) / (C * 9) ** 0.5
     b = torch.randn(N, generator=g)
-    x0, w0 = x.clone(), w.clone().requires_grad_(True)
+    x0, w0 = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
     ref = JC._torch_conv([x0], [bool(up)], w0, b, 1, 1, bool(reflect), act, None)
     x1 = D(x, dev).contiguous(memory_format=torch.channels_last)
     w1 = D(w, dev).contiguous(memory_format=torch.channels_last)
@@ -302,5 +302,6 @@ def test_small_n_conv_forward_and_wgrad_vs_torch(dev, C, N, up, reflect, act):
     z = JC._torch_conv([x0], [bool(up)], w0, b, 1, 1, bool(reflect), "none", None)
     dz = torch.randn(z.shape, generator=g)
     z.backward(dz)
-    gw = JC.smalln_wgrad(x1, bool(up), D(dz, dev).contiguous(memory_format=torch.channels_last), w1, bool(reflect))
+    gw, gx = JC.smalln_bwd(x1, bool(up), D(dz, dev).contiguous(memory_format=torch.channels_last), w1, bool(reflect))
     assert (gw.cpu() - w0.grad).abs().max().item() <= 2e-5 * max(1.0, w0.grad.abs().max().item())
+    assert (gx.cpu() - x0.grad).abs().max().item() <= 2e-5 * max(1.0, x0.grad.abs().max().item())
