@@ -55,6 +55,22 @@ __global__ void __launch_bounds__(256) smalln_project_kernel(const float* x, con
   JPB_DYN_SMEM(float, sw);   // [NT][C]
   for (int i = JPB_TID; i < NT * C; i += JPB_NT) sw[i] = w[i];
   __syncthreads();
+  if (C <= 32) {   // narrow inputs (topview heads, C = 16): one thread per source pixel, weights broadcast from shared memory
+    for (long long s = (long long)blockIdx.x * JPB_NT + JPB_TID; s < S; s += (long long)gridDim.x * JPB_NT) {
+      float acc[MAXNT];
+      for (int j = 0; j < MAXNT; ++j) acc[j] = 0.f;
+      const float* xp = x + (size_t)s * C;
+      for (int c = 0; c < C; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xp + c);
+        for (int j = 0; j < NT; ++j) {
+          const float* wj = sw + j * C + c;
+          acc[j] += v.x * wj[0] + v.y * wj[1] + v.z * wj[2] + v.w * wj[3];
+        }
+      }
+      for (int j = 0; j < NT; ++j) D[s * NT + j] = acc[j];
+    }
+    return;
+  }
   for (long long s = (long long)blockIdx.x * SM_WARPS + SM_WARP; s < S; s += (long long)gridDim.x * SM_WARPS) {
     float acc[MAXNT];
     for (int j = 0; j < MAXNT; ++j) acc[j] = 0.f;
@@ -115,17 +131,20 @@ __global__ void __launch_bounds__(256) smalln_adjoint_kernel(const float* dz, fl
   }
 }
 
-// dw[j][c] += sum_s x[s][c] * G[s][j]; thread owns 4 channels, threadIdx.y strides the block's slab of source pixels
+// dw[j][c] += sum_s x[s][c] * G[s][j]; a thread owns 4 channels and one of the block's pixel lanes; partial sums are
+// reduced across pixel lanes in shared memory so each block issues one atomic per (tap, channel)
 __global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* x, const float* G, float* dw, long long S, int C, int NT) {
+  JPB_DYN_SMEM(float, part);   // [36][U], U = C4 * lanes_s <= 256
   const int C4 = C >> 2;
-  const int lanes_s = JPB_NT / C4 > 0 ? JPB_NT / C4 : 1;   // threads striding the pixel dimension
+  const int lanes_s = 256 / C4 > 0 ? 256 / C4 : 1;   // pixel lanes (the launch uses 256 threads; emulation loops over u)
+  const int U = C4 * lanes_s;
   const long long per = (S + gridDim.x - 1) / gridDim.x;
   const long long s0 = (long long)blockIdx.x * per;
   long long s1 = s0 + per;
   if (s1 > S) s1 = S;
-  for (int u = JPB_TID; u < C4 * lanes_s; u += JPB_NT) {
-    const int cg = u % C4, ls = u / C4;           // channel group / pixel lane of this thread
-    for (int j0 = 0; j0 < NT; j0 += 9) {          // one output channel (9 taps) at a time: 36 accumulators
+  for (int j0 = 0; j0 < NT; j0 += 9) {            // one output channel (9 taps) at a time: 36 accumulators per thread
+    for (int u = JPB_TID; u < U; u += JPB_NT) {
+      const int cg = u % C4, ls = u / C4;
       float acc[9][4];
       for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
       for (long long s = s0 + ls; s < s1; s += lanes_s) {
@@ -136,10 +155,18 @@ __global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* x, const
           acc[t][0] += gv * v.x; acc[t][1] += gv * v.y; acc[t][2] += gv * v.z; acc[t][3] += gv * v.w;
         }
       }
-      if (s1 > s0)
-        for (int t = 0; t < 9; ++t)
-          for (int q = 0; q < 4; ++q) atomicAdd(&dw[(size_t)(j0 + t) * C + cg * 4 + q], acc[t][q]);
+      for (int t = 0; t < 9; ++t)
+        for (int q = 0; q < 4; ++q) part[(t * 4 + q) * U + u] = acc[t][q];
     }
+    __syncthreads();
+    for (int i = JPB_TID; i < 9 * C; i += JPB_NT) {
+      const int t = i / C, c = i - t * C;
+      const float* pp = part + (t * 4 + (c & 3)) * U + (c >> 2);
+      float sum = 0.f;
+      for (int ls = 0; ls < lanes_s; ++ls) sum += pp[ls * C4];
+      if (s1 > s0) atomicAdd(&dw[(size_t)(j0 + t) * C + c], sum);
+    }
+    __syncthreads();
   }
 }
 
@@ -179,7 +206,7 @@ extern "C" int jpb_conv3x3_smalln_fwd(const float* x, const float* w, const floa
   if (!x || !w || !y || !work || !small_ok(N, C)) return JPB_ERR_ARG;
   SmallGeom g{B, Hs, Ws, C, up, up ? 2 * Hs : Hs, up ? 2 * Ws : Ws, N, reflect, act};
   const long long S = (long long)B * Hs * Ws;
-  JPB_LAUNCH(smalln_project_kernel, dim3(sm_grid(S, 8)), dim3(256), (size_t)N * 9 * C * 4, (cudaStream_t)stream, x, w, work, S, C, N * 9);
+  JPB_LAUNCH(smalln_project_kernel, dim3(sm_grid(S, C <= 32 ? 256 : 8)), dim3(256), (size_t)N * 9 * C * 4, (cudaStream_t)stream, x, w, work, S, C, N * 9);
   JPB_LAUNCH(smalln_gather_kernel, dim3(sm_grid((long long)B * g.Ho * g.Wo, 256)), dim3(256), 0, (cudaStream_t)stream, work, bias, y, g);
   return jpb_status();
 }
@@ -191,9 +218,10 @@ extern "C" int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const floa
   const long long S = (long long)B * Hs * Ws;
   JPB_LAUNCH(smalln_adjoint_kernel, dim3(sm_grid((long long)B * g.Ho * g.Wo, 256)), dim3(256), 0, (cudaStream_t)stream, dz, work, g);
   if (dw) {
-    int threads = 256;
     if (C / 4 > 256) return JPB_ERR_UNSUPPORTED;
-    JPB_LAUNCH(smalln_wgrad_kernel, dim3(sm_grid(S, 64, 148 * 4)), dim3(threads), 0, (cudaStream_t)stream, x, work, dw, S, C, N * 9);
+    const int C4 = C / 4, lanes_s = 256 / C4 > 0 ? 256 / C4 : 1;
+    JPB_LAUNCH(smalln_wgrad_kernel, dim3(sm_grid(S, 256, 148 * 2)), dim3(256), (size_t)36 * C4 * lanes_s * sizeof(float), (cudaStream_t)stream,
+               x, work, dw, S, C, N * 9);
   }
   if (dx)
     JPB_LAUNCH(smalln_dgrad_kernel, dim3(sm_grid(S * (C / 4), 256)), dim3(256), (size_t)N * 9 * C * 4, (cudaStream_t)stream, work, w, dx, S, C, N * 9);

@@ -2,8 +2,8 @@
 set -x
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_conv.py tests/test_losses.py -m gpu -q -x > gpurun_out/conv_test.log 2>&1; tail -3 gpurun_out/conv_test.log
-python tools/bench_conv.py > gpurun_out/conv_bench.jsonl 2> gpurun_out/conv_bench.err; cat gpurun_out/conv_bench.jsonl; tail -3 gpurun_out/conv_bench.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 9 -c 3 -o gpurun_out/conv_prof python tools/bench_conv.py iconv1 1 > gpurun_out/ncu_conv.log 2>&1; tail -2 gpurun_out/ncu_conv.log
+
+
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; python -c "
 import json
 d=json.loads(open('gpurun_out/bench_n1.json').read())
