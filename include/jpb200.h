@@ -205,6 +205,17 @@ int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const float* dz, floa
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */
 int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int C, int act, float* dbias, void* stream);
 
+/* ---- BatchNorm2d (training: per-GPU batch statistics) fused with the residual add and ReLU that follow it
+ * (resnet.py:28-45, layout_model.py:146-158).  x, res, y, dy, dx, dres: [rows][C] NHWC, C % 4 == 0.
+ * stat: [2][C] floats (mean, 1/sqrt(var+eps)) written by the forward and read by the backward; acc: [2][C] doubles,
+ * ZERO-FILLED by the caller before each call.  running_* are updated in place (momentum, unbiased variance).    */
+int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream);
+int jpb_bn_eval_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* stat, int relu, float* y,
+                    long long rows, int C, void* stream);
+int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
+                     float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream);
+
 /* ---- NHWC max pooling (nn.MaxPool2d(k, s, p); layers.py:191, resnet.py:91, layout_model.py:84) --------------
  * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.               */
 int jpb_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, int k, int s, int p, void* stream);

@@ -137,6 +137,9 @@ class _Signatures:
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]
+    jpb_bn_train_fwd = [P, P, P, P, P, P, F, F, I, P, P, P, C.c_longlong, I, V]
+    jpb_bn_eval_fwd = [P, P, P, P, P, I, P, C.c_longlong, I, V]
+    jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, P, C.c_longlong, I, V]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
 

@@ -1,0 +1,165 @@
+// Training-mode BatchNorm2d on NHWC fp32, fused with the residual add and ReLU that follow it in every ResNet block
+// (resnet.py:28-45: out = relu(bn2(conv2(.)) + residual)) and layout-decoder stage (layout_model.py:146-158).
+// Per-GPU batch statistics (no SyncBN, as the reference), running statistics updated in place with the unbiased variance.
+//   forward : stats   acc[c] += (sum x, sum x^2)                       one pass over x
+//             apply   y = relu?((x-mean)*rstd*gamma + beta (+ res))     one pass; block 0 also updates running stats
+//   backward: reduce  acc[c] += (sum g, sum g*xhat),  g = dy * [y > 0]  one pass over (dy, x, y)
+//             apply   dx = gamma*rstd*(g - s1/n - xhat*s2/n), dres = g   one pass
+// The library path needs separate kernels for BN, the add and the ReLU in each direction.
+#include "jpb_common.cuh"
+#include "../../include/jpb200.h"
+
+namespace {
+
+// column sums of two per-element quantities over a [rows][C] matrix, accumulated into double acc[2][C].
+// MODE 0: (x, x*x)    MODE 1: (g, g*xhat) with g = dy*[y>0 or no relu], xhat = (x-mean)*rstd
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const float* dy, const float* y, const float* stat, long long rows,
+                                                       int C, int relu, double* acc) {
+  JPB_DYN_SMEM(float, part);   // [2][256]
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per;
+  long long r1 = r0 + per;
+  if (r1 > rows) r1 = rows;
+  const int Ct = C < 256 ? C : 256;                 // channels covered per pass
+  const int lanes_r = 256 / Ct > 0 ? 256 / Ct : 1;  // row lanes
+  const int U = Ct * lanes_r;
+  for (int cbase = 0; cbase < C; cbase += Ct) {
+    for (int u = JPB_TID; u < U; u += JPB_NT) {
+      const int c = cbase + u % Ct, lr = u / Ct;
+      float s1 = 0.f, s2 = 0.f;
+      if (c < C) {
+        float mean = 0.f, rstd = 1.f;
+        if (MODE == 1) { mean = stat[c]; rstd = stat[C + c]; }
+        for (long long r = r0 + lr; r < r1; r += lanes_r) {
+          const long long i = r * C + c;
+          if (MODE == 0) {
+            const float v = x[i];
+            s1 += v; s2 += v * v;
+          } else {
+            float g = dy[i];
+            if (relu && !(y[i] > 0.f)) g = 0.f;
+            s1 += g; s2 += g * ((x[i] - mean) * rstd);
+          }
+        }
+      }
+      part[u] = s1; part[256 + u] = s2;
+    }
+    __syncthreads();
+    for (int c = JPB_TID; c < Ct; c += JPB_NT) {
+      if (cbase + c < C && r1 > r0) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int lr = 0; lr < lanes_r; ++lr) { s1 += part[lr * Ct + c]; s2 += part[256 + lr * Ct + c]; }
+        atomicAdd(&acc[cbase + c], (double)s1);
+        atomicAdd(&acc[C + cbase + c], (double)s2);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// finalise batch statistics: stat = (mean, rstd); running stats updated (momentum m, unbiased variance)
+__global__ void bn_finalize_kernel(const double* acc, long long rows, int C, float eps, float momentum, float* stat, float* running_mean,
+                                   float* running_var) {
+  for (int c = blockIdx.x * JPB_NT + JPB_TID; c < C; c += gridDim.x * JPB_NT) {
+    const double mean = acc[c] / (double)rows;
+    double var = acc[C + c] / (double)rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[c] = (float)mean;
+    stat[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const float* res, const float* stat, const float* gamma, const float* beta,
+                                                      float* y, long long n4, int C, int relu) {
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n4; i += (long long)gridDim.x * JPB_NT) {
+    const int c = (int)((i * 4) % C);
+    const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (res) { const float4 q = *reinterpret_cast<const float4*>(res + i * 4); r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
+    for (int k = 0; k < 4; ++k) {
+      float t = (o[k] - stat[c + k]) * stat[C + c + k] * gamma[c + k] + beta[c + k] + r[k];
+      if (relu && !(t > 0.f)) t = 0.f;
+      o[k] = t;
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* x, const float* dy, const float* y, const float* stat, const float* gamma,
+                                                          const double* acc, float* dx, float* dres, long long rows, long long n4, int C, int relu) {
+  const double inv_n = 1.0 / (double)rows;
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n4; i += (long long)gridDim.x * JPB_NT) {
+    const int c = (int)((i * 4) % C);
+    const float4 xv = *reinterpret_cast<const float4*>(x + i * 4);
+    const float4 gv = *reinterpret_cast<const float4*>(dy + i * 4);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, g[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
+    if (relu) {
+      const float4 yv = *reinterpret_cast<const float4*>(y + i * 4);
+      if (!(yv.x > 0.f)) g[0] = 0.f;
+      if (!(yv.y > 0.f)) g[1] = 0.f;
+      if (!(yv.z > 0.f)) g[2] = 0.f;
+      if (!(yv.w > 0.f)) g[3] = 0.f;
+    }
+    for (int k = 0; k < 4; ++k) {
+      const float mean = stat[c + k], rstd = stat[C + c + k];
+      const float xh = (xs[k] - mean) * rstd;
+      const float m1 = (float)(acc[c + k] * inv_n), m2 = (float)(acc[C + c + k] * inv_n);
+      o[k] = gamma[c + k] * rstd * (g[k] - m1 - xh * m2);
+    }
+    *reinterpret_cast<float4*>(dx + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (dres) *reinterpret_cast<float4*>(dres + i * 4) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+}
+
+// dgamma = s2, dbeta = s1
+__global__ void bn_param_grad_kernel(const double* acc, int C, float* dgamma, float* dbeta) {
+  for (int c = blockIdx.x * JPB_NT + JPB_TID; c < C; c += gridDim.x * JPB_NT) {
+    dbeta[c] = (float)acc[c];
+    dgamma[c] = (float)acc[C + c];
+  }
+}
+
+inline unsigned bn_grid(long long work, int per_block, int cap) {
+  long long g = (work + per_block - 1) / per_block;
+  if (g > cap) g = cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream) {
+  if (!x || !gamma || !beta || !y || !stat || !acc || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(bn_grid(rows, 128, 148 * 4)), dim3(256), 2 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, acc);
+  JPB_LAUNCH(bn_finalize_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, rows, C, eps, momentum, stat, running_mean, running_var);
+  const long long n4 = rows * C / 4;
+  JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, res, stat, gamma, beta, y, n4, C, relu);
+  return jpb_status();
+}
+
+extern "C" int jpb_bn_eval_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* stat, int relu, float* y,
+                               long long rows, int C, void* stream) {
+  if (!x || !gamma || !beta || !y || !stat || rows < 1 || (C & 3)) return JPB_ERR_ARG;
+  const long long n4 = rows * C / 4;
+  JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, (cudaStream_t)stream, x, res, stat, gamma, beta, y, n4, C, relu);
+  return jpb_status();
+}
+
+extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
+                                float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream) {
+  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !acc || (relu && !y) || (C & 3)) return JPB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(bn_grid(rows, 128, 148 * 4)), dim3(256), 2 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, acc);
+  JPB_LAUNCH(bn_param_grad_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, C, dgamma, dbeta);
+  const long long n4 = rows * C / 4;
+  JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, acc, dx, dres, rows, n4, C, relu);
+  return jpb_status();
+}

@@ -362,3 +362,60 @@ class _MaxPool(torch.autograd.Function):
 def maxpool(x, k, s, p):
     """nn.MaxPool2d(k, s, p) on a channels-last tensor (C % 4 == 0)."""
     return _MaxPool.apply(x, k, s, p)
+
+
+# --------------------------------------------------------------------------------------------------
+# BatchNorm2d (+ residual) (+ ReLU), NHWC
+# --------------------------------------------------------------------------------------------------
+def _clast(t):
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+class _BNTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        x = _clast(x)
+        res = _clast(res) if res is not None else None
+        B, Cc, H, W = x.shape
+        rows = B * H * W
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        stat = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
+        acc = torch.zeros(2 * Cc, dtype=torch.float64, device=x.device)
+        check(_launch("bn_fwd", x, lambda: _lib.lib().jpb_bn_train_fwd(
+            ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(running_mean), ptr(running_var), float(momentum), float(eps),
+            int(relu), ptr(y), ptr(stat), ptr(acc), rows, Cc, stream_of(x))), "jpb_bn_train_fwd")
+        ctx.save_for_backward(x, y if relu else None, stat, gamma)
+        ctx.cfg = (rows, Cc, int(relu), res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, stat, gamma = ctx.saved_tensors
+        rows, Cc, relu, has_res = ctx.cfg
+        gy = _clast(gy)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and relu) else None
+        dgamma = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        acc = torch.zeros(2 * Cc, dtype=torch.float64, device=x.device)
+        check(_launch("bn_bwd", x, lambda: _lib.lib().jpb_bn_train_bwd(
+            ptr(x), ptr(gy), ptr(y), ptr(stat), ptr(gamma.detach()), relu, ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta), ptr(acc), rows, Cc,
+            stream_of(x))), "jpb_bn_train_bwd")
+        if has_res and not relu:
+            dres = gy
+        return dx, dres, dgamma, dbeta, None, None, None, None, None
+
+
+def batchnorm_train(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    return _BNTrain.apply(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu)
+
+
+def batchnorm_eval(x, res, gamma, beta, running_mean, running_var, eps, relu):
+    x = _clast(x)
+    res = _clast(res) if res is not None else None
+    B, Cc, H, W = x.shape
+    stat = torch.cat([running_mean, torch.rsqrt(running_var + eps)]).float().contiguous()
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    check(_launch("bn_eval", x, lambda: _lib.lib().jpb_bn_eval_fwd(ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(stat),
+                                                                   int(relu), ptr(y), B * H * W, Cc, stream_of(x))), "jpb_bn_eval_fwd")
+    return y

@@ -19,7 +19,7 @@ CL = torch.channels_last
 BACKEND = {
     "conv2d": "jpb",        # tcgen05 implicit GEMM: forward, dgrad, wgrad (csrc/conv_tc.cu) + epilogue backward (elementwise.cu)
     "maxpool": "jpb",       # csrc/pool.cu
-    "batchnorm": "torch",   # cuDNN batch-norm (NHWC) — next kernel to replace
+    "batchnorm": "jpb",     # csrc/bn.cu: batch statistics + normalise + residual + ReLU fused, fwd and bwd
     "dropout": "torch", "image_prep": "torch", "cvp_mlp": "torch", "cct_attention": "torch", "pose_head": "torch",
 }
 
@@ -62,6 +62,14 @@ def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1
     """BatchNorm2d (+residual) (+ReLU).  Training mode uses per-GPU batch statistics and updates the
     running statistics in place, as nn.BatchNorm2d does."""
     _need_cuda(x)
+    if BACKEND["batchnorm"] == "jpb" and x.shape[1] % 4 == 0:
+        from . import functional as JF
+        if training:
+            k = getattr(bn, "stat_updates", 1)
+            bn.num_batches_tracked += k
+            return JF.batchnorm_train(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                      1.0 - (1.0 - momentum) ** k, eps, relu)
+        return JF.batchnorm_eval(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, eps, relu)
     if training:
         # ``stat_updates`` = 2 on the road-head BNs reproduces the reference's duplicated forward pass
         # (net.py:73-74): two momentum updates with the same batch statistics == one with 1-(1-m)^2.

@@ -305,3 +305,43 @@ def test_small_n_conv_forward_backward_vs_torch(dev, C, N, up, reflect, act):
     gw, gx = JC.smalln_bwd(x1, bool(up), D(dz, dev).contiguous(memory_format=torch.channels_last), w1, bool(reflect))
     assert (gw.cpu() - w0.grad).abs().max().item() <= 2e-5 * max(1.0, w0.grad.abs().max().item())
     assert (gx.cpu() - x0.grad).abs().max().item() <= 2e-5 * max(1.0, x0.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("C,H,W,relu,has_res", [(64, 12, 20, True, True), (16, 32, 32, True, False), (512, 3, 5, False, False), (128, 8, 8, False, True)])
+def test_batchnorm_train_forward_backward_vs_torch(dev, C, H, W, relu, has_res):
+    """Fused BN(+residual)(+ReLU): output, running statistics and all gradients against nn.functional.batch_norm."""
+    g = torch.Generator().manual_seed(8)
+    B = 3
+    x = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+    res = torch.randn(B, C, H, W, generator=g) if has_res else None
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    x0, g0, b0 = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    r0 = res.clone().requires_grad_(True) if has_res else None
+    rm0, rv0 = rm.clone(), rv.clone()
+    ref = torch.nn.functional.batch_norm(x0, rm0, rv0, g0, b0, True, 0.19, 1e-5)
+    if has_res:
+        ref = ref + r0
+    if relu:
+        ref = torch.relu(ref)
+    gy = torch.randn(ref.shape, generator=g)
+    ref.backward(gy)
+    cl = torch.channels_last
+    x1 = D(x, dev).contiguous(memory_format=cl).requires_grad_(True)
+    g1, b1 = D(gamma, dev).requires_grad_(True), D(beta, dev).requires_grad_(True)
+    r1 = D(res, dev).contiguous(memory_format=cl).requires_grad_(True) if has_res else None
+    rm1, rv1 = D(rm, dev), D(rv, dev)
+    got = JF.batchnorm_train(x1, r1, g1, b1, rm1, rv1, 0.19, 1e-5, relu)
+    assert (got.cpu() - ref.detach()).abs().max().item() < 2e-5
+    assert (rm1.cpu() - rm0).abs().max().item() < 1e-6 and (rv1.cpu() - rv0).abs().max().item() < 2e-6
+    got.backward(D(gy, dev))
+    assert (x1.grad.cpu() - x0.grad).abs().max().item() <= 2e-5 * max(1.0, x0.grad.abs().max().item())
+    assert (g1.grad.cpu() - g0.grad).abs().max().item() <= 2e-5 * max(1.0, g0.grad.abs().max().item())
+    assert (b1.grad.cpu() - b0.grad).abs().max().item() <= 2e-5 * max(1.0, b0.grad.abs().max().item())
+    if has_res:
+        assert (r1.grad.cpu() - r0.grad).abs().max().item() < 1e-6
+    ev = JF.batchnorm_eval(x1.detach(), r1.detach() if has_res else None, g1.detach(), b1.detach(), rm1, rv1, 1e-5, relu)
+    rev = torch.nn.functional.batch_norm(x, rm0, rv0, gamma, beta, False, 0.1, 1e-5)
+    rev = rev + res if has_res else rev
+    rev = torch.relu(rev) if relu else rev
+    assert (ev.cpu() - rev).abs().max().item() < 2e-5
