@@ -207,8 +207,10 @@ int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int 
 
 /* ---- BatchNorm2d (training: per-GPU batch statistics) fused with the residual add and ReLU that follow it
  * (resnet.py:28-45, layout_model.py:146-158).  x, res, y, dy, dx, dres: [rows][C] NHWC, C % 4 == 0.
- * stat: [2][C] floats (mean, 1/sqrt(var+eps)) written by the forward and read by the backward; acc: [2][C] doubles,
- * ZERO-FILLED by the caller before each call.  running_* are updated in place (momentum, unbiased variance).    */
+ * stat: [2][C] floats (mean, 1/sqrt(var+eps)) written by the forward and read by the backward; acc: workspace of
+ * jpb_bn_workspace_doubles(C) doubles (per-block partial sums, no initialisation needed).  running_* are updated in
+ * place (momentum, unbiased variance).                                                                          */
+long long jpb_bn_workspace_doubles(int C);
 int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream);
 int jpb_bn_eval_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* stat, int relu, float* y,

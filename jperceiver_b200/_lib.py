@@ -104,6 +104,8 @@ EMU_MISSING = ("jpb_conv2d_fwd", "jpb_conv2d_wgrad")   # tcgen05/TMA entry point
 def _declare(h):
     h.jpb_abi_version.restype = C.c_int
     h.jpb_build_info.restype = C.c_char_p
+    h.jpb_bn_workspace_doubles.restype = C.c_longlong
+    h.jpb_bn_workspace_doubles.argtypes = [C.c_int]
     for name in dir(_Signatures):
         if name.startswith("jpb_"):
             if not hasattr(h, name) and name in EMU_MISSING:
@@ -145,7 +147,7 @@ class _Signatures:
 
 
 def exported_symbols():
-    return ["jpb_abi_version", "jpb_build_info"] + [n for n in dir(_Signatures) if n.startswith("jpb_")]
+    return ["jpb_abi_version", "jpb_build_info", "jpb_bn_workspace_doubles"] + [n for n in dir(_Signatures) if n.startswith("jpb_")]
 
 
 def lib():

@@ -11,50 +11,77 @@
 
 namespace {
 
-// column sums of two per-element quantities over a [rows][C] matrix, accumulated into double acc[2][C].
+constexpr int BN_MAX_BLOCKS = 148 * 2;
+
+// column sums of two per-element quantities over a [rows][C] matrix.  Each block reduces a slab of rows and writes its
+// partial sums to ws[(1 + blockIdx.x) * 2C ...] (no atomics: 300 blocks hammering 2C addresses serialise in L2);
+// bn_reduce_partials_kernel then folds them into ws[0 .. 2C).
 // MODE 0: (x, x*x)    MODE 1: (g, g*xhat) with g = dy*[y>0 or no relu], xhat = (x-mean)*rstd
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const float* dy, const float* y, const float* stat, long long rows,
-                                                       int C, int relu, double* acc) {
-  JPB_DYN_SMEM(float, part);   // [2][256]
+                                                       int C, int relu, double* ws) {
+  JPB_DYN_SMEM(float, part);   // [8][256]
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * per;
   long long r1 = r0 + per;
   if (r1 > rows) r1 = rows;
-  const int Ct = C < 256 ? C : 256;                 // channels covered per pass
+  const int C4 = C >> 2;
+  const int Ct = C4 < 256 ? C4 : 256;               // float4 channel groups covered per pass
   const int lanes_r = 256 / Ct > 0 ? 256 / Ct : 1;  // row lanes
   const int U = Ct * lanes_r;
-  for (int cbase = 0; cbase < C; cbase += Ct) {
+  double* out = ws + (size_t)(1 + blockIdx.x) * 2 * C;
+  for (int cbase = 0; cbase < C4; cbase += Ct) {
     for (int u = JPB_TID; u < U; u += JPB_NT) {
-      const int c = cbase + u % Ct, lr = u / Ct;
-      float s1 = 0.f, s2 = 0.f;
-      if (c < C) {
-        float mean = 0.f, rstd = 1.f;
-        if (MODE == 1) { mean = stat[c]; rstd = stat[C + c]; }
+      const int c4 = cbase + u % Ct, lr = u / Ct;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c4 < C4) {
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
+        if (MODE == 1)
+          for (int k = 0; k < 4; ++k) { mean[k] = stat[c4 * 4 + k]; rstd[k] = stat[C + c4 * 4 + k]; }
         for (long long r = r0 + lr; r < r1; r += lanes_r) {
-          const long long i = r * C + c;
+          const long long i = r * C + c4 * 4;
           if (MODE == 0) {
-            const float v = x[i];
-            s1 += v; s2 += v * v;
+            const float4 v = *reinterpret_cast<const float4*>(x + i);
+            s1[0] += v.x; s2[0] += v.x * v.x; s1[1] += v.y; s2[1] += v.y * v.y;
+            s1[2] += v.z; s2[2] += v.z * v.z; s1[3] += v.w; s2[3] += v.w * v.w;
           } else {
-            float g = dy[i];
-            if (relu && !(y[i] > 0.f)) g = 0.f;
-            s1 += g; s2 += g * ((x[i] - mean) * rstd);
+            const float4 gv = *reinterpret_cast<const float4*>(dy + i);
+            const float4 xv = *reinterpret_cast<const float4*>(x + i);
+            float g[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            if (relu) {
+              const float4 yv = *reinterpret_cast<const float4*>(y + i);
+              if (!(yv.x > 0.f)) g[0] = 0.f;
+              if (!(yv.y > 0.f)) g[1] = 0.f;
+              if (!(yv.z > 0.f)) g[2] = 0.f;
+              if (!(yv.w > 0.f)) g[3] = 0.f;
+            }
+            for (int k = 0; k < 4; ++k) { s1[k] += g[k]; s2[k] += g[k] * ((xs[k] - mean[k]) * rstd[k]); }
           }
         }
       }
-      part[u] = s1; part[256 + u] = s2;
+      for (int k = 0; k < 4; ++k) { part[k * 256 + u] = s1[k]; part[(4 + k) * 256 + u] = s2[k]; }
     }
     __syncthreads();
-    for (int c = JPB_TID; c < Ct; c += JPB_NT) {
-      if (cbase + c < C && r1 > r0) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int lr = 0; lr < lanes_r; ++lr) { s1 += part[lr * Ct + c]; s2 += part[256 + lr * Ct + c]; }
-        atomicAdd(&acc[cbase + c], (double)s1);
-        atomicAdd(&acc[C + cbase + c], (double)s2);
+    for (int i = JPB_TID; i < Ct * 4; i += JPB_NT) {
+      const int cl = i >> 2, k = i & 3;
+      const int c = (cbase + cl) * 4 + k;
+      if (c < C) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int lr = 0; lr < lanes_r; ++lr) { a1 += part[k * 256 + lr * Ct + cl]; a2 += part[(4 + k) * 256 + lr * Ct + cl]; }
+        out[c] = (double)a1;
+        out[C + c] = (double)a2;
       }
     }
     __syncthreads();
+  }
+}
+
+__global__ void bn_reduce_partials_kernel(double* ws, int nb, int C) {
+  for (int j = blockIdx.x * JPB_NT + JPB_TID; j < 2 * C; j += gridDim.x * JPB_NT) {
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += ws[(size_t)(1 + b) * 2 * C + j];
+    ws[j] = s;
   }
 }
 
@@ -134,11 +161,15 @@ inline unsigned bn_grid(long long work, int per_block, int cap) {
 
 }  // namespace
 
+extern "C" long long jpb_bn_workspace_doubles(int C) { return (long long)2 * C * (1 + BN_MAX_BLOCKS); }
+
 extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                 float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream) {
   if (!x || !gamma || !beta || !y || !stat || !acc || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(bn_grid(rows, 128, 148 * 4)), dim3(256), 2 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, acc);
+  const unsigned nb = bn_grid(rows, 64, BN_MAX_BLOCKS);
+  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, acc);
+  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 256, 8)), dim3(256), 0, st, acc, (int)nb, C);
   JPB_LAUNCH(bn_finalize_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, rows, C, eps, momentum, stat, running_mean, running_var);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, res, stat, gamma, beta, y, n4, C, relu);
@@ -157,7 +188,9 @@ extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y,
                                 float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream) {
   if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !acc || (relu && !y) || (C & 3)) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(bn_grid(rows, 128, 148 * 4)), dim3(256), 2 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, acc);
+  const unsigned nb = bn_grid(rows, 64, BN_MAX_BLOCKS);
+  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, acc);
+  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 256, 8)), dim3(256), 0, st, acc, (int)nb, C);
   JPB_LAUNCH(bn_param_grad_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, C, dgamma, dbeta);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, acc, dx, dres, rows, n4, C, relu);

@@ -380,7 +380,7 @@ class _BNTrain(torch.autograd.Function):
         rows = B * H * W
         y = torch.empty_like(x, memory_format=torch.channels_last)
         stat = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
-        acc = torch.zeros(2 * Cc, dtype=torch.float64, device=x.device)
+        acc = torch.empty(_lib.lib().jpb_bn_workspace_doubles(Cc), dtype=torch.float64, device=x.device)
         check(_launch("bn_fwd", x, lambda: _lib.lib().jpb_bn_train_fwd(
             ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(running_mean), ptr(running_var), float(momentum), float(eps),
             int(relu), ptr(y), ptr(stat), ptr(acc), rows, Cc, stream_of(x))), "jpb_bn_train_fwd")
@@ -397,7 +397,7 @@ class _BNTrain(torch.autograd.Function):
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and relu) else None
         dgamma = torch.empty(Cc, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        acc = torch.zeros(2 * Cc, dtype=torch.float64, device=x.device)
+        acc = torch.empty(_lib.lib().jpb_bn_workspace_doubles(Cc), dtype=torch.float64, device=x.device)
         check(_launch("bn_bwd", x, lambda: _lib.lib().jpb_bn_train_bwd(
             ptr(x), ptr(gy), ptr(y), ptr(stat), ptr(gamma.detach()), relu, ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta), ptr(acc), rows, Cc,
             stream_of(x))), "jpb_bn_train_bwd")
