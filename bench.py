@@ -175,29 +175,49 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    step_resident = lambda: engine.step(resident, need_log=False)
     d2h = torch.empty(32, dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        data = change_input_variable(host, dev)           # H2D of this step's inputs from pinned memory
-        out = engine.step(data, need_log=True)             # stacked loss scalars
-        d2h[:out.numel()].copy_(out, non_blocking=False)   # D2H of the step's result (blocks: the loss is read)
-
+    # ---- eager profiling pass: per-kernel CUDA-event timings (roofline inputs) and the launch count of one step
     for _ in range(args.warmup):
-        step_resident()
-    launches0 = _lib.launches
+        engine.step(resident, need_log=False)
+    torch.cuda.synchronize()
     JF.PROFILE.clear()
     JF.PROFILE_ON = True
+    launches0 = _lib.launches
+    prof_steps = 3
+    for _ in range(prof_steps):
+        engine.step(resident, need_log=False)
+    torch.cuda.synchronize()
+    JF.PROFILE_ON = False
+    launches_per_step = (_lib.launches - launches0) // prof_steps
+    kern = JF.profile_summary()
+    for v in kern.values():
+        v["ms_per_step"] = v["ms_total"] / prof_steps
+        v["launches_per_step"] = v["launches"] // prof_steps
+
+    if args.graph:
+        engine.capture(resident, warmup=2)
+        step_resident = lambda: engine.replay()
+
+        def step_e2e():
+            out = engine.replay(host)                          # H2D of this step's inputs from pinned memory, then the step
+            d2h[:out.numel()].copy_(out, non_blocking=False)   # D2H of the step's result (blocks: the loss is read)
+    else:
+        step_resident = lambda: engine.step(resident, need_log=False)
+
+        def step_e2e():
+            data = change_input_variable(host, dev)
+            out = engine.step(data, need_log=True)
+            d2h[:out.numel()].copy_(out, non_blocking=False)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop()
-    JF.PROFILE_ON = False
-    launches = _lib.launches - launches0
-    torch.cuda.synchronize()
-    kern = JF.profile_summary()
-    for _ in range(min(args.warmup, 2)):
+    launches = launches_per_step * args.steps
+    for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     if rank != 0:
@@ -221,7 +241,8 @@ def run_ours(args):
                                "(fwd + compute_losses + bwd + allreduce + clip + Adam)" % (CONFIG_NAME, H, W, B),
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (activations, several GB) exceeds the 126 MB L2; no explicit flush",
-                   "frames_per_s": value * (1 + F_src), "operator_backends": dict(netops.BACKEND)},
+                   "frames_per_s": value * (1 + F_src), "operator_backends": dict(netops.BACKEND),
+                   "execution": "one CUDA graph per step (captured from the eager step)" if args.graph else "eager"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": synthetic.batch_bytes(host),
                 "d2h_bytes_per_step": 4 * (len(engine.last_names))},
         "gpu_launches": launches, "clocks": clocks,
@@ -229,7 +250,9 @@ def run_ours(args):
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (achieved / pk["hbm_gbs"]) if achieved else None,
                      "traffic": None, "peak_source": pk_src, "algorithmic_bytes_per_launch": sum(alg) / 4,
                      "ms_per_launch": pf["ms_per_launch"]},
-        "kernels": kern,
+        "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
+                        "ms_per_launch": round(v["ms_per_launch"], 5)} for k, v in kern.items()},
+        "kernel_timing": "CUDA events around each C-ABI call during %d eager steps before the timed region" % prof_steps,
     }
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(1, 1, batch=1)
@@ -247,6 +270,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

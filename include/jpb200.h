@@ -43,6 +43,8 @@ typedef struct JpbPhotoArgs {
   float min_disp, max_disp;        /* 1/max_depth, 1/min_depth (layers.py:33-38)                   */
   float noise_scale;               /* 1e-5 in the reference (net.py:163); used when noise[f]==NULL */
   uint64_t seed, stream;           /* Philox key / stream id for the in-kernel N(0,1) draw         */
+  const long long* step;           /* optional device step counter: stream += 64 * step[0] (fresh noise per
+                                      step even when the launch is replayed from a CUDA graph)               */
   double* loss_sum;                /* [1] += sum over b,y,x of min over candidates                 */
   long long* min_index;            /* [B,H,W] int64 argmin (outputs[("min_index",s)]) or NULL      */
   unsigned char* winner;           /* [B,H,W] same argmin as a byte (kept for backward) or NULL    */

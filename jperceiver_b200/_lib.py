@@ -31,7 +31,7 @@ class PhotoArgs(C.Structure):
         ("noise", C.c_void_p * MAX_SRC), ("disp", C.c_void_p), ("K", C.c_void_p), ("invK", C.c_void_p),
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hs", C.c_int), ("ws", C.c_int), ("F", C.c_int),
         ("automask", C.c_int), ("min_disp", C.c_float), ("max_disp", C.c_float), ("noise_scale", C.c_float),
-        ("seed", C.c_uint64), ("stream", C.c_uint64), ("loss_sum", C.c_void_p), ("min_index", C.c_void_p),
+        ("seed", C.c_uint64), ("stream", C.c_uint64), ("step", C.c_void_p), ("loss_sum", C.c_void_p), ("min_index", C.c_void_p),
         ("winner", C.c_void_p), ("warped", C.c_void_p * MAX_SRC),
     ]
 

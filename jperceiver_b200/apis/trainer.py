@@ -177,6 +177,9 @@ class TrainEngine:
         self.flat = model._jpb_flat
         self.rank, self.world = get_dist_info()
         self.last_names = None
+        if hasattr(model, "step_counter"):
+            model.step_counter = self.optimizer.step_count   # fresh automask noise per step, also under graph replay
+        self._graph = None
 
     def exchange_gradients(self):
         """The path's only collective: all-reduce(sum) of the flat gradient buffer (dist_utils.py:27);
@@ -197,6 +200,39 @@ class TrainEngine:
         if need_log:
             return torch.stack([v.detach() for v in vals] + [total.detach()])
         return total.detach()
+
+
+    # ------------------------------------------------------------------ CUDA-graph execution of the whole step
+    def capture(self, data, warmup=3):
+        """Capture forward + losses + backward + gradient exchange + optimizer into one CUDA graph.  ``data`` provides the
+        shapes; its tensors become the static input buffers (``replay`` copies new batches into them).  Shapes are static
+        in this workload, so one graph serves the whole run; every kernel is launched on the capture stream by the same
+        code path as the eager step."""
+        from .. import functional as JF
+        self._static_in = {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in data.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):      # also creates chunk tables, sets kernel attributes, fills host-side caches
+                self.step(self._static_in, need_log=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        prof, JF.PROFILE_ON = JF.PROFILE_ON, False
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self.step(self._static_in, need_log=True)
+        JF.PROFILE_ON = prof
+        return self
+
+    def replay(self, data=None):
+        """Run the captured step; ``data`` (device or pinned-host tensors) is copied into the static inputs first."""
+        if data is not None:
+            for k, v in data.items():
+                dst = self._static_in.get(k)
+                if torch.is_tensor(dst) and dst.is_cuda and torch.is_tensor(v) and v is not dst:
+                    dst.copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
 
 
 def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=False, validate=False, logger=None):

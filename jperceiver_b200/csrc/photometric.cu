@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) photometric_fwd_kernel(JpbPhotoArgs a) {
     for (int f = 0; f < nid; ++f) {
       float err = reproj_error(s_id + f * 3 * P1_N, s_tgt, P1_N, P1_W, ctr, my, vyy);
       if (a.noise[f]) err += a.noise[f][po];
-      else if (a.noise_scale != 0.f) err += a.noise_scale * jpb_randn(a.seed, a.stream + (uint64_t)f, (uint64_t)po);
+      else if (a.noise_scale != 0.f)
+        err += a.noise_scale * jpb_randn(a.seed, a.stream + (uint64_t)f + (a.step ? 64ull * (uint64_t)a.step[0] : 0ull), (uint64_t)po);
       if (err < best) { best = err; besti = f; }
     }
     for (int f = 0; f < F; ++f) {

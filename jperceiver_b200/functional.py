@@ -53,7 +53,7 @@ def finalize(acc, scale, den=None):
 # --------------------------------------------------------------------------------------------------
 # fused photometric reprojection loss (one launch per scale)
 # --------------------------------------------------------------------------------------------------
-def _photo_args(disp, target, sources, Ts, noises, K, invK, automask, min_depth, max_depth, noise_scale, seed, stream_id):
+def _photo_args(disp, target, sources, Ts, noises, K, invK, automask, min_depth, max_depth, noise_scale, seed, stream_id, step=None):
     a = PhotoArgs()
     B, _, H, W = target.shape
     a.target = ptr(target)
@@ -67,6 +67,7 @@ def _photo_args(disp, target, sources, Ts, noises, K, invK, automask, min_depth,
     a.min_disp, a.max_disp = 1.0 / max_depth, 1.0 / min_depth
     a.noise_scale = float(noise_scale)
     a.seed, a.stream = int(seed), int(stream_id)
+    a.step = ptr(step) if step is not None else None
     return a
 
 
@@ -84,7 +85,7 @@ class _Photometric(torch.autograd.Function):
         B, _, H, W = target.shape
         dev = target.device
         a = _photo_args(disp_c, target, sources, Ts, noises, K, invK, cfg["automask"], cfg["min_depth"],
-                        cfg["max_depth"], cfg["noise_scale"], cfg["seed"], cfg["stream"])
+                        cfg["max_depth"], cfg["noise_scale"], cfg["seed"], cfg["stream"], cfg.get("step"))
         acc = torch.zeros(1, dtype=torch.float64, device=dev)
         winner = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
         a.loss_sum, a.winner = ptr(acc), ptr(winner)
@@ -132,14 +133,14 @@ class _Photometric(torch.autograd.Function):
 
 
 def photometric_loss(disp, target, sources, Ts, K, invK, *, num_scales=4, automask=True, min_depth=0.1,
-                     max_depth=100.0, noise=None, noise_scale=1e-5, seed=0, stream=0, debug_outputs=False):
+                     max_depth=100.0, noise=None, noise_scale=1e-5, seed=0, stream=0, step=None, debug_outputs=False):
     """``loss_dict[("min_reconstruct_loss", s)]`` of one scale (already divided by ``num_scales``).
 
     Returns ``(loss, winner_u8, min_index|None, [warped...])``.  ``noise``: list of B×H×W tensors for the
     identity terms (tests) or None for the in-kernel Philox draw scaled by ``noise_scale``.
     """
     cfg = dict(F=len(sources), num_scales=num_scales, automask=automask, min_depth=min_depth, max_depth=max_depth,
-               noise_scale=noise_scale, seed=seed, stream=stream, debug_outputs=debug_outputs)
+               noise_scale=noise_scale, seed=seed, stream=stream, step=step, debug_outputs=debug_outputs)
     rest = list(sources) + list(Ts) + (list(noise) if noise is not None else [])
     out = _Photometric.apply(disp, K, invK, target, cfg, *rest)
     loss, winner = out[0], out[1]

@@ -109,6 +109,7 @@ class Baseline(nn.Module):
         self.noise_override = None   # tests: {scale: [B,H,W tensors]}
         self.scale_label_override = None   # tests: inject a label (the Argo_both label is ill-conditioned)
         self._step = 0
+        self.step_counter = None     # optional device int64 step counter (the optimizer's): decorrelates the automask noise per step
         self._quad_cache = {}
         if self.bn_double_update:   # second running-stat update of the reference's duplicated road-head pass
             for m in (self.LayoutEncoder, self.LayoutDecoder, self.LayoutTransformDecoder):
@@ -239,7 +240,7 @@ class Baseline(nn.Module):
             loss, winner, min_index, warped = JF.photometric_loss(
                 disp, target, sources, poses, inputs[("K", 0)], inputs[("inv_K", 0)], num_scales=nsc, automask=o.automask,
                 min_depth=o.min_depth, max_depth=o.max_depth, noise=noise, noise_scale=self.noise_scale,
-                seed=int(o.get("seed", 1024)), stream=self._step * 16 + 4 * s, debug_outputs=self.debug_outputs)
+                seed=int(o.get("seed", 1024)), stream=4 * s, step=self.step_counter, debug_outputs=self.debug_outputs)
             L[("min_reconstruct_loss", s)] = loss
             if self.debug_outputs:
                 lo, hi = 1.0 / o.max_depth, 1.0 / o.min_depth
