@@ -176,6 +176,9 @@ def run_ours(args):
         return float(ms.item())
 
     d2h = torch.empty(32, dtype=torch.float32).pin_memory()
+    work_stream = torch.cuda.Stream()          # all steps (eager and captured) run on one non-default stream
+    work_stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work_stream)
     # ---- eager profiling pass: per-kernel CUDA-event timings (roofline inputs) and the launch count of one step
     for _ in range(args.warmup):
         engine.step(resident, need_log=False)

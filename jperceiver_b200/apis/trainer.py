@@ -210,18 +210,20 @@ class TrainEngine:
         code path as the eager step."""
         from .. import functional as JF
         self._static_in = {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in data.items()}
-        side = torch.cuda.Stream()
+        # everything that touches autograd before / during capture runs on ONE non-default stream: a leaf whose gradient
+        # accumulator was bound to the legacy default stream would make the capture depend on it (cudaErrorStreamCaptureImplicit)
+        side = self._capture_stream = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):      # also creates chunk tables, sets kernel attributes, fills host-side caches
                 self.step(self._static_in, need_log=True)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        side.synchronize()
         prof, JF.PROFILE_ON = JF.PROFILE_ON, False
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):
             self._static_out = self.step(self._static_in, need_log=True)
         JF.PROFILE_ON = prof
+        torch.cuda.current_stream().wait_stream(side)
         return self
 
     def replay(self, data=None):

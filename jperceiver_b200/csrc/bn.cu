@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int BN_MAX_BLOCKS = 148 * 2;
+constexpr int BN_MAX_BLOCKS = 148 * 8;
 
 // column sums of two per-element quantities over a [rows][C] matrix.  Each block reduces a slab of rows and writes its
 // partial sums to ws[(1 + blockIdx.x) * 2C ...] (no atomics: 300 blocks hammering 2C addresses serialise in L2);
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
         float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
         if (MODE == 1)
           for (int k = 0; k < 4; ++k) { mean[k] = stat[c4 * 4 + k]; rstd[k] = stat[C + c4 * 4 + k]; }
+#pragma unroll 4
         for (long long r = r0 + lr; r < r1; r += lanes_r) {
           const long long i = r * C + c4 * 4;
           if (MODE == 0) {
@@ -167,7 +168,7 @@ extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* g
                                 float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream) {
   if (!x || !gamma || !beta || !y || !stat || !acc || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned nb = bn_grid(rows, 64, BN_MAX_BLOCKS);
+  const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
   JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, acc);
   JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 256, 8)), dim3(256), 0, st, acc, (int)nb, C);
   JPB_LAUNCH(bn_finalize_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, rows, C, eps, momentum, stat, running_mean, running_var);
@@ -188,7 +189,7 @@ extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y,
                                 float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream) {
   if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !acc || (relu && !y) || (C & 3)) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned nb = bn_grid(rows, 64, BN_MAX_BLOCKS);
+  const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
   JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, acc);
   JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 256, 8)), dim3(256), 0, st, acc, (int)nb, C);
   JPB_LAUNCH(bn_param_grad_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, C, dgamma, dbeta);
