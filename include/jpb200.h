@@ -221,7 +221,8 @@ int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const floa
                      float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream);
 
 /* ---- NHWC max pooling (nn.MaxPool2d(k, s, p); layers.py:191, resnet.py:91, layout_model.py:84) --------------
- * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.               */
+ * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.
+ * Backward: gx must be ZERO-FILLED by the caller (overlapping windows are scattered with red.global.add).      */
 int jpb_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, int k, int s, int p, void* stream);
 int jpb_maxpool_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, int k, int s, int p, void* stream);
 

@@ -280,7 +280,8 @@ def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
     got = JF.maxpool(x1, k, s, p)
     assert torch.equal(got.cpu(), ref.detach())
     got.backward(D(gy, dev))
-    assert (x1.grad.cpu() - x0.grad).abs().max().item() < 1e-6
+    # overlapping windows accumulate by atomics: summation order differs from ATen's
+    assert (x1.grad.cpu() - x0.grad).abs().max().item() <= 1e-5 * max(1.0, x0.grad.abs().max().item())
 
 
 @pytest.mark.parametrize("C,N,up,reflect,act", [(256, 1, 1, 1, "sigmoid"), (16, 2, 0, 1, "none"), (32, 2, 0, 0, "leaky"), (64, 1, 1, 0, "none")])
