@@ -78,11 +78,20 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
   }
 }
 
-__global__ void bn_reduce_partials_kernel(double* ws, int nb, int C) {
-  for (int j = blockIdx.x * JPB_NT + JPB_TID; j < 2 * C; j += gridDim.x * JPB_NT) {
+// one warp per column j of the [nb][2C] partials: lanes stride the blocks, shuffle-reduce, lane 0 writes ws[j]
+__global__ void __launch_bounds__(256) bn_reduce_partials_kernel(double* ws, int nb, int C) {
+#ifdef JPB_HOST_EMU
+  const int lanes = 1, lane = 0, warps = 1, warp = 0;
+#else
+  const int lanes = 32, lane = threadIdx.x & 31, warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+#endif
+  for (int j = blockIdx.x * warps + warp; j < 2 * C; j += gridDim.x * warps) {
     double s = 0.0;
-    for (int b = 0; b < nb; ++b) s += ws[(size_t)(1 + b) * 2 * C + j];
-    ws[j] = s;
+    for (int b = lane; b < nb; b += lanes) s += ws[(size_t)(1 + b) * 2 * C + j];
+#ifndef JPB_HOST_EMU
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#endif
+    if (lane == 0) ws[j] = s;
   }
 }
 
@@ -170,7 +179,7 @@ extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* g
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
   JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, acc);
-  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 256, 8)), dim3(256), 0, st, acc, (int)nb, C);
+  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 8, 148)), dim3(256), 0, st, acc, (int)nb, C);
   JPB_LAUNCH(bn_finalize_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, rows, C, eps, momentum, stat, running_mean, running_var);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, res, stat, gamma, beta, y, n4, C, relu);
@@ -191,7 +200,7 @@ extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y,
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
   JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, acc);
-  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 256, 8)), dim3(256), 0, st, acc, (int)nb, C);
+  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 8, 148)), dim3(256), 0, st, acc, (int)nb, C);
   JPB_LAUNCH(bn_param_grad_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, C, dgamma, dbeta);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, acc, dx, dres, rows, n4, C, relu);
