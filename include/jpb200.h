@@ -170,6 +170,8 @@ typedef struct JpbConvArgs {
   int dst_C[JPB_CONV_MAX_SRC], dst_H[JPB_CONV_MAX_SRC], dst_W[JPB_CONV_MAX_SRC], dst_up[JPB_CONV_MAX_SRC];
   int ndst;
   int fold_pad, fold_reflect, fold_H, fold_W; /* output pixel (py,px) -> (py-fold_pad, px-fold_pad), reflected into fold_H x fold_W */
+  int ksplit;                           /* > 1: split the K blocks over this many CTAs per tile (no bias/residual/act; output
+                                           zero-filled by the caller, partial tiles are added atomically) */
 } JpbConvArgs;
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
 

@@ -81,6 +81,17 @@ def _torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual):
     return y
 
 
+def _ksplit(M, N, nkb):
+    """Split-K factor for tiles that cannot fill the 148 SMs (deep, small-extent layers: layer3/4, pose and layout tails)."""
+    nt = 16
+    while nt < N and nt < 256:
+        nt *= 2
+    tiles = ((M + 127) // 128) * ((N + nt - 1) // nt)
+    if tiles >= 74 or nkb < 16:
+        return 1
+    return max(1, min(148 // tiles, nkb // 8, 16))
+
+
 def _fill_sources(a, xs, ups):
     for i, x in enumerate(xs):
         a.src[i] = ptr(x)
@@ -149,6 +160,11 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
     a.table, a.nkb = ptr(table), table.shape[0] // 8
     a.act = 0
+    ks = _ksplit(B * a.Ho * a.Wo, Cin, table.shape[0] // 8)
+    if ks > 1:
+        a.ksplit = ks
+        if simple:
+            grads[0].zero_()
     if simple:
         a.out = ptr(grads[0])
     else:
@@ -274,8 +290,13 @@ class _ConvTC(torch.autograd.Function):
         dev = xs[0].device
         table = chunk_table(src_C, kh, kw, dev)
         wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
+        nkb = table.shape[0] // 8
+        ks = _ksplit(B * Ho * Wo, N, nkb) if (bias is None and residual is None and act == "none") else 1
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=dev, memory_format=CL)
+        if ks > 1:
+            out.zero_()
         a = _lib.ConvArgs()
+        a.ksplit = ks
         _fill_sources(a, xs, ups)
         a.B, a.Hin, a.Win, a.Ho, a.Wo, a.N = B, Hin, Win, Ho, Wo, N
         a.stride, a.pad, a.reflect = stride, pad, int(reflect)

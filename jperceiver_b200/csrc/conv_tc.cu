@@ -133,7 +133,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.B * a.Ho * a.Wo;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT;
-  const int nkb = a.nkb;
+  // split-K: gridDim.z CTAs share one output tile, each reduces a slice of the K blocks and adds its partial tile
+  // atomically (only used for epilogue-free convolutions; the output is zero-filled by the caller)
+  const int kb_per = (a.nkb + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int kb0 = (int)blockIdx.z * kb_per;
+  int nkb = a.nkb - kb0;
+  if (nkb > kb_per) nkb = kb_per;
+  if (nkb < 0) nkb = 0;
+  const bool split = gridDim.z > 1;
 
   if (tid < a.nsrc) {
     srcs[tid].ptr = a.src[tid];
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + kb * 8 + c);   // x: source (-1 none), y: dy<<16 | (dx & 0xffff), z: channel offset, w: valid bytes
+      const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + (kb0 + kb) * 8 + c);   // x: source (-1 none), y: dy<<16 | (dx & 0xffff), z: channel offset, w: valid bytes
       const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
       if (e.x < 0 || e.w == 16) {
         const SrcDev sd = srcs[e.x < 0 ? 0 : e.x];
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
     }
 
     // ===================================================== epilogue
+    if (nkb > 0) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int row = warp * 32 + lane;
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     float* out = nullptr;
     const float* res = nullptr;
-    bool atomic = false, vec_ok = (a.N & 3) == 0;
+    bool atomic = split, vec_ok = (a.N & 3) == 0;
     int nvalid = a.N - n0;                    // channels of this N tile that exist
     if (!a.scatter) {
       out = a.out + (size_t)m * a.N + n0;
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
       const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
       int ty = rem / a.Wo - a.fold_pad, tx = rem % a.Wo - a.fold_pad;
       if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
-      atomic = a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
+      atomic = split || a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
       if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
       out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
       vec_ok = (a.dst_C[j] & 3) == 0;
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
         }
       }
     }
+    }
     tc_fence_before();
   } else if (warp == 4) {
     // ===================================================== weight TMA producer
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
-        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], kb * BK, n0);
+        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], (kb0 + kb) * BK, n0);
       }
     }
   } else {
@@ -520,7 +529,7 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
     configured = true;
   }
   const int M = a->B * a->Ho * a->Wo;
-  dim3 grid((M + BM - 1) / BM, (a->N + NT - 1) / NT);
+  dim3 grid((M + BM - 1) / BM, (a->N + NT - 1) / NT, a->ksplit > 1 ? a->ksplit : 1);
   conv_tc_fwd_kernel<NT, STAGES><<<grid, 192, smem, st>>>(map, *a);
   return jpb_status();
 }
@@ -537,6 +546,7 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   if (a->nt) nt = a->nt;
   if (nt != 16 && nt != 32 && nt != 64 && nt != 128 && nt != 256) return JPB_ERR_ARG;
   if (a->scatter && (a->ndst < 1 || a->ndst > JPB_CONV_MAX_SRC)) return JPB_ERR_ARG;
+  if (a->ksplit > 1 && (a->bias || a->residual || a->act)) return JPB_ERR_ARG;   // partial tiles cannot run the epilogue
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)a->w_cols, (cuuint64_t)a->N};
   const cuuint64_t gstr[1] = {(cuuint64_t)a->w_row * 4};
