@@ -142,7 +142,8 @@ int jpb_l1_mean_bwd(const float* x, const float* y, long long n, const float* gr
  * three sources (depth_decoder.py:76,96,115), bias, residual add (layers.py:197) and the activation
  * (F.leaky_relu depth_decoder.py:60, ReLU, sigmoid depth_decoder.py:35-38).
  * Activations are NHWC fp32.  K is walked in 16-byte chunks described by `table` (4 ints per chunk:
- * {source index or -1, dy<<16 | (dx & 0xffff), channel offset, valid bytes}); 8 chunks = one 32-float K block.
+ * {source | (tap*nsrc + source) << 8, or -1; dy<<16 | (dx & 0xffff); channel offset; valid bytes}); 8 chunks = one
+ * 32-float K block.
  * `weight` is the K-major matrix [N][w_row] whose first w_cols columns follow the same chunk order.      */
 #define JPB_CONV_MAX_SRC 3
 typedef struct JpbConvArgs {
@@ -170,6 +171,7 @@ typedef struct JpbConvArgs {
   int dst_C[JPB_CONV_MAX_SRC], dst_H[JPB_CONV_MAX_SRC], dst_W[JPB_CONV_MAX_SRC], dst_up[JPB_CONV_MAX_SRC];
   int ndst;
   int fold_pad, fold_reflect, fold_H, fold_W; /* output pixel (py,px) -> (py-fold_pad, px-fold_pad), reflected into fold_H x fold_W */
+  int ntaps, kw;                        /* filter taps (kh*kw) and filter width: tap t reads (dy, dx) = (t / kw, t % kw) */
   int ksplit;                           /* > 1: split the K blocks over this many CTAs per tile (no bias/residual/act; output
                                            zero-filled by the caller, partial tiles are added atomically) */
 } JpbConvArgs;

@@ -31,11 +31,13 @@ def chunk_table(src_channels, kh, kw, device):
     t = _TABLES.get(key)
     if t is None:
         rows = []
+        nsrc = len(src_channels)
         for ky in range(kh):
             for kx in range(kw):
+                tap = ky * kw + kx
                 for si, c in enumerate(src_channels):
                     for coff in range(0, c, 4):
-                        rows.append((si, (ky << 16) | (kx & 0xFFFF), coff, min(16, (c - coff) * 4)))
+                        rows.append((si | ((tap * nsrc + si) << 8), (ky << 16) | (kx & 0xFFFF), coff, min(16, (c - coff) * 4)))
         while len(rows) % 8:
             rows.append((-1, 0, 0, 0))
         t = _TABLES[key] = torch.tensor(rows, dtype=torch.int32, device=device).contiguous()
@@ -159,6 +161,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     a.fold_H, a.fold_W = H, W
     a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
     a.table, a.nkb = ptr(table), table.shape[0] // 8
+    a.ntaps, a.kw = kh * kw, kw
     a.act = 0
     ks = _ksplit(B * a.Ho * a.Wo, Cin, table.shape[0] // 8)
     if ks > 1:
@@ -302,6 +305,7 @@ class _ConvTC(torch.autograd.Function):
         a.stride, a.pad, a.reflect = stride, pad, int(reflect)
         a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
         a.table, a.nkb = ptr(table), table.shape[0] // 8
+        a.ntaps, a.kw = kh * kw, kw
         a.bias = ptr(bias.detach()) if bias is not None else None
         if residual is not None:
             residual = residual if residual.is_contiguous(memory_format=CL) else residual.contiguous(memory_format=CL)

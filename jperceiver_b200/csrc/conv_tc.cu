@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   SrcDev* srcs = reinterpret_cast<SrcDev*>(tmem_slot + 2);
+  int* s_off = reinterpret_cast<int*>(srcs + JPB_CONV_MAX_SRC);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.B * a.Ho * a.Wo;
@@ -161,57 +162,67 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ===================================================== A gather (producers)
-    const int c = tid & 7;           // 16-byte chunk column inside the 128-byte K row
-    const int rbase = tid >> 3;      // rows rbase + 16*i
-    int iy0[8], ix0[8], bb[8];
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rbase + 16 * i;
+  // ---- per-tile gather offsets, all 192 threads: s_off[(tap*nsrc + src)*BM + row] = element offset of the pixel that
+  // tile row `row` reads for filter tap `tap` in source `src` (padding / reflection / up-sampling / stride folded), or -1
+  {
+    const int nts = a.ntaps * a.nsrc;
+    for (int idx = tid; idx < nts * BM; idx += 192) {
+      const int ts = idx / BM, row = idx - ts * BM;
+      const int tap = ts / a.nsrc, si = ts - tap * a.nsrc;
+      const int m = m0 + row;
+      int off = -1;
       if (m < M) {
         const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
         const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
-        bb[i] = b; iy0[i] = oy * a.stride - a.pad; ix0[i] = ox * a.stride - a.pad;
-      } else {
-        bb[i] = -1; iy0[i] = 0; ix0[i] = 0;
+        int iy = oy * a.stride - a.pad + tap / a.kw, ix = ox * a.stride - a.pad + tap % a.kw;
+        bool ok = true;
+        if (a.in_div == 2) { ok = !((iy | ix) & 1); iy >>= 1; ix >>= 1; }   // dgrad of a stride-2 convolution
+        if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+        else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+        if (ok) {
+          if (a.src_up[si]) { iy >>= 1; ix >>= 1; }
+          off = ((b * a.src_H[si] + iy) * a.src_W[si] + ix) * a.src_C[si];
+        }
       }
+      s_off[idx] = off;
     }
+  }
+  __syncthreads();
+
+  if (warp < 4) {
+    // ===================================================== A gather (producers)
+    // The element offset of (tile row, tap, source) does not depend on the channel block: all threads computed it once
+    // into s_off[(tap*nsrc + src)*128 + row] (-1 = zero fill) before the role split, so the K loop below is one shared
+    // load, one add and one cp.async per 16-byte chunk (the gather used to spend ~60 integer instructions per chunk,
+    // which made the four producer warps — not L2, not the tensor pipe — the bottleneck of the whole kernel).
+    const int c = tid & 7;           // 16-byte chunk column inside the 128-byte K row
+    const int rbase = tid >> 3;      // rows rbase + 16*i
     const uint32_t swz = (uint32_t)((c ^ (rbase & 7)) << 4) + (uint32_t)(rbase & 7) * 128u + (uint32_t)(rbase >> 3) * 1024u;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + (kb0 + kb) * 8 + c);   // x: source (-1 none), y: dy<<16 | (dx & 0xffff), z: channel offset, w: valid bytes
+      // x: source | (tap*nsrc + source) << 8, or -1; y: dy<<16 | dx (wgrad only); z: channel offset; w: valid bytes
+      const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + (kb0 + kb) * 8 + c);
       const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
-      if (e.x < 0 || e.w == 16) {
-        const SrcDev sd = srcs[e.x < 0 ? 0 : e.x];
-        const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
+      const bool live = e.x >= 0;
+      const float* base = srcs[live ? (e.x & 0xff) : 0].ptr + e.z;
+      const int* offs = s_off + (live ? (e.x >> 8) : 0) * BM + rbase;
+      if (!live || e.w == 16) {
         for (int i = 0; i < 8; ++i) {
-          int iy = iy0[i] + dy, ix = ix0[i] + dx;
-          bool ok = bb[i] >= 0 && e.x >= 0;
-          if (a.in_div == 2) { ok = ok && !((iy | ix) & 1); iy >>= 1; ix >>= 1; }   // dgrad of a stride-2 convolution
-          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
-          else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-          if (!ok) { iy = 0; ix = 0; }
-          if (sd.up) { iy >>= 1; ix >>= 1; }
-          const float* g = sd.ptr + ((size_t)((ok ? bb[i] : 0) * sd.H + iy) * sd.W + ix) * sd.C + e.z;
-          cp_async16(sbase + (uint32_t)i * 2048u, g, ok ? 16u : 0u);
+          const int off = offs[16 * i];
+          const bool ok = live && off >= 0;
+          cp_async16(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
         }
       } else {
         // partial chunk (a source whose channel count is not a multiple of 4, e.g. the 1-channel disparity):
         // synchronous scalar loads, zero padded
-        const SrcDev sd = srcs[e.x];
-        const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
         const int nval = e.w >> 2;
         for (int i = 0; i < 8; ++i) {
-          int iy = iy0[i] + dy, ix = ix0[i] + dx;
-          bool ok = bb[i] >= 0;
-          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
-          else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+          const int off = offs[16 * i];
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            if (sd.up) { iy >>= 1; ix >>= 1; }
-            const float* g = sd.ptr + ((size_t)(bb[i] * sd.H + iy) * sd.W + ix) * sd.C + e.z;
+          if (off >= 0) {
+            const float* g = base + off;
             v.x = g[0];
             if (nval > 1) v.y = g[1];
             if (nval > 2) v.z = g[2];
@@ -381,9 +392,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
     const int gq = mt * 32 + q;
     int4 e = make_int4(-1, 0, 0, 0);
     if (gq < a.nchunks) e = __ldg(reinterpret_cast<const int4*>(a.table) + gq);
-    const float* sptr = a.src[e.x < 0 ? 0 : e.x];
-    const int sC = a.src_C[e.x < 0 ? 0 : e.x], sH = a.src_H[e.x < 0 ? 0 : e.x], sW = a.src_W[e.x < 0 ? 0 : e.x];
-    const int sup = a.src_up[e.x < 0 ? 0 : e.x];
+    const int esrc = e.x < 0 ? 0 : (e.x & 0xff);
+    const float* sptr = a.src[esrc];
+    const int sC = a.src_C[esrc], sH = a.src_H[esrc], sW = a.src_W[esrc];
+    const int sup = a.src_up[esrc];
     const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
     const int nval = e.w >> 2;
     const int HoWo = a.Ho * a.Wo;
@@ -522,11 +534,12 @@ EncodeTiledFn get_encode() {
 
 template <int NT, int STAGES>
 int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+  static int configured = 0;
+  if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
+  if (smem > configured) {
     if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
-    configured = true;
+    configured = smem;
   }
   const int M = a->B * a->Ho * a->Wo;
   dim3 grid((M + BM - 1) / BM, (a->N + NT - 1) / NT, a->ksplit > 1 ? a->ksplit : 1);
@@ -547,6 +560,7 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   if (nt != 16 && nt != 32 && nt != 64 && nt != 128 && nt != 256) return JPB_ERR_ARG;
   if (a->scatter && (a->ndst < 1 || a->ndst > JPB_CONV_MAX_SRC)) return JPB_ERR_ARG;
   if (a->ksplit > 1 && (a->bias || a->residual || a->act)) return JPB_ERR_ARG;   // partial tiles cannot run the epilogue
+  if (a->ntaps < 1 || a->kw < 1 || a->ntaps * a->nsrc > 64) return JPB_ERR_ARG;
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)a->w_cols, (cuuint64_t)a->N};
   const cuuint64_t gstr[1] = {(cuuint64_t)a->w_row * 4};
