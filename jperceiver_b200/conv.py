@@ -105,9 +105,9 @@ def _cl(x):
     return x if x.is_contiguous(memory_format=CL) else x.contiguous(memory_format=CL)
 
 
-def _launch(name, t, call):
+def _launch(name, t, call, tag=None):
     from .functional import _launch as L
-    return L(name, t, call)
+    return L(name, t, call, tag)
 
 
 def act_bwd(gy, y, act, want_bias):
@@ -186,7 +186,8 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
             nt = 0
         assert nt == 0 or nt >= 16
         a.nt = nt
-    check(_launch("conv_dgrad", dz, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(dz))), "jpb_conv2d_fwd(dgrad)")
+    tag = (B * a.Ho * a.Wo, Cin, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
+    check(_launch("conv_dgrad", dz, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_fwd(dgrad)")
     return grads
 
 
@@ -218,7 +219,8 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
     a.splits = max(1, min(steps, (2 * 148 + tiles - 1) // tiles))
     if dbg is not None:
         a.dbg = ptr(dbg)
-    check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz))), "jpb_conv2d_wgrad")
+    tag = (B * Ho * Wo, Nc, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), a.splits)
+    check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_wgrad")
     dw = dw[:N]
     if raw:
         return dw.view(N, kh, kw, Cin).permute(0, 3, 1, 2)
@@ -312,7 +314,8 @@ class _ConvTC(torch.autograd.Function):
             a.residual = ptr(residual)
         a.act = ACT[act]
         a.out = ptr(out)
-        check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out))), "jpb_conv2d_fwd")
+        tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
+        check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd")
         ctx.cfg = cfg
         ctx.has = (bias is not None, residual is not None)
         ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)

@@ -14,9 +14,10 @@ from ._lib import PhotoArgs, PhotoGrad, check, ptr, stream_of
 # ---- optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline figures) ----
 PROFILE_ON = False
 PROFILE: dict = {}
+PROFILE_DETAIL: dict = {}     # (name, tag) -> events; tag = the caller's shape description (per-layer tables, tools/conv_layers.py)
 
 
-def _launch(name, tensor, call):
+def _launch(name, tensor, call, tag=None):
     """Run one C-ABI launch; when profiling, bracket it with CUDA events on the tensor's current stream."""
     if PROFILE_ON and tensor.is_cuda:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -24,6 +25,8 @@ def _launch(name, tensor, call):
         status = call()
         e1.record()
         PROFILE.setdefault(name, []).append((e0, e1))
+        if tag is not None:
+            PROFILE_DETAIL.setdefault((name, tag), []).append((e0, e1))
         return status
     return call()
 
