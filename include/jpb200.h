@@ -174,6 +174,9 @@ typedef struct JpbConvArgs {
   int ntaps, kw;                        /* filter taps (kh*kw) and filter width: tap t reads (dy, dx) = (t / kw, t % kw) */
   int ksplit;                           /* > 1: split the K blocks over this many CTAs per tile (no bias/residual/act; output
                                            zero-filled by the caller, partial tiles are added atomically) */
+  const int* kcol;                      /* [nkb] weight column (float index) of K block i, or NULL for i*32: lets the host order
+                                           the K blocks so that taps sharing input pixels are consecutive */
+  int l1_gather;                        /* 1: gather through L1 (cp.async.ca) — pays off with the K-block order above */
 } JpbConvArgs;
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
 

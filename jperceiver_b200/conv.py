@@ -19,6 +19,12 @@ ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3}
 SMALLN = True      # route 3x3 convolutions with <= 2 output channels to the CUDA-core kernels (csrc/conv_smalln.cu)
 BACKWARD = "jpb"   # "jpb": tcgen05 dgrad/wgrad kernels; "torch": library backward on a re-materialised input (debug)
 _TABLES: dict = {}
+_ORDERS: dict = {}
+import os as _os
+# K-block order of the forward / data-gradient GEMM: "cb" = channel-block major (the taps of one 32-channel block are
+# consecutive, so their gathers re-read the same pixels and hit L1), "tap" = the natural weight order
+KORDER = _os.environ.get("JPB_CONV_KORDER", "cb")
+L1_GATHER = int(_os.environ.get("JPB_CONV_L1", "1"))
 
 
 def _pad4(c):
@@ -42,6 +48,32 @@ def chunk_table(src_channels, kh, kw, device):
             rows.append((-1, 0, 0, 0))
         t = _TABLES[key] = torch.tensor(rows, dtype=torch.int32, device=device).contiguous()
     return t
+
+
+def ordered_table(src_channels, kh, kw, device):
+    """(table, kcol): the chunk table with its K blocks (8 rows each) re-ordered channel-block major, and the weight column
+    of each K block (int32 [nkb]) for the weight TMA.  Any order is valid — K is the GEMM reduction."""
+    if KORDER != "cb" or kh * kw == 1:
+        return chunk_table(src_channels, kh, kw, device), None
+    key = (tuple(src_channels), kh, kw, str(device))
+    r = _ORDERS.get(key)
+    if r is None:
+        t = chunk_table(src_channels, kh, kw, device).cpu().view(-1, 8, 4)
+        first = t[:, 0, :]                                       # first chunk of each K block: (src | tapsrc<<8, dydx, coff, bytes)
+        nsrc = len(src_channels)
+        keys = []
+        for i in range(t.shape[0]):
+            x, _, coff, _ = [int(v) for v in first[i]]
+            if x < 0:
+                keys.append((1 << 30, 0, 0, i))
+            else:
+                si, tap = x & 0xff, (x >> 8) // nsrc
+                keys.append((si, coff // 32, tap, i))
+        perm = torch.tensor([k[3] for k in sorted(keys)], dtype=torch.long)
+        tab = t[perm].reshape(-1, 4).contiguous().to(device)
+        kcol = (perm * 32).to(torch.int32).to(device)
+        r = _ORDERS[key] = (tab, kcol)
+    return r
 
 
 def gemm_weight(weight, src_channels, weight_channels):
@@ -135,7 +167,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     Nc = dz.shape[1]                                   # possibly channel-padded dz
     wT = weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=CL)   # [Cin][kh][kw][Cout]
     wmat, wcols = gemm_weight(wT, [Nc], [N])
-    table = chunk_table([Nc], kh, kw, dev)
+    table, kcol = ordered_table([Nc], kh, kw, dev)
     src_C = [x.shape[1] for x in xs]
     if len(xs) == 1 and src_C[0] != Cin:                # zero-padded stem input: gradient not needed (images)
         return [None]
@@ -162,6 +194,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
     a.table, a.nkb = ptr(table), table.shape[0] // 8
     a.ntaps, a.kw = kh * kw, kw
+    a.kcol, a.l1_gather = (ptr(kcol) if kcol is not None else None), int(L1_GATHER and kcol is not None)
     a.act = 0
     ks = _ksplit(B * a.Ho * a.Wo, Cin, table.shape[0] // 8)
     if ks > 1:
@@ -293,7 +326,7 @@ class _ConvTC(torch.autograd.Function):
         Ho = (Hin + 2 * pad - kh) // stride + 1
         Wo = (Win + 2 * pad - kw) // stride + 1
         dev = xs[0].device
-        table = chunk_table(src_C, kh, kw, dev)
+        table, kcol = ordered_table(src_C, kh, kw, dev)
         wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
         nkb = table.shape[0] // 8
         ks = _ksplit(B * Ho * Wo, N, nkb) if (bias is None and residual is None and act == "none") else 1
@@ -308,6 +341,7 @@ class _ConvTC(torch.autograd.Function):
         a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
         a.table, a.nkb = ptr(table), table.shape[0] // 8
         a.ntaps, a.kw = kh * kw, kw
+        a.kcol, a.l1_gather = (ptr(kcol) if kcol is not None else None), int(L1_GATHER and kcol is not None)
         a.bias = ptr(bias.detach()) if bias is not None else None
         if residual is not None:
             residual = residual if residual.is_contiguous(memory_format=CL) else residual.contiguous(memory_format=CL)

@@ -26,6 +26,7 @@
 #ifndef JPB_HOST_EMU
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace {
 
@@ -58,12 +59,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(a), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// L1-allocating variant: neighbouring filter taps of one channel block re-read (almost) the same pixels; issued back to
+// back (host K-block order) they hit L1 instead of crossing the L2 fabric again
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// wait until the oldest of `pending` (1..4) committed groups has landed
+__device__ __forceinline__ void cp_async_wait_oldest(int pending) {
+  if (pending <= 1) cp_async_wait<0>();
+  else if (pending == 2) cp_async_wait<1>();
+  else if (pending == 3) cp_async_wait<2>();
+  else cp_async_wait<3>();
+}
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -104,6 +128,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 struct SrcDev {
   const float* ptr;
   int C, H, W, up;
@@ -117,8 +155,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // NT: N tile (UMMA N), multiple of 16 in [16,256].  STAGES: smem pipeline depth.
-template <int NT, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap wmap, JpbConvArgs a) {
+template <int NT, int STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap wmap, JpbConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [STAGES][A 16KB][B NT*128] | barriers | tmem ptr | src table
   constexpr int B_STAGE = NT * BK * 4;
@@ -198,50 +236,71 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
     const int c = tid & 7;           // 16-byte chunk column inside the 128-byte K row
     const int rbase = tid >> 3;      // rows rbase + 16*i
     const uint32_t swz = (uint32_t)((c ^ (rbase & 7)) << 4) + (uint32_t)(rbase & 7) * 128u + (uint32_t)(rbase >> 3) * 1024u;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      // x: source | (tap*nsrc + source) << 8, or -1; y: dy<<16 | dx (wgrad only); z: channel offset; w: valid bytes
-      const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + (kb0 + kb) * 8 + c);
-      const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
-      const bool live = e.x >= 0;
-      const float* base = srcs[live ? (e.x & 0xff) : 0].ptr + e.z;
-      const int* offs = s_off + (live ? (e.x >> 8) : 0) * BM + rbase;
-      if (!live || e.w == 16) {
-        for (int i = 0; i < 8; ++i) {
-          const int off = offs[16 * i];
-          const bool ok = live && off >= 0;
-          cp_async16(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
-        }
-      } else {
-        // partial chunk (a source whose channel count is not a multiple of 4, e.g. the 1-channel disparity):
-        // synchronous scalar loads, zero padded
-        const int nval = e.w >> 2;
-        for (int i = 0; i < 8; ++i) {
-          const int off = offs[16 * i];
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (off >= 0) {
-            const float* g = base + off;
-            v.x = g[0];
-            if (nval > 1) v.y = g[1];
-            if (nval > 2) v.z = g[2];
+    // Producer state machine: a K block is published (proxy fence + arrive on its full barrier) as soon as its copies have
+    // landed, independently of whether the NEXT block's stage is free — an in-order "issue kb, then publish kb-2" loop
+    // made every publish wait for an MMA two blocks back and left the tensor pipe idle 60 % of the time.
+    constexpr int MAXFLY = STAGES < 4 ? STAGES : 4;
+    const bool use_ca = a.l1_gather != 0;
+    int issued = 0, published = 0;
+    // the chunk-table row of the NEXT K block is fetched one block ahead: a dependent global load per block (an L2 round trip:
+    // L1 is carved down to almost nothing by the pipeline stages) was the largest single stall of the producer warps
+    int4 e_next = make_int4(-1, 0, 0, 0);
+    if (nkb > 0) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)kb0 * 8 + c);
+    while (published < nkb) {
+      bool can = false;
+      if (issued < nkb && issued - published < MAXFLY) {
+        const int s = issued % STAGES;
+        const uint32_t ph = ((uint32_t)(issued / STAGES) & 1u) ^ 1u;
+        if (issued == published) { mbar_wait(&empty_bar[s], ph); can = true; }
+        else can = mbar_test(&empty_bar[s], ph);
+      }
+      if (can) {
+        const int kb = issued, s = kb % STAGES;
+        // x: source | (tap*nsrc + source) << 8, or -1; y: dy<<16 | dx (wgrad only); z: channel offset; w: valid bytes
+        const int4 e = e_next;
+        if (kb + 1 < nkb) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + kb + 1) * 8 + c);
+        const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
+        const bool live = e.x >= 0;
+        const float* base = srcs[live ? (e.x & 0xff) : 0].ptr + e.z;
+        const int* offs = s_off + (live ? (e.x >> 8) : 0) * BM + rbase;
+        if (!live || e.w == 16) {
+          if (use_ca) {
+            for (int i = 0; i < 8; ++i) {
+              const int off = offs[16 * i];
+              const bool ok = live && off >= 0;
+              cp_async16_ca(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
+            }
+          } else {
+            for (int i = 0; i < 8; ++i) {
+              const int off = offs[16 * i];
+              const bool ok = live && off >= 0;
+              cp_async16(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
+            }
           }
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + (uint32_t)i * 2048u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        } else {
+          // partial chunk (a source whose channel count is not a multiple of 4, e.g. the 1-channel disparity):
+          // synchronous scalar loads, zero padded
+          const int nval = e.w >> 2;
+          for (int i = 0; i < 8; ++i) {
+            const int off = offs[16 * i];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (off >= 0) {
+              const float* g = base + off;
+              v.x = g[0];
+              if (nval > 1) v.y = g[1];
+              if (nval > 2) v.z = g[2];
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + (uint32_t)i * 2048u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          }
         }
-      }
-      cp_async_commit();
-      // keep up to 2 K blocks of copies in flight per thread; publish the one before the previous
-      if (kb >= 2) {
-        cp_async_wait<2>();
+        cp_async_commit();
+        ++issued;
+      } else {
+        cp_async_wait_oldest(issued - published);
         fence_async_proxy();
-        mbar_arrive(&full_bar[(kb - 2) % STAGES]);
+        mbar_arrive(&full_bar[published % STAGES]);
+        ++published;
       }
-    }
-    for (int kb = (nkb >= 2 ? nkb - 2 : 0); kb < nkb; ++kb) {
-      if (kb == nkb - 2) cp_async_wait<1>(); else cp_async_wait<0>();
-      fence_async_proxy();
-      mbar_arrive(&full_bar[kb % STAGES]);
     }
 
     // ===================================================== epilogue
@@ -258,20 +317,62 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
     if (!a.scatter) {
       out = a.out + (size_t)m * a.N + n0;
       res = a.residual ? a.residual + (size_t)m * a.N + n0 : nullptr;
-    } else if (m < M) {
+    } else {
       // dgrad scatter: this launch's output pixel (py,px) lives in the (padded) gradient domain; fold it back through
       // the reflection padding and the nearest up-sampling of the forward gather, into the source that owns channels n0..
       int j = 0, cbase = 0;
       while (j + 1 < a.ndst && n0 >= cbase + a.dst_C[j]) { cbase += a.dst_C[j]; ++j; }
-      const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
-      int ty = rem / a.Wo - a.fold_pad, tx = rem % a.Wo - a.fold_pad;
-      if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
-      atomic = split || a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
-      if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
-      out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
       vec_ok = (a.dst_C[j] & 3) == 0;
       nvalid = cbase + a.dst_C[j] - n0;
+      if (m < M) {
+        const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
+        int ty = rem / a.Wo - a.fold_pad, tx = rem % a.Wo - a.fold_pad;
+        if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
+        atomic = split || a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
+        if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
+        out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
+      }
     }
+    const bool vec_ok_all = vec_ok;           // uniform over the CTA (depends on n0 only)
+    const int nvalid_all = nvalid;
+    if (vec_ok_all) {
+      // Coalesced epilogue: 32 accumulator columns per pass go TMEM -> registers (lane = row) -> a padded per-warp tile in
+      // the (now idle) pipeline memory -> registers (8 lanes = one 128-byte row segment), so every global access of the
+      // bias / residual / output covers whole 128-byte lines instead of 32 rows x 16 bytes.
+      float* sbuf = reinterpret_cast<float*>(smem) + warp * (32 * 36 + 64);
+      unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(sbuf + 32 * 36);
+      rowptr[lane] = (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull;
+      __syncwarp();
+      const int c4 = (lane & 7) * 4, r0 = lane >> 3;
+      for (int j = 0; j < NT; j += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)j, v);
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(sbuf + lane * 36 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        __syncwarp();
+        const int col = j + c4;
+        if (col < nvalid_all) {
+          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 4 * i;
+            const unsigned long long rp = rowptr[r];
+            if (!rp) continue;
+            float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + col;
+            float4 o = *reinterpret_cast<const float4*>(sbuf + r * 36 + c4);
+            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+            if (a.residual) {
+              const float4 rq = *reinterpret_cast<const float4*>(a.residual + (size_t)(m0 + warp * 32 + r) * a.N + n0 + col);
+              o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+            }
+            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+            if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            else *reinterpret_cast<float4*>(op) = o;
+          }
+        }
+        __syncwarp();
+      }
+    } else {
     for (int j = 0; j < NT; j += 16) {
       float v[16];
       tmem_ld16(taddr + (uint32_t)j, v);   // warp-collective: every lane executes it, even for rows >= M
@@ -298,6 +399,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
       }
     }
     }
+    }
     tc_fence_before();
   } else if (warp == 4) {
     // ===================================================== weight TMA producer
@@ -307,7 +409,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
-        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], (kb0 + kb) * BK, n0);
+        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kb0 + kb] : (kb0 + kb) * BK, n0);
       }
     }
   } else {
@@ -348,8 +450,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_kernel(const __grid_consta
 //   M tile = 128 consecutive K positions (32 chunks of the table), N tile = NT output channels,
 //   each pipeline stage = 32 pixels = 4 tcgen05.mma (K = 8 pixels each).
 // The pixel range is split over gridDim.z CTAs; partial tiles are accumulated with red.global.add.
-template <int NT, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, JpbConvWgradArgs a) {
+template <int NT, int STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, JpbConvWgradArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int B_STAGE = NT * BK * 4;
   constexpr int STAGE = A_STAGE + B_STAGE;
@@ -408,46 +510,51 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
       poy[i] = rem / a.Wo;
       pox[i] = rem - poy[i] * a.Wo;
     }
-    for (int st = 0; st < nsteps; ++st) {
-      const int s = st % STAGES;
-      const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const uint32_t abase = smem_u32(smem + s * STAGE);
-      for (int i = 0; i < 8; ++i) {
-        const int slot = prow + 4 * i;            // pixel slot 0..31 of this step
-        // MN group (q>>3) of 4096 B = 8 K-groups of 4 pixels (512 B); row = slot&3; 32-byte chunk ((q&7)>>1) ^ row, 16-byte half q&1
-        const uint32_t dst = abase + (uint32_t)((q >> 3) * 4096 + (slot >> 2) * 512 + (slot & 3) * 128 +
-                                                 (((((q & 7) >> 1) ^ (slot & 3)) << 5) | ((q & 1) << 4)));
-        bool ok = pb[i] < a.B && e.x >= 0;
-        int iy = poy[i] * a.stride - a.pad + dy, ix = pox[i] * a.stride - a.pad + dx, b = pb[i];
-        if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
-        else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-        if (sup) { iy >>= 1; ix >>= 1; }
-        if (!ok) { iy = 0; ix = 0; b = 0; }
-        const float* g = sptr + ((size_t)(b * sH + iy) * sW + ix) * sC + e.z;
-        if (e.w == 16 || !ok) cp_async16(dst, g, ok ? 16u : 0u);
-        else {
-          float4 v = make_float4(g[0], nval > 1 ? g[1] : 0.f, nval > 2 ? g[2] : 0.f, 0.f);
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        }
-        // advance this slot by 32 pixels
-        pox[i] += 32;
-        while (pox[i] >= a.Wo) {
-          pox[i] -= a.Wo;
-          if (++poy[i] >= a.Ho) { poy[i] = 0; ++pb[i]; }
-        }
+    constexpr int MAXFLY = STAGES < 4 ? STAGES : 4;
+    int issued = 0, published = 0;      // same producer state machine as the forward kernel
+    while (published < nsteps) {
+      bool can = false;
+      if (issued < nsteps && issued - published < MAXFLY) {
+        const int s = issued % STAGES;
+        const uint32_t ph = ((uint32_t)(issued / STAGES) & 1u) ^ 1u;
+        if (issued == published) { mbar_wait(&empty_bar[s], ph); can = true; }
+        else can = mbar_test(&empty_bar[s], ph);
       }
-      cp_async_commit();
-      if (st >= 2) {
-        cp_async_wait<2>();
+      if (can) {
+        const int s = issued % STAGES;
+        const uint32_t abase = smem_u32(smem + s * STAGE);
+        for (int i = 0; i < 8; ++i) {
+          const int slot = prow + 4 * i;            // pixel slot 0..31 of this step
+          // MN group (q>>3) of 4096 B = 8 K-groups of 4 pixels (512 B); row = slot&3; 32-byte chunk ((q&7)>>1) ^ row, 16-byte half q&1
+          const uint32_t dst = abase + (uint32_t)((q >> 3) * 4096 + (slot >> 2) * 512 + (slot & 3) * 128 +
+                                                   (((((q & 7) >> 1) ^ (slot & 3)) << 5) | ((q & 1) << 4)));
+          bool ok = pb[i] < a.B && e.x >= 0;
+          int iy = poy[i] * a.stride - a.pad + dy, ix = pox[i] * a.stride - a.pad + dx, b = pb[i];
+          if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+          else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+          if (sup) { iy >>= 1; ix >>= 1; }
+          if (!ok) { iy = 0; ix = 0; b = 0; }
+          const float* g = sptr + ((size_t)(b * sH + iy) * sW + ix) * sC + e.z;
+          if (e.w == 16 || !ok) cp_async16(dst, g, ok ? 16u : 0u);
+          else {
+            float4 v = make_float4(g[0], nval > 1 ? g[1] : 0.f, nval > 2 ? g[2] : 0.f, 0.f);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          }
+          // advance this slot by 32 pixels
+          pox[i] += 32;
+          while (pox[i] >= a.Wo) {
+            pox[i] -= a.Wo;
+            if (++poy[i] >= a.Ho) { poy[i] = 0; ++pb[i]; }
+          }
+        }
+        cp_async_commit();
+        ++issued;
+      } else {
+        cp_async_wait_oldest(issued - published);
         fence_async_proxy();
-        mbar_arrive(&full_bar[(st - 2) % STAGES]);
+        mbar_arrive(&full_bar[published % STAGES]);
+        ++published;
       }
-    }
-    for (int st = (nsteps >= 2 ? nsteps - 2 : 0); st < nsteps; ++st) {
-      if (st == nsteps - 2) cp_async_wait<1>(); else cp_async_wait<0>();
-      fence_async_proxy();
-      mbar_arrive(&full_bar[st % STAGES]);
     }
     // ------------------------------------------------ epilogue: dW[n0 + j][k] (+)= D[k, j]
     mbar_wait(accum_bar, 0);
@@ -532,18 +639,25 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int NT, int STAGES>
+// Experiment switch (tools/bench_conv.py): JPB_CONV_VARIANT selects the pipeline depth / CTAs-per-SM table below.
+int conv_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JPB_CONV_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+template <int NT, int STAGES, int MINB>
 int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
   const int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
   static int configured = 0;
   if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
     configured = smem;
   }
   const int M = a->B * a->Ho * a->Wo;
   dim3 grid((M + BM - 1) / BM, (a->N + NT - 1) / NT, a->ksplit > 1 ? a->ksplit : 1);
-  conv_tc_fwd_kernel<NT, STAGES><<<grid, 192, smem, st>>>(map, *a);
+  conv_tc_fwd_kernel<NT, STAGES, MINB><<<grid, 192, smem, st>>>(map, *a);
   return jpb_status();
 }
 
@@ -570,26 +684,41 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  // pipeline depth x resident CTAs per SM: several shallow CTAs per SM overlap one tile's prologue (offset table, TMEM
+  // allocation) and epilogue (TMEM -> registers -> global) with the other tiles' main loops
+  const int nts = a->ntaps * a->nsrc;
+  const int var = conv_variant();
+  if (var == 0) {
+    switch (nt) {
+      case 16: return launch_fwd<16, 6, 1>(a, map, st);
+      case 32: return launch_fwd<32, 6, 1>(a, map, st);
+      case 64: return launch_fwd<64, 6, 1>(a, map, st);
+      case 128: return launch_fwd<128, 5, 1>(a, map, st);
+      default: return launch_fwd<256, 4, 1>(a, map, st);
+    }
+  }
   switch (nt) {
-    case 16: return launch_fwd<16, 6>(a, map, st);
-    case 32: return launch_fwd<32, 6>(a, map, st);
-    case 64: return launch_fwd<64, 6>(a, map, st);
-    case 128: return launch_fwd<128, 5>(a, map, st);
-    default: return launch_fwd<256, 4>(a, map, st);
+    case 16: return nts <= 27 ? launch_fwd<16, 3, 3>(a, map, st) : launch_fwd<16, 6, 1>(a, map, st);
+    case 32: return nts <= 27 ? launch_fwd<32, 3, 3>(a, map, st) : launch_fwd<32, 6, 1>(a, map, st);
+    case 64: return nts <= 9 ? launch_fwd<64, 3, 3>(a, map, st) : (nts <= 27 ? launch_fwd<64, 4, 2>(a, map, st) : launch_fwd<64, 6, 1>(a, map, st));
+    case 128: return nts <= 27 ? launch_fwd<128, 3, 2>(a, map, st) : launch_fwd<128, 5, 1>(a, map, st);
+    default:
+      if (var == 2 && nts <= 27) return launch_fwd<256, 2, 2>(a, map, st);
+      return launch_fwd<256, 4, 1>(a, map, st);
   }
 }
 
 namespace {
-template <int NT, int STAGES>
+template <int NT, int STAGES, int MINB>
 int launch_wgrad(const JpbConvWgradArgs* a, const CUtensorMap& map, cudaStream_t st) {
   constexpr int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<NT, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
     configured = true;
   }
   dim3 grid((a->nchunks + 31) / 32, (a->N + NT - 1) / NT, a->splits);
-  conv_tc_wgrad_kernel<NT, STAGES><<<grid, 192, smem, st>>>(map, *a);
+  conv_tc_wgrad_kernel<NT, STAGES, MINB><<<grid, 192, smem, st>>>(map, *a);
   return jpb_status();
 }
 }  // namespace
@@ -611,11 +740,20 @@ extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  const int var = conv_variant();
+  if (var == 0) {
+    switch (nt) {
+      case 32: return launch_wgrad<32, 6, 1>(a, map, st);
+      case 64: return launch_wgrad<64, 6, 1>(a, map, st);
+      case 128: return launch_wgrad<128, 5, 1>(a, map, st);
+      default: return launch_wgrad<256, 4, 1>(a, map, st);
+    }
+  }
   switch (nt) {
-    case 32: return launch_wgrad<32, 6>(a, map, st);
-    case 64: return launch_wgrad<64, 6>(a, map, st);
-    case 128: return launch_wgrad<128, 5>(a, map, st);
-    default: return launch_wgrad<256, 4>(a, map, st);
+    case 32: return launch_wgrad<32, 3, 3>(a, map, st);
+    case 64: return launch_wgrad<64, 3, 3>(a, map, st);
+    case 128: return launch_wgrad<128, 3, 2>(a, map, st);
+    default: return var == 2 ? launch_wgrad<256, 2, 2>(a, map, st) : launch_wgrad<256, 4, 1>(a, map, st);
   }
 }
 

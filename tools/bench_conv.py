@@ -23,6 +23,13 @@ LAYERS = [
     ("layer4 512->512 @10x32", [(512, 10, 32, 0)], 512, 3, 1, 1, 0, "none"),
     ("layout layer1 64->64 @256x256", [(64, 256, 256, 0)], 64, 3, 1, 1, 0, "none"),
     ("stem 7x7 s2 (3->4)->64 @320x1024", [(4, 320, 1024, 0)], 64, 7, 2, 3, 0, "none"),
+    ("iconv2 cat(256,up256,1)->256 @40x128", [(256, 40, 128, 0), (256, 20, 64, 1), (1, 40, 128, 0)], 256, 3, 1, 1, 1, "leaky"),
+    ("layout layer2 128->128 @128x128", [(128, 128, 128, 0)], 128, 3, 1, 1, 0, "none"),
+    ("layout layer3 256->256 @64x64", [(256, 64, 64, 0)], 256, 3, 1, 1, 0, "none"),
+    ("layout layer4 512->512 @32x32", [(512, 32, 32, 0)], 512, 3, 1, 1, 0, "none"),
+    ("pose layer1 64->64 @48x160", [(64, 48, 160, 0)], 64, 3, 1, 1, 0, "none"),
+    ("layoutdec up16->16 @256x256", [(16, 128, 128, 1)], 16, 3, 1, 1, 0, "none"),
+    ("crp2 1x1 256->256 @40x128", [(256, 40, 128, 0)], 256, 1, 1, 0, 0, "none"),
 ]
 
 
