@@ -177,6 +177,7 @@ typedef struct JpbConvArgs {
   const int* kcol;                      /* [nkb] weight column (float index) of K block i, or NULL for i*32: lets the host order
                                            the K blocks so that taps sharing input pixels are consecutive */
   int l1_gather;                        /* 1: gather through L1 (cp.async.ca) — pays off with the K-block order above */
+  long long* dbg;                       /* debug only: [512 CTAs][6 warps][8] globaltimer stamps (tools/conv_timeline.py), or NULL */
 } JpbConvArgs;
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
 

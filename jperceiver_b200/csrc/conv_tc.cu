@@ -37,6 +37,22 @@ constexpr int NPROD = 128;       // A producer threads (warps 0-3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Explicit shared-space accesses.  All shared pointers of these kernels derive from one dynamically aligned base, so the
+// compiler no longer knows their address space and emits GENERIC loads/stores (LD.E/ST.E): those sit on the same (long)
+// scoreboard as in-flight global loads — an offset-table read then waits for an unrelated L2 round trip.
+__device__ __forceinline__ int lds32(uint32_t a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) { unsigned long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -168,10 +184,21 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   SrcDev* srcs = reinterpret_cast<SrcDev*>(tmem_slot + 2);
   int* s_off = reinterpret_cast<int*>(srcs + JPB_CONV_MAX_SRC);
+  const uint32_t srcs_u32 = smem_u32(srcs), soff_u32 = smem_u32(s_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.B * a.Ho * a.Wo;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT;
+  // debug timeline (tools/conv_timeline.py): stamps[cta][warp][slot] = globaltimer ns at fixed points of each role
+#define JPB_STAMP(slot)                                                                                         \
+  do {                                                                                                          \
+    if (a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 512) {                        \
+      unsigned long long t_;                                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                    \
+      a.dbg[((size_t)blockIdx.x * 6 + warp) * 8 + (slot)] = (long long)t_;                                      \
+    }                                                                                                           \
+  } while (0)
+  JPB_STAMP(0);
   // split-K: gridDim.z CTAs share one output tile, each reduces a slice of the K blocks and adds its partial tile
   // atomically (only used for epilogue-free convolutions; the output is zero-filled by the caller)
   const int kb_per = (a.nkb + (int)gridDim.z - 1) / (int)gridDim.z;
@@ -180,6 +207,9 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   if (nkb > kb_per) nkb = kb_per;
   if (nkb < 0) nkb = 0;
   const bool split = gridDim.z > 1;
+  // rotated K loop (see the persistent kernel): CTAs of one N column must not all stream the same weight tile at once
+  const int rot = nkb > 1 ? (int)((((uint32_t)blockIdx.x * 0x9E3779B1u) >> 12) % (uint32_t)nkb) : 0;
+#define JPB_KROT(kb) ((kb) + rot >= nkb ? (kb) + rot - nkb : (kb) + rot)
 
   if (tid < a.nsrc) {
     srcs[tid].ptr = a.src[tid];
@@ -199,6 +229,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  JPB_STAMP(1);
 
   // ---- per-tile gather offsets, all 192 threads: s_off[(tap*nsrc + src)*BM + row] = element offset of the pixel that
   // tile row `row` reads for filter tap `tap` in source `src` (padding / reflection / up-sampling / stride folded), or -1
@@ -222,10 +253,11 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
           off = ((b * a.src_H[si] + iy) * a.src_W[si] + ix) * a.src_C[si];
         }
       }
-      s_off[idx] = off;
+      sts32(soff_u32 + (uint32_t)idx * 4u, off);
     }
   }
   __syncthreads();
+  JPB_STAMP(2);
 
   if (warp < 4) {
     // ===================================================== A gather (producers)
@@ -245,7 +277,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     // the chunk-table row of the NEXT K block is fetched one block ahead: a dependent global load per block (an L2 round trip:
     // L1 is carved down to almost nothing by the pipeline stages) was the largest single stall of the producer warps
     int4 e_next = make_int4(-1, 0, 0, 0);
-    if (nkb > 0) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)kb0 * 8 + c);
+    if (nkb > 0) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(0)) * 8 + c);
     while (published < nkb) {
       bool can = false;
       if (issued < nkb && issued - published < MAXFLY) {
@@ -258,21 +290,21 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         const int kb = issued, s = kb % STAGES;
         // x: source | (tap*nsrc + source) << 8, or -1; y: dy<<16 | dx (wgrad only); z: channel offset; w: valid bytes
         const int4 e = e_next;
-        if (kb + 1 < nkb) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + kb + 1) * 8 + c);
+        if (kb + 1 < nkb) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(kb + 1)) * 8 + c);
         const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
         const bool live = e.x >= 0;
-        const float* base = srcs[live ? (e.x & 0xff) : 0].ptr + e.z;
-        const int* offs = s_off + (live ? (e.x >> 8) : 0) * BM + rbase;
+        const float* base = reinterpret_cast<const float*>((uintptr_t)lds64(srcs_u32 + (uint32_t)(live ? (e.x & 0xff) : 0) * (uint32_t)sizeof(SrcDev))) + e.z;
+        const uint32_t offs = soff_u32 + (uint32_t)(((live ? (e.x >> 8) : 0) * BM + rbase) * 4);
         if (!live || e.w == 16) {
           if (use_ca) {
             for (int i = 0; i < 8; ++i) {
-              const int off = offs[16 * i];
+              const int off = lds32(offs + 64u * (uint32_t)i);
               const bool ok = live && off >= 0;
               cp_async16_ca(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
             }
           } else {
             for (int i = 0; i < 8; ++i) {
-              const int off = offs[16 * i];
+              const int off = lds32(offs + 64u * (uint32_t)i);
               const bool ok = live && off >= 0;
               cp_async16(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
             }
@@ -282,7 +314,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
           // synchronous scalar loads, zero padded
           const int nval = e.w >> 2;
           for (int i = 0; i < 8; ++i) {
-            const int off = offs[16 * i];
+            const int off = lds32(offs + 64u * (uint32_t)i);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (off >= 0) {
               const float* g = base + off;
@@ -304,9 +336,11 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     }
 
     // ===================================================== epilogue
+    JPB_STAMP(3);
     if (nkb > 0) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    JPB_STAMP(4);
     const int row = warp * 32 + lane;
     const int m = m0 + row;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -339,16 +373,16 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       // Coalesced epilogue: 32 accumulator columns per pass go TMEM -> registers (lane = row) -> a padded per-warp tile in
       // the (now idle) pipeline memory -> registers (8 lanes = one 128-byte row segment), so every global access of the
       // bias / residual / output covers whole 128-byte lines instead of 32 rows x 16 bytes.
-      float* sbuf = reinterpret_cast<float*>(smem) + warp * (32 * 36 + 64);
-      unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(sbuf + 32 * 36);
-      rowptr[lane] = (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull;
+      const uint32_t sbuf = smem_u32(smem) + (uint32_t)warp * (32 * 36 + 64) * 4u;
+      const uint32_t rowptr = sbuf + 32 * 36 * 4;
+      sts64(rowptr + (uint32_t)lane * 8u, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull);
       __syncwarp();
       const int c4 = (lane & 7) * 4, r0 = lane >> 3;
       for (int j = 0; j < NT; j += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)j, v);
         for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<float4*>(sbuf + lane * 36 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+          sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
         __syncwarp();
         const int col = j + c4;
         if (col < nvalid_all) {
@@ -356,10 +390,10 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
           if (a.bias) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);
           for (int i = 0; i < 8; ++i) {
             const int r = r0 + 4 * i;
-            const unsigned long long rp = rowptr[r];
+            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
             if (!rp) continue;
             float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + col;
-            float4 o = *reinterpret_cast<const float4*>(sbuf + r * 36 + c4);
+            float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
             o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
             if (a.residual) {
               const float4 rq = *reinterpret_cast<const float4*>(a.residual + (size_t)(m0 + warp * 32 + r) * a.N + n0 + col);
@@ -400,6 +434,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     }
     }
     }
+    JPB_STAMP(5);
     tc_fence_before();
   } else if (warp == 4) {
     // ===================================================== weight TMA producer
@@ -409,7 +444,8 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
-        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kb0 + kb] : (kb0 + kb) * BK, n0);
+        const int kr = kb0 + JPB_KROT(kb);
+        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kr] : kr * BK, n0);
       }
     }
   } else {
@@ -422,6 +458,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
+      if (kb == 0) JPB_STAMP(3);
       if (lane == 0) {
         const uint64_t ad = umma_desc_sw128(smem_u32(smem + s * STAGE));
         const uint64_t bd = umma_desc_sw128(smem_u32(smem + s * STAGE + A_STAGE));
@@ -432,12 +469,328 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       }
       __syncwarp();
     }
+    JPB_STAMP(4);
   }
   __syncthreads();
+  JPB_STAMP(6);
   if (warp == 4) {
     tc_fence_after();
     constexpr uint32_t cols = NT < 32 ? 32 : NT;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+#undef JPB_STAMP
+#undef JPB_KROT
+}
+
+
+// ======================================================================================== persistent forward (v2)
+// Same GEMM, different schedule.  The per-CTA timeline of the one-tile-per-CTA kernel above showed 20-45 % of every tile
+// outside the main loop (4.7 us of set-up + first operands, 5-20 us of epilogue during which every SM writes at once and
+// the tensor pipe idles).  Here one CTA per SM slot stays resident and walks over tiles:
+//   warps 0-3  epilogue   (TMEM lanes 32w..32w+31 -> padded smem tile -> coalesced global, fused bias/residual/act/scatter)
+//   warps 4-7  A gather   (cp.async through the per-tile offset table; the ring of STAGES buffers runs across tiles)
+//   warp  8    weight TMA
+//   warp  9    MMA issue  (accumulator double-buffered in TMEM: tile i+1 is computed while tile i is drained)
+template <int NT, int STAGES, int MINB>
+__global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_constant__ CUtensorMap wmap, JpbConvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int B_STAGE = NT * BK * 4;
+  constexpr int STAGE = A_STAGE + B_STAGE;
+  constexpr int ACC_STRIDE = NT < 32 ? 32 : NT;          // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr int EPI_WARP_FLOATS = 32 * 36 + 64;          // padded 32x32 tile + 32 row pointers
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + 4 * EPI_WARP_FLOATS);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accf_bar = empty_bar + STAGES;   // [2] accumulator buffer complete (MMA -> epilogue)
+  uint64_t* acce_bar = accf_bar + 2;         // [2] accumulator buffer drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce_bar + 2);
+  SrcDev* srcs = reinterpret_cast<SrcDev*>(tmem_slot + 2);
+  int* s_off = reinterpret_cast<int*>(srcs + JPB_CONV_MAX_SRC);
+  const uint32_t srcs_u32 = smem_u32(srcs), soff_u32 = smem_u32(s_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = a.B * a.Ho * a.Wo;
+  const int mtiles = (M + BM - 1) / BM, ntiles = (a.N + NT - 1) / NT;
+  const int ks = a.ksplit > 1 ? a.ksplit : 1;
+  const int total = mtiles * ntiles * ks;
+  const int kb_per = (a.nkb + ks - 1) / ks;
+  const bool split = ks > 1;
+
+  if (tid < a.nsrc) {
+    srcs[tid].ptr = a.src[tid];
+    srcs[tid].C = a.src_C[tid]; srcs[tid].H = a.src_H[tid]; srcs[tid].W = a.src_W[tid]; srcs[tid].up = a.src_up[tid];
+  }
+  if (tid == 32) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD + 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], 1); mbar_init(&acce_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile t -> (m tile, n tile, K slice); every role walks the same sequence
+#define JPB_TILE_DECODE(t)                                              \
+  const int mt_ = (t) % mtiles, nz_ = (t) / mtiles;                     \
+  const int m0 = mt_ * BM, n0 = (nz_ % ntiles) * NT;                    \
+  const int kb0 = (nz_ / ntiles) * kb_per;                              \
+  int nkb = a.nkb - kb0;                                                \
+  if (nkb > kb_per) nkb = kb_per;                                       \
+  if (nkb < 0) nkb = 0;                                                 \
+  const int rot = nkb > 1 ? (int)((((uint32_t)(t) * 0x9E3779B1u) >> 12) % (uint32_t)nkb) : 0;
+  // `rot` rotates the K loop of each tile: K is a sum, so any order is valid, and CTAs that would otherwise stream the SAME
+  // weight tile at the same moment (every CTA of an N column walks K in lock-step) now read different ones — without it the
+  // few L2 slices holding the current 8-32 KB weight tile serve all 148 SMs at once and bound the whole main loop.
+#define JPB_KROT(kb) ((kb) + rot >= nkb ? (kb) + rot - nkb : (kb) + rot)
+
+  if (warp >= 4 && warp < 8) {
+    // ===================================================== A gather (producers)
+    const int ptid = tid - 128;
+    const int c = ptid & 7;           // 16-byte chunk column inside the 128-byte K row
+    const int rbase = ptid >> 3;      // rows rbase + 16*i
+    const uint32_t swz = (uint32_t)((c ^ (rbase & 7)) << 4) + (uint32_t)(rbase & 7) * 128u + (uint32_t)(rbase >> 3) * 1024u;
+    constexpr int MAXFLY = STAGES < 4 ? STAGES : 4;
+    const bool use_ca = a.l1_gather != 0;
+    const int HoWo = a.Ho * a.Wo;
+    int ring = 0;                     // K blocks issued by this CTA so far (ring position)
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      JPB_TILE_DECODE(t)
+      (void)n0;
+      // ---- gather offsets of this tile: thread = tile row; s_off[(tap*nsrc + src)*BM + row] = element offset of the pixel the
+      // row reads for filter tap `tap` in source `src` (padding / reflection / up-sampling / stride folded), or -1
+      {
+        const int m = m0 + ptid;
+        const bool rowok = m < M;
+        const int b = rowok ? m / HoWo : 0, rem = m - b * HoWo;
+        const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
+        int tap = 0;
+        for (int ky = 0; tap < a.ntaps; ++ky)
+          for (int kx = 0; kx < a.kw && tap < a.ntaps; ++kx, ++tap) {
+            int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+            bool ok = rowok;
+            if (a.in_div == 2) { ok = ok && !((iy | ix) & 1); iy >>= 1; ix >>= 1; }   // dgrad of a stride-2 convolution
+            if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
+            else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+            for (int si = 0; si < a.nsrc; ++si) {
+              int off = -1;
+              if (ok) {
+                const int sy = a.src_up[si] ? (iy >> 1) : iy, sx = a.src_up[si] ? (ix >> 1) : ix;
+                off = ((b * a.src_H[si] + sy) * a.src_W[si] + sx) * a.src_C[si];
+              }
+              sts32(soff_u32 + (uint32_t)((tap * a.nsrc + si) * BM + ptid) * 4u, off);
+            }
+          }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      int issued = 0, published = 0;
+      int4 e_next = make_int4(-1, 0, 0, 0);
+      if (nkb > 0) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(0)) * 8 + c);
+      while (published < nkb) {
+        bool can = false;
+        if (issued < nkb && issued - published < MAXFLY) {
+          const int ri = ring + issued, s = ri % STAGES;
+          const uint32_t ph = ((uint32_t)(ri / STAGES) & 1u) ^ 1u;
+          if (issued == published) { mbar_wait(&empty_bar[s], ph); can = true; }
+          else can = mbar_test(&empty_bar[s], ph);
+        }
+        if (can) {
+          const int kb = issued, s = (ring + issued) % STAGES;
+          const int4 e = e_next;   // x: source | (tap*nsrc + source) << 8, or -1; z: channel offset; w: valid bytes
+          if (kb + 1 < nkb) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(kb + 1)) * 8 + c);
+          const uint32_t sbase = smem_u32(smem + s * STAGE) + swz;
+          const bool live = e.x >= 0;
+          const float* base = reinterpret_cast<const float*>((uintptr_t)lds64(srcs_u32 + (uint32_t)(live ? (e.x & 0xff) : 0) * (uint32_t)sizeof(SrcDev))) + e.z;
+          const uint32_t offs = soff_u32 + (uint32_t)(((live ? (e.x >> 8) : 0) * BM + rbase) * 4);
+          if (!live || e.w == 16) {
+            if (use_ca) {
+              for (int i = 0; i < 8; ++i) {
+                const int off = lds32(offs + 64u * (uint32_t)i);
+                const bool ok = live && off >= 0;
+                cp_async16_ca(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
+              }
+            } else {
+              for (int i = 0; i < 8; ++i) {
+                const int off = lds32(offs + 64u * (uint32_t)i);
+                const bool ok = live && off >= 0;
+                cp_async16(sbase + (uint32_t)i * 2048u, base + (ok ? off : 0), ok ? 16u : 0u);
+              }
+            }
+          } else {
+            // partial chunk (a source whose channel count is not a multiple of 4, e.g. the 1-channel disparity)
+            const int nval = e.w >> 2;
+            for (int i = 0; i < 8; ++i) {
+              const int off = lds32(offs + 64u * (uint32_t)i);
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (off >= 0) {
+                const float* g = base + off;
+                v.x = g[0];
+                if (nval > 1) v.y = g[1];
+                if (nval > 2) v.z = g[2];
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + (uint32_t)i * 2048u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+          }
+          cp_async_commit();
+          ++issued;
+        } else {
+          cp_async_wait_oldest(issued - published);
+          fence_async_proxy();
+          mbar_arrive(&full_bar[(ring + published) % STAGES]);
+          ++published;
+        }
+      }
+      ring += nkb;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // nobody still reads s_off when the next tile's offsets are written
+    }
+  } else if (warp == 8) {
+    // ===================================================== weight TMA producer
+    if (lane == 0) {
+      int ring = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        JPB_TILE_DECODE(t)
+        (void)m0;
+        for (int kb = 0; kb < nkb; ++kb, ++ring) {
+          const int s = ring % STAGES;
+          const uint32_t ph = (uint32_t)(ring / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
+          const int kr = kb0 + JPB_KROT(kb);
+          tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kr] : kr * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int ring = 0, it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      JPB_TILE_DECODE(t)
+      (void)m0; (void)n0; (void)kb0;
+      if (nkb == 0) continue;
+      const int buf = it & 1;
+      mbar_wait(&acce_bar[buf], (((uint32_t)(it >> 1)) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_STRIDE);
+      for (int kb = 0; kb < nkb; ++kb, ++ring) {
+        const int s = ring % STAGES;
+        const uint32_t ph = (uint32_t)(ring / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(smem + s * STAGE));
+          const uint64_t bd = umma_desc_sw128(smem_u32(smem + s * STAGE + A_STAGE));
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (kb == nkb - 1) umma_commit(&accf_bar[buf]);
+        }
+        __syncwarp();
+      }
+      ++it;
+    }
+  } else {
+    // ===================================================== epilogue (warps 0-3)
+    const uint32_t sbuf = smem_u32(epi) + (uint32_t)(warp * EPI_WARP_FLOATS) * 4u;
+    const uint32_t rowptr = sbuf + 32 * 36 * 4;
+    const int c4 = (lane & 7) * 4, r0 = lane >> 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      JPB_TILE_DECODE(t)
+      (void)kb0;
+      if (nkb == 0) continue;
+      const int buf = it & 1;
+      const int row = warp * 32 + lane;
+      const int m = m0 + row;
+      float* out = nullptr;
+      bool atomic = split, vec_ok = (a.N & 3) == 0;
+      int nvalid = a.N - n0;                    // channels of this N tile that exist
+      if (!a.scatter) {
+        out = a.out + (size_t)m * a.N + n0;
+      } else {
+        // dgrad scatter: this launch's output pixel (py,px) lives in the (padded) gradient domain; fold it back through
+        // the reflection padding and the nearest up-sampling of the forward gather, into the source that owns channels n0..
+        int j = 0, cbase = 0;
+        while (j + 1 < a.ndst && n0 >= cbase + a.dst_C[j]) { cbase += a.dst_C[j]; ++j; }
+        vec_ok = (a.dst_C[j] & 3) == 0;
+        nvalid = cbase + a.dst_C[j] - n0;
+        if (m < M) {
+          const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
+          int ty = rem / a.Wo - a.fold_pad, tx = rem % a.Wo - a.fold_pad;
+          if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
+          atomic = split || a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
+          if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
+          out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
+        }
+      }
+      if (nvalid > NT) nvalid = NT;
+      sts64(rowptr + (uint32_t)lane * 8u, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull);
+      mbar_wait(&accf_bar[buf], ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+      __syncwarp();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
+      for (int j = 0; j < NT && j < nvalid; j += 32) {
+        const int col = j + c4;
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias && vec_ok && col < nvalid) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);   // issued early: overlaps the TMEM load
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)j, v);
+        for (int q = 0; q < 32; q += 4)
+          sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
+        __syncwarp();
+        if (vec_ok) {
+          if (col < nvalid) {
+            for (int i = 0; i < 8; ++i) {
+              const int r = r0 + 4 * i;
+              const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
+              if (!rp) continue;
+              float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + col;
+              float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
+              o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+              if (a.residual) {
+                const float4 rq = *reinterpret_cast<const float4*>(a.residual + (size_t)(m0 + warp * 32 + r) * a.N + n0 + col);
+                o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+              }
+              o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+              if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+              else *reinterpret_cast<float4*>(op) = o;
+            }
+          }
+        } else {
+          // ragged channel counts (destination C % 4 != 0): scalar accesses, lane = column
+          for (int r = 0; r < 32; ++r) {
+            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
+            const int cc = j + lane;
+            if (!rp || cc >= nvalid) continue;
+            float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + cc;
+            float o = __int_as_float(lds32(sbuf + (uint32_t)(r * 36 + lane) * 4u));
+            if (a.bias) o += a.bias[n0 + cc];
+            if (a.residual) o += a.residual[(size_t)(m0 + warp * 32 + r) * a.N + n0 + cc];
+            o = apply_act(o, a.act);
+            if (rp & 1ull) atomicAdd(op, o); else *op = o;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acce_bar[buf]);
+      ++it;
+    }
+  }
+#undef JPB_TILE_DECODE
+#undef JPB_KROT
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -639,10 +992,31 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+template <int NT, int STAGES, int MINB>
+int launch_fwd2(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
+  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 4 * (32 * 36 + 64) * 4 + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+  static int configured = 0;
+  if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(conv_tc_fwd2_kernel<NT, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = smem;
+  }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int M = a->B * a->Ho * a->Wo;
+  const long long total = (long long)((M + BM - 1) / BM) * ((a->N + NT - 1) / NT) * (a->ksplit > 1 ? a->ksplit : 1);
+  const int slots = sms * MINB;
+  // balanced persistent grid: every CTA walks ceil(total / grid) or one fewer tiles
+  const int waves = (int)((total + slots - 1) / slots);
+  const int grid = (int)((total + waves - 1) / waves);
+  conv_tc_fwd2_kernel<NT, STAGES, MINB><<<grid, 320, smem, st>>>(map, *a);
+  return jpb_status();
+}
+
 // Experiment switch (tools/bench_conv.py): JPB_CONV_VARIANT selects the pipeline depth / CTAs-per-SM table below.
 int conv_variant() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("JPB_CONV_VARIANT"); v = e ? atoi(e) : 1; }
+  if (v < 0) { const char* e = getenv("JPB_CONV_VARIANT"); v = e ? atoi(e) : 5; }
   return v;
 }
 
@@ -688,6 +1062,36 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   // allocation) and epilogue (TMEM -> registers -> global) with the other tiles' main loops
   const int nts = a->ntaps * a->nsrc;
   const int var = conv_variant();
+  if (var == 5) {
+    // measured best per N tile (tools/bench_conv.py, B200): narrow tiles -> persistent kernel, two CTAs per SM; wide tiles ->
+    // one tile per CTA, two shallow CTAs per SM when there are enough tiles to fill them, else one deep CTA
+    const long long tiles = (long long)((a->B * a->Ho * a->Wo + BM - 1) / BM) * ((a->N + nt - 1) / nt) * (a->ksplit > 1 ? a->ksplit : 1);
+    switch (nt) {
+      case 16: return launch_fwd2<16, 4, 2>(a, map, st);
+      case 32: return launch_fwd2<32, 4, 2>(a, map, st);
+      case 64: return nts <= 27 ? launch_fwd2<64, 3, 2>(a, map, st) : launch_fwd2<64, 4, 1>(a, map, st);
+      case 128: return (nts <= 27 && tiles > 148) ? launch_fwd<128, 3, 2>(a, map, st) : launch_fwd<128, 5, 1>(a, map, st);
+      default: return (nts <= 27 && tiles > 148) ? launch_fwd<256, 2, 2>(a, map, st) : launch_fwd<256, 4, 1>(a, map, st);
+    }
+  }
+  if (var >= 3) {   // persistent kernel
+    if (var == 4) {
+      switch (nt) {
+        case 16: return launch_fwd2<16, 4, 2>(a, map, st);
+        case 32: return launch_fwd2<32, 4, 2>(a, map, st);
+        case 64: return nts <= 27 ? launch_fwd2<64, 3, 2>(a, map, st) : launch_fwd2<64, 4, 1>(a, map, st);
+        case 128: return launch_fwd2<128, 4, 1>(a, map, st);
+        default: return launch_fwd2<256, 4, 1>(a, map, st);
+      }
+    }
+    switch (nt) {
+      case 16: return launch_fwd2<16, 6, 1>(a, map, st);
+      case 32: return launch_fwd2<32, 6, 1>(a, map, st);
+      case 64: return launch_fwd2<64, 6, 1>(a, map, st);
+      case 128: return launch_fwd2<128, 5, 1>(a, map, st);
+      default: return launch_fwd2<256, 4, 1>(a, map, st);
+    }
+  }
   if (var == 0) {
     switch (nt) {
       case 16: return launch_fwd<16, 6, 1>(a, map, st);
@@ -753,7 +1157,7 @@ extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
     case 32: return launch_wgrad<32, 3, 3>(a, map, st);
     case 64: return launch_wgrad<64, 3, 3>(a, map, st);
     case 128: return launch_wgrad<128, 3, 2>(a, map, st);
-    default: return var == 2 ? launch_wgrad<256, 2, 2>(a, map, st) : launch_wgrad<256, 4, 1>(a, map, st);
+    default: return var != 1 ? launch_wgrad<256, 2, 2>(a, map, st) : launch_wgrad<256, 4, 1>(a, map, st);
   }
 }
 
