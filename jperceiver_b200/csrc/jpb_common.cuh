@@ -43,6 +43,8 @@ static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define __expf expf
 #define __logf logf
+#define __cosf cosf
+#define __sinf sinf
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 using std::max;

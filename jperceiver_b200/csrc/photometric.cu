@@ -135,7 +135,7 @@ __device__ __forceinline__ float reproj_error(const float* xs, const float* ys, 
 }
 
 // ------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256) photometric_fwd_kernel(JpbPhotoArgs a) {
+__global__ void __launch_bounds__(256) photometric_fwd_generic_kernel(JpbPhotoArgs a) {
   JPB_DYN_SMEM(float, sm);
   __shared__ SrcGeom geom[JPB_MAX_SRC];
   __shared__ double red[32];
@@ -223,6 +223,207 @@ __global__ void __launch_bounds__(256) photometric_fwd_kernel(JpbPhotoArgs a) {
   const double tot = jpb_block_sum<double>((double)local, red);
   if (JPB_TID == 0) atomicAdd(a.loss_sum, tot);
 }
+
+
+// ------------------------------------------------------------------------------------ forward, fast path (F <= 2)
+// Same staging as the generic kernel (phase 1), but on 32x32 tiles, and the 3x3 window statistics are separable running
+// sums: a thread owns one column of an 8-row strip, walks down it once per (channel, candidate) keeping the horizontal
+// 3-sums of x, x^2 and x*y of the previous two rows in registers, so one output costs 3 shared loads + ~40 flops per
+// (candidate, channel) instead of 18 loads + ~70 flops; the target's own window sums are computed once per channel and
+// shared by all candidates; one Philox call per pixel feeds the noise of both identity candidates.
+constexpr int QT_W = 32, QT_H = 32, QSR = 4;                   // tile and strip height
+constexpr int Q1_W = QT_W + 2, Q1_H = QT_H + 2, Q1_N = Q1_W * Q1_H;
+constexpr int QNC = 4;                                          // candidates handled by the fast path (2 identity + 2 warped)
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+#ifdef JPB_HOST_EMU
+  return sqrtf(x);
+#else
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
+// two independent standard normals from one Philox call (fast-math Box-Muller; the draw only breaks ties at 1e-5)
+__device__ __forceinline__ void randn2(uint64_t seed, uint64_t stream, uint64_t ctr, float& n0, float& n1) {
+  uint32_t r[4];
+  jpb_philox4(seed, stream, ctr, r);
+  const float u1 = jpb_u01(r[0]), u2 = jpb_u01(r[1]);
+  const float rad = fast_sqrt(-2.0f * __logf(u1));
+  const float ang = 6.28318530717958647692f * u2;
+  n0 = rad * __cosf(ang);
+  n1 = rad * __sinf(ang);
+}
+
+// one candidate, one channel, one strip: running 3x3 sums down the column.  X(r, j) returns the candidate's value in strip
+// row r (0 = apron row above the strip) and horizontal neighbour j (0 left, 1 centre, 2 right).
+#define JPB_STRIP_CANDIDATE(X, ERR)                                                                        \
+  {                                                                                                        \
+    float h1a = 0.f, h1b = 0.f, h2a = 0.f, h2b = 0.f, h3a = 0.f, h3b = 0.f, xc_prev = 0.f;                 \
+    _Pragma("unroll") for (int r = 0; r < QSR + 2; ++r) {                                                  \
+      const float xa = X(r, 0), xb = X(r, 1), xc = X(r, 2);                                                \
+      const float h1 = xa + xb + xc;                                                                       \
+      const float h2 = xa * xa + xb * xb + xc * xc;                                                        \
+      const float h3 = xa * yw[r][0] + xb * yw[r][1] + xc * yw[r][2];                                      \
+      if (r >= 2) {                                                                                        \
+        const int o = r - 2; /* output row; its window centre is strip row r-1 */                          \
+        const float mx = (h1a + h1b + h1) * (1.f / 9.f), m_y = my[o];                                      \
+        const float vx = (h2a + h2b + h2) * (1.f / 9.f) - mx * mx;                                         \
+        const float vxy = (h3a + h3b + h3) * (1.f / 9.f) - mx * m_y;                                       \
+        const float n = (2.f * mx * m_y + SSIM_C1) * (2.f * vxy + SSIM_C2);                                \
+        const float d = (mx * mx + cy1[o]) * (vx + cy2[o]);                                                \
+        const float ssim = __saturatef(0.5f - 0.5f * __fdividef(n, d));                                    \
+        const float df = yw[r - 1][1] - xc_prev;                                                           \
+        ERR[o] += (0.85f / 3.f) * ssim + (0.15f / 3.f) * fast_sqrt(df * df + 1e-6f);                       \
+      }                                                                                                    \
+      h1a = h1b; h1b = h1; h2a = h2b; h2b = h2; h3a = h3b; h3b = h3; xc_prev = xb;                         \
+    }                                                                                                      \
+  }
+
+__global__ void __launch_bounds__(256, 3) photometric_fwd_kernel(JpbPhotoArgs a) {
+  JPB_DYN_SMEM(float, sm);
+  __shared__ SrcGeom geom[JPB_MAX_SRC];
+  __shared__ double red[32];
+  const int b = blockIdx.z, x0 = blockIdx.x * QT_W, y0 = blockIdx.y * QT_H;
+  const int F = a.F, H = a.H, W = a.W;
+  const int nid = a.automask ? F : 0;
+  float* s_tgt = sm;                       // [3][Q1_N]
+  float* s_wp = s_tgt + 3 * Q1_N;          // [F][3][Q1_N] warped sources (the identity candidates are read from global / L1)
+  const size_t plane = (size_t)H * W;
+
+  for (int f = JPB_TID; f < F; f += JPB_NT) make_geom(a.K + b * 16, a.T[f] + b * 16, geom[f]);
+  __syncthreads();
+
+  // ---- phase 1: stage target and warped pixels of the tile + 1-pixel apron (reflect-indexed at the border)
+  const float* disp = a.disp + (size_t)b * a.hs * a.ws;
+  const float sy = (float)a.hs / (float)H, sx = (float)a.ws / (float)W;
+  const float* iK = a.invK + b * 16;
+#pragma unroll 2
+  for (int e = JPB_TID; e < Q1_N; e += JPB_NT) {
+    const int hy = e / Q1_W, hx = e - hy * Q1_W;
+    const int y = jpb_reflect(min(y0 + hy - 1, H), H), x = jpb_reflect(min(x0 + hx - 1, W), W);
+    const size_t o = (size_t)y * W + x;
+    const float* tg = a.target + (size_t)b * 3 * plane + o;
+    s_tgt[e] = tg[0]; s_tgt[Q1_N + e] = tg[plane]; s_tgt[2 * Q1_N + e] = tg[2 * plane];
+    DispTap tp;
+    const float D = disp_upsample(disp, a.hs, a.ws, sy, sx, y, x, tp);
+    const float z = 1.f / (a.min_disp + (a.max_disp - a.min_disp) * D);
+    const bool interior = hy >= 1 && hy <= QT_H && hx >= 1 && hx <= QT_W && (y0 + hy - 1) < H && (x0 + hx - 1) < W;
+    float rc[3];
+    pixel_ray(iK, x, y, rc);
+    for (int f = 0; f < F; ++f) {
+      const float* sp = a.src[f] + (size_t)b * 3 * plane;
+      Sample s;
+      project(geom[f], z, rc, W, H, s);
+      float v[3];
+      gather3(sp, H, W, s, v);
+      float* d = s_wp + f * 3 * Q1_N + e;
+      d[0] = v[0]; d[Q1_N] = v[1]; d[2 * Q1_N] = v[2];
+      if (interior && a.warped[f]) {
+        float* wo = a.warped[f] + (size_t)b * 3 * plane + o;
+        wo[0] = v[0]; wo[plane] = v[1]; wo[2 * plane] = v[2];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: one (column, QSR-row strip) per thread
+  float local = 0.f;
+  for (int e = JPB_TID; e < QT_W * (QT_H / QSR); e += JPB_NT) {
+    const int tx = e % QT_W, ry0 = (e / QT_W) * QSR;
+    const int x = x0 + tx;
+    if (x >= W || y0 + ry0 >= H) continue;
+    float err[QNC][QSR];
+#pragma unroll
+    for (int k = 0; k < QNC; ++k)
+#pragma unroll
+      for (int r = 0; r < QSR; ++r) err[k][r] = 0.f;
+    const int col = tx + 1;   // apron column of the window centre
+    // global (reflected) coordinates of the strip's window rows / columns, for the identity candidates
+    const int gxa = jpb_reflect(x - 1, W), gxc = jpb_reflect(min(x + 1, W), W);
+    int grow[QSR + 2];
+#pragma unroll
+    for (int r = 0; r < QSR + 2; ++r) grow[r] = jpb_reflect(min(y0 + ry0 + r - 1, H), H) * W;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      // target window: the three horizontal neighbours of every row of the strip (+apron rows), and per output row
+      // my = mean, cy1 = my^2 + C1, cy2 = var_y + C2
+      float yw[QSR + 2][3], my[QSR], cy1[QSR], cy2[QSR];
+      {
+        const float* yp = s_tgt + c * Q1_N + ry0 * Q1_W + col;
+        float h1a = 0.f, h1b = 0.f, h2a = 0.f, h2b = 0.f;
+#pragma unroll
+        for (int r = 0; r < QSR + 2; ++r) {
+          const float ya = yp[r * Q1_W - 1], yb = yp[r * Q1_W], yc = yp[r * Q1_W + 1];
+          yw[r][0] = ya; yw[r][1] = yb; yw[r][2] = yc;
+          const float h1 = ya + yb + yc, h2 = ya * ya + yb * yb + yc * yc;
+          if (r >= 2) {
+            const float m = (h1a + h1b + h1) * (1.f / 9.f);
+            my[r - 2] = m;
+            cy1[r - 2] = m * m + SSIM_C1;
+            cy2[r - 2] = (h2a + h2b + h2) * (1.f / 9.f) - m * m + SSIM_C2;
+          }
+          h1a = h1b; h1b = h1; h2a = h2b; h2b = h2;
+        }
+      }
+      if (nid) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          if (f < F) {
+            const float* gp = a.src[f] + ((size_t)b * 3 + c) * plane;
+#define JPB_XG(r, j) __ldg(gp + grow[r] + ((j) == 0 ? gxa : ((j) == 1 ? x : gxc)))
+            JPB_STRIP_CANDIDATE(JPB_XG, err[f])
+#undef JPB_XG
+          }
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        if (f < F) {
+          const float* xp = s_wp + (f * 3 + c) * Q1_N + ry0 * Q1_W + col;
+#define JPB_XS(r, j) xp[(r) * Q1_W + (j) - 1]
+          JPB_STRIP_CANDIDATE(JPB_XS, err[2 + f])
+#undef JPB_XS
+        }
+      }
+    }
+    // ---- candidates -> min / argmin (identity terms first, with their tie-breaking noise)
+#pragma unroll
+    for (int r = 0; r < QSR; ++r) {
+      const int y = y0 + ry0 + r;
+      if (y >= H) continue;
+      const size_t po = (size_t)b * plane + (size_t)y * W + x;
+      float nz[2] = {0.f, 0.f};
+      if (nid && !a.noise[0] && a.noise_scale != 0.f) {
+        randn2(a.seed, a.stream + (a.step ? 64ull * (uint64_t)a.step[0] : 0ull), (uint64_t)po, nz[0], nz[1]);
+        nz[0] *= a.noise_scale; nz[1] *= a.noise_scale;
+      }
+      float best = 3.0e38f;
+      int besti = 0;
+      if (nid) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+          if (f < F) {
+            const float v = err[f][r] + (a.noise[f] ? a.noise[f][po] : nz[f]);
+            if (v < best) { best = v; besti = f; }
+          }
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+        if (f < F) {
+          const float v = err[2 + f][r];
+          if (v < best) { best = v; besti = nid + f; }
+        }
+      if (a.min_index) a.min_index[po] = (long long)besti;
+      if (a.winner) a.winner[po] = (unsigned char)besti;
+      local += best;
+    }
+  }
+  const double tot = jpb_block_sum<double>((double)local, red);
+  if (JPB_TID == 0) atomicAdd(a.loss_sum, tot);
+}
+#undef JPB_STRIP_CANDIDATE
 
 // ------------------------------------------------------------------------------------ backward
 // d(loss_s)/d(disp_s) and d(loss_s)/d(T_f).  Gradient reaches a warped candidate only where it is the
@@ -436,16 +637,29 @@ __global__ void __launch_bounds__(256) photometric_bwd_kernel(JpbPhotoArgs a, Jp
 extern "C" int jpb_photometric_fwd(const JpbPhotoArgs* a, void* stream) {
   if (!a || a->F < 1 || a->F > JPB_MAX_SRC || a->H < 3 || a->W < 3 || !a->loss_sum) return JPB_ERR_ARG;
   const int nid = a->automask ? a->F : 0;
+  if (a->F <= 2) {   // fast path: 32x32 tiles, separable window sums (every reference configuration: F <= 2)
+    const size_t smem = (size_t)(3 + 3 * a->F) * Q1_N * sizeof(float);
+    dim3 grid((a->W + QT_W - 1) / QT_W, (a->H + QT_H - 1) / QT_H, a->B);
+#ifndef JPB_HOST_EMU
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      if (cudaFuncSetAttribute(photometric_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+      configured = smem;
+    }
+#endif
+    JPB_LAUNCH(photometric_fwd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+    return jpb_status();
+  }
   const size_t smem = (size_t)(3 + 3 * nid + 3 * a->F) * P1_N * sizeof(float);
   dim3 grid((a->W + PT_W - 1) / PT_W, (a->H + PT_H - 1) / PT_H, a->B);
 #ifndef JPB_HOST_EMU
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(photometric_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(photometric_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
     configured = smem;
   }
 #endif
-  JPB_LAUNCH(photometric_fwd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+  JPB_LAUNCH(photometric_fwd_generic_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a);
   return jpb_status();
 }
 
