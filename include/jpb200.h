@@ -198,6 +198,7 @@ typedef struct JpbConvWgradArgs {
   int w_cols;
   int splits;
   float* dbg;                /* debug only: first pipeline stage (A then B tile) is copied here when non-NULL */
+  int accumulate;            /* 1: always add into dw (dw aliases the parameter's slot of the flat gradient buffer) */
 } JpbConvWgradArgs;
 int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
 
@@ -217,16 +218,20 @@ int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int 
 
 /* ---- BatchNorm2d (training: per-GPU batch statistics) fused with the residual add and ReLU that follow it
  * (resnet.py:28-45, layout_model.py:146-158).  x, res, y, dy, dx, dres: [rows][C] NHWC, C % 4 == 0.
- * stat: [2][C] floats (mean, 1/sqrt(var+eps)) written by the forward and read by the backward; acc: workspace of
- * jpb_bn_workspace_doubles(C) doubles (per-block partial sums, no initialisation needed).  running_* are updated in
- * place (momentum, unbiased variance).                                                                          */
+ * stat: [2][C] floats (mean, 1/sqrt(var+eps)) written by the forward and read by the backward.
+ * ws: workspace of jpb_bn_workspace_doubles(C) doubles (final sums, per-block partials, a ticket counter); the caller
+ * zero-fills it ONCE when allocating it (the kernels leave the counter at zero) and may share one workspace between all
+ * BatchNorm calls of a stream.  Each direction is two launches: column sums whose last block folds the partials and
+ * finalises (statistics + running_* update + num_batches_tracked += nbt_inc, or the affine gradients), then the apply pass.
+ * accumulate != 0: dgamma/dbeta are added to (they alias the flat gradient buffer) instead of overwritten.          */
 long long jpb_bn_workspace_doubles(int C);
 int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                     float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream);
+                     long long* num_batches_tracked, int nbt_inc, float momentum, float eps, int relu, float* y, float* stat,
+                     double* ws, long long rows, int C, void* stream);
 int jpb_bn_eval_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* stat, int relu, float* y,
                     long long rows, int C, void* stream);
 int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
-                     float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream);
+                     float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream);
 
 /* ---- NHWC max pooling (nn.MaxPool2d(k, s, p); layers.py:191, resnet.py:91, layout_model.py:84) --------------
  * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.
@@ -248,6 +253,16 @@ typedef struct JpbAdamArgs {
 } JpbAdamArgs;
 int jpb_sumsq(const float* g, long long n, double* acc, void* stream);
 int jpb_adam_step(float* p, const float* g, float* m, float* v, long long n, const JpbAdamArgs* args, void* stream);
+
+/* ---- batched weight re-layout for the data-gradient GEMMs (autograd's convolution_backward re-lays out each weight
+ * separately): dst [Cin][taps][N] = src [N][taps][Cin] with the tap order reversed, for `nent` layers in one launch.
+ * entries_dev: device array; block_start = exclusive prefix sum of taps*ceil(N/32)*ceil(Cin/32); nblocks = the total. */
+typedef struct JpbWeightT {
+  const float* src;
+  float* dst;
+  int N, Cin, taps, block_start;
+} JpbWeightT;
+int jpb_weight_flipT(const JpbWeightT* entries_dev, int nent, int nblocks, void* stream);
 
 /* ---- accumulator finalisation: out[i] = (float)(acc[i] / (den ? den[i] : 1) * scale) --------------
  * (the `.mean()` / weight scalings of net.py:175-190, done on device so no loss term syncs the host) */

@@ -91,8 +91,12 @@ class ConvWgradArgs(C.Structure):
         ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
         ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("table", C.c_void_p), ("nchunks", C.c_int),
         ("dy", C.c_void_p), ("dw", C.c_void_p), ("w_row", C.c_longlong), ("w_cols", C.c_int), ("splits", C.c_int),
-        ("dbg", C.c_void_p),
+        ("dbg", C.c_void_p), ("accumulate", C.c_int),
     ]
+
+
+class WeightT(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("Cin", C.c_int), ("taps", C.c_int), ("block_start", C.c_int)]
 
 
 class AdamArgs(C.Structure):
@@ -123,6 +127,7 @@ class _Signatures:
     jpb_photometric_fwd = [C.POINTER(PhotoArgs), V]
     jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
     jpb_finalize = [P, P, F, P, I, V]
+    jpb_weight_flipT = [P, I, I, V]
     jpb_area_pyramid = [P, I, I, I, C.POINTER(Pyramid), V]
     jpb_smooth_fwd = [P, P, I, I, I, I, F, P, P, V]
     jpb_smooth_bwd = [P, P, I, I, I, I, F, P, P, P, V]
@@ -141,9 +146,9 @@ class _Signatures:
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]
-    jpb_bn_train_fwd = [P, P, P, P, P, P, F, F, I, P, P, P, C.c_longlong, I, V]
+    jpb_bn_train_fwd = [P, P, P, P, P, P, P, I, F, F, I, P, P, P, C.c_longlong, I, V]
     jpb_bn_eval_fwd = [P, P, P, P, P, I, P, C.c_longlong, I, V]
-    jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, P, C.c_longlong, I, V]
+    jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, I, P, C.c_longlong, I, V]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
 

@@ -28,6 +28,60 @@ DBG_STAMPS = None   # int64 [512, 6, 8] device tensor: per-CTA timeline of the n
 L1_GATHER = int(_os.environ.get("JPB_CONV_L1", "1"))
 
 
+class _WTCache:
+    """Flipped/transposed weights for the data-gradient GEMMs, rebuilt for all registered layers by ONE launch per step
+    (``refresh``; called by TrainEngine.step while the weights are final for the step).  Outside an engine step the data
+    gradient re-lays out its weight per call, as before."""
+
+    def __init__(self):
+        self.enabled = False     # inside TrainEngine.step
+        self.fresh = False       # buffers hold this step's weights
+        self.entries = {}        # (data_ptr, shape) -> (weight, wT)
+        self.table = None        # device copy of the descriptor array
+        self.nblocks = 0
+        self.dirty = False
+
+    def lookup(self, weight):
+        if not (self.enabled and self.fresh):
+            return None
+        e = self.entries.get((weight.data_ptr(), tuple(weight.shape)))
+        return e[1] if e is not None else None
+
+    def register(self, weight):
+        if not self.enabled:
+            return
+        key = (weight.data_ptr(), tuple(weight.shape))
+        if key not in self.entries:
+            N, Cin, kh, kw = weight.shape
+            wT = torch.empty((Cin, N, kh, kw), dtype=torch.float32, device=weight.device).contiguous(memory_format=CL)
+            self.entries[key] = (weight, wT)
+            self.dirty = True
+
+    def refresh(self):
+        if not self.entries:
+            self.fresh = True
+            return
+        if self.dirty or self.table is None:
+            arr = (_lib.WeightT * len(self.entries))()
+            start = 0
+            for i, (w, wT) in enumerate(self.entries.values()):
+                N, Cin, kh, kw = w.shape
+                arr[i].src, arr[i].dst, arr[i].N, arr[i].Cin, arr[i].taps, arr[i].block_start = ptr(w), ptr(wT), N, Cin, kh * kw, start
+                start += kh * kw * ((N + 31) // 32) * ((Cin + 31) // 32)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            dev = next(iter(self.entries.values()))[0].device
+            self.table = raw.to(dev)
+            self.nblocks = start
+            self.dirty = False
+        t = self.table
+        check(_launch("weight_flipT", t, lambda: _lib.lib().jpb_weight_flipT(ptr(t), len(self.entries), self.nblocks, stream_of(t))),
+              "jpb_weight_flipT")
+        self.fresh = True
+
+
+WT = _WTCache()
+
+
 def _pad4(c):
     return (c + 3) // 4 * 4
 
@@ -143,8 +197,9 @@ def _launch(name, t, call, tag=None):
     return L(name, t, call, tag)
 
 
-def act_bwd(gy, y, act, want_bias):
-    """dz = gy * act'(y) [+ bias gradient] in one pass over NHWC data."""
+def act_bwd(gy, y, act, want_bias, bias_target=None):
+    """dz = gy * act'(y) [+ bias gradient] in one pass over NHWC data.  ``bias_target``: accumulate the bias gradient
+    straight into this tensor (the parameter's slot of the flat gradient buffer) instead of a fresh zero-filled one."""
     gy = _cl(gy)
     B, N, Ho, Wo = gy.shape
     rows = B * Ho * Wo
@@ -152,7 +207,7 @@ def act_bwd(gy, y, act, want_bias):
     if not need_dz and not want_bias:
         return gy, None
     dz = torch.empty_like(gy, memory_format=CL) if need_dz else None
-    gb = torch.zeros(N, dtype=torch.float32, device=gy.device) if want_bias else None
+    gb = (bias_target if bias_target is not None else torch.zeros(N, dtype=torch.float32, device=gy.device)) if want_bias else None
     check(_launch("act_bwd", gy, lambda: _lib.lib().jpb_act_bwd(ptr(gy), ptr(y) if need_dz else None, ptr(dz), rows, N, ACT[act],
                                                                  ptr(gb), stream_of(gy))), "jpb_act_bwd")
     return (dz if need_dz else gy), gb
@@ -166,7 +221,11 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     W = xs[0].shape[3] * (2 if ups[0] else 1)
     dev = dz.device
     Nc = dz.shape[1]                                   # possibly channel-padded dz
-    wT = weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=CL)   # [Cin][kh][kw][Cout]
+    wT = WT.lookup(weight) if (Nc == N and N % 4 == 0 and weight.is_contiguous(memory_format=CL)) else None
+    if wT is None:
+        wT = weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=CL)   # [Cin][kh][kw][Cout]
+        if Nc == N and N % 4 == 0 and weight.is_contiguous(memory_format=CL):
+            WT.register(weight)
     wmat, wcols = gemm_weight(wT, [Nc], [N])
     table, kcol = ordered_table([Nc], kh, kw, dev)
     src_C = [x.shape[1] for x in xs]
@@ -225,7 +284,9 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     return grads
 
 
-def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
+def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None):
+    """``target``: the weight's channels-last gradient view; when given (and the K layout needs no padding) the kernel adds
+    into it and None is returned."""
     N, Cin, kh, kw = weight.shape
     B, Nc, Ho, Wo = dz.shape
     dev = dz.device
@@ -235,8 +296,10 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
     raw = all(c % 4 == 0 for c in src_C) and src_C == w_C
     Cpad = sum(_pad4(c) for c in src_C)
     wcols = kh * kw * (Cin if raw else Cpad)
-    dw = torch.zeros(Nc, wcols, dtype=torch.float32, device=dev)
+    direct = target is not None and raw and Nc == N and target.permute(0, 2, 3, 1).is_contiguous()
+    dw = target if direct else torch.zeros(Nc, wcols, dtype=torch.float32, device=dev)
     a = _lib.ConvWgradArgs()
+    a.accumulate = int(direct)
     _fill_sources(a, xs, ups)
     a.B = B
     a.Hin = xs[0].shape[2] * (2 if ups[0] else 1)
@@ -255,6 +318,8 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None):
         a.dbg = ptr(dbg)
     tag = (B * Ho * Wo, Nc, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), a.splits)
     check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_wgrad")
+    if direct:
+        return None
     dw = dw[:N]
     if raw:
         return dw.view(N, kh, kw, Cin).permute(0, 3, 1, 2)
@@ -366,7 +431,11 @@ class _ConvTC(torch.autograd.Function):
             return _ConvTC._backward_library(ctx, gy)
         ups, stride, pad, reflect, act = cfg["ups"], cfg["stride"], cfg["pad"], cfg["reflect"], cfg["act"]
         N = weight.shape[0]
-        dz, gb = act_bwd(gy, out, act, bias is not None)
+        from .functional import direct_grad_target
+        bt = direct_grad_target(bias) if bias is not None else None
+        dz, gb = act_bwd(gy, out, act, bias is not None, bt)
+        if bt is not None:
+            gb = None
         gr = dz if residual is not None else None
         if SMALLN and _is_smalln(weight, xs, stride, pad, residual):
             gw, gx = smalln_bwd(xs[0], ups[0], _cl(dz), weight, reflect, ctx.needs_input_grad[1], ctx.needs_input_grad[4])
@@ -377,7 +446,7 @@ class _ConvTC(torch.autograd.Function):
         gxs = [None] * len(xs)
         if any(ctx.needs_input_grad[4:]):
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
-        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect) if ctx.needs_input_grad[1] else None
+        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=direct_grad_target(weight)) if ctx.needs_input_grad[1] else None
         return (None, gw, gb, gr) + tuple(gxs)
 
     @staticmethod

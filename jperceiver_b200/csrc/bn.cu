@@ -11,16 +11,38 @@
 
 namespace {
 
-constexpr int BN_MAX_BLOCKS = 148 * 8;
+constexpr int BN_MAX_BLOCKS = 148 * 2;
+
+// Workspace layout (jpb_bn_workspace_doubles): one int ticket counter in the first 16 bytes (zero at allocation; every
+// launch leaves it at zero again; its position does not depend on C, so launches with different C can share the workspace)
+// | [2C] doubles final column sums | [BN_MAX_BLOCKS][2C] float per-block partials.
+__device__ __forceinline__ int* bn_ticket(double* ws, int) { return reinterpret_cast<int*>(ws); }
+__device__ __forceinline__ double* bn_sums(double* ws) { return ws + 2; }
+__device__ __forceinline__ float* bn_partials(double* ws, int C) { return reinterpret_cast<float*>(ws + 2 + 2 * C); }
+
+struct BnTail {   // what the last block to finish does after folding the partials (one launch instead of three)
+  long long rows;
+  float eps, momentum;
+  float* stat;                 // MODE 0: (mean, rstd) out
+  float* running_mean;         // MODE 0: updated in place (may be NULL)
+  float* running_var;
+  long long* num_batches_tracked;  // MODE 0: += nbt_inc (may be NULL)
+  int nbt_inc;
+  float* dgamma;               // MODE 1: (+)= s2
+  float* dbeta;                // MODE 1: (+)= s1
+  int accumulate;              // MODE 1: 1 = add into dgamma/dbeta (they are views of the flat gradient buffer), 0 = overwrite
+};
 
 // column sums of two per-element quantities over a [rows][C] matrix.  Each block reduces a slab of rows and writes its
-// partial sums to ws[(1 + blockIdx.x) * 2C ...] (no atomics: 300 blocks hammering 2C addresses serialise in L2);
-// bn_reduce_partials_kernel then folds them into ws[0 .. 2C).
+// partial sums (no atomics: hundreds of blocks hammering 2C addresses serialise in L2); the LAST block to finish (ticket
+// counter) folds the partials in double precision into ws[0 .. 2C) and finalises: batch statistics + running statistics
+// (MODE 0) or the affine-parameter gradients (MODE 1).
 // MODE 0: (x, x*x)    MODE 1: (g, g*xhat) with g = dy*[y>0 or no relu], xhat = (x-mean)*rstd
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const float* dy, const float* y, const float* stat, long long rows,
-                                                       int C, int relu, double* ws) {
+                                                       int C, int relu, double* ws, BnTail tail) {
   JPB_DYN_SMEM(float, part);   // [8][256]
+  __shared__ int s_last;
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * per;
   long long r1 = r0 + per;
@@ -29,7 +51,7 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
   const int Ct = C4 < 256 ? C4 : 256;               // float4 channel groups covered per pass
   const int lanes_r = 256 / Ct > 0 ? 256 / Ct : 1;  // row lanes
   const int U = Ct * lanes_r;
-  double* out = ws + (size_t)(1 + blockIdx.x) * 2 * C;
+  float* out = bn_partials(ws, C) + (size_t)blockIdx.x * 2 * C;
   for (int cbase = 0; cbase < C4; cbase += Ct) {
     for (int u = JPB_TID; u < U; u += JPB_NT) {
       const int c4 = cbase + u % Ct, lr = u / Ct;
@@ -38,7 +60,7 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
         float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
         if (MODE == 1)
           for (int k = 0; k < 4; ++k) { mean[k] = stat[c4 * 4 + k]; rstd[k] = stat[C + c4 * 4 + k]; }
-#pragma unroll 4
+#pragma unroll 8
         for (long long r = r0 + lr; r < r1; r += lanes_r) {
           const long long i = r * C + c4 * 4;
           if (MODE == 0) {
@@ -70,44 +92,80 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
       if (c < C) {
         float a1 = 0.f, a2 = 0.f;
         for (int lr = 0; lr < lanes_r; ++lr) { a1 += part[k * 256 + lr * Ct + cl]; a2 += part[(4 + k) * 256 + lr * Ct + cl]; }
-        out[c] = (double)a1;
-        out[C + c] = (double)a2;
+        out[c] = a1;
+        out[C + c] = a2;
       }
     }
     __syncthreads();
   }
-}
-
-// one warp per column j of the [nb][2C] partials: lanes stride the blocks, shuffle-reduce, lane 0 writes ws[j]
-__global__ void __launch_bounds__(256) bn_reduce_partials_kernel(double* ws, int nb, int C) {
-#ifdef JPB_HOST_EMU
-  const int lanes = 1, lane = 0, warps = 1, warp = 0;
-#else
-  const int lanes = 32, lane = threadIdx.x & 31, warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-#endif
-  for (int j = blockIdx.x * warps + warp; j < 2 * C; j += gridDim.x * warps) {
-    double s = 0.0;
-    for (int b = lane; b < nb; b += lanes) s += ws[(size_t)(1 + b) * 2 * C + j];
-#ifndef JPB_HOST_EMU
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-#endif
-    if (lane == 0) ws[j] = s;
-  }
-}
-
-// finalise batch statistics: stat = (mean, rstd); running stats updated (momentum m, unbiased variance)
-__global__ void bn_finalize_kernel(const double* acc, long long rows, int C, float eps, float momentum, float* stat, float* running_mean,
-                                   float* running_var) {
-  for (int c = blockIdx.x * JPB_NT + JPB_TID; c < C; c += gridDim.x * JPB_NT) {
-    const double mean = acc[c] / (double)rows;
-    double var = acc[C + c] / (double)rows - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stat[c] = (float)mean;
-    stat[C + c] = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) {
-      const double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
-      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
-      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+  // ---- last block: fold the partials, finalise
+  __threadfence();
+  __syncthreads();
+  if (JPB_TID == 0) s_last = (atomicAdd(bn_ticket(ws, C), 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const int ncol = 2 * C, nb = (int)gridDim.x;
+    double* sums = bn_sums(ws);
+    const float* pr = bn_partials(ws, C);
+    double* sred = reinterpret_cast<double*>(part);    // [G][ncol] doubles, G*ncol <= NT
+    const int G = (int)JPB_NT / ncol;                  // column groups that split the blocks (0 when ncol > NT)
+    if (G >= 2) {
+      for (int t = JPB_TID; t < G * ncol; t += JPB_NT) {
+        const int j = t % ncol, g = t / ncol;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // independent chains: the loads pipeline instead of serialising
+        int bb = g;
+        for (; bb + 3 * G < nb; bb += 4 * G) {
+          a0 += (double)pr[(size_t)bb * ncol + j];
+          a1 += (double)pr[(size_t)(bb + G) * ncol + j];
+          a2 += (double)pr[(size_t)(bb + 2 * G) * ncol + j];
+          a3 += (double)pr[(size_t)(bb + 3 * G) * ncol + j];
+        }
+        for (; bb < nb; bb += G) a0 += (double)pr[(size_t)bb * ncol + j];
+        sred[g * ncol + j] = (a0 + a1) + (a2 + a3);
+      }
+      __syncthreads();
+      for (int j = JPB_TID; j < ncol; j += JPB_NT) {
+        double acc = 0.0;
+        for (int g = 0; g < G; ++g) acc += sred[g * ncol + j];
+        sums[j] = acc;
+      }
+    } else {
+      for (int j = JPB_TID; j < ncol; j += JPB_NT) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int bb = 0;
+        for (; bb + 3 < nb; bb += 4) {
+          a0 += (double)pr[(size_t)bb * ncol + j];
+          a1 += (double)pr[(size_t)(bb + 1) * ncol + j];
+          a2 += (double)pr[(size_t)(bb + 2) * ncol + j];
+          a3 += (double)pr[(size_t)(bb + 3) * ncol + j];
+        }
+        for (; bb < nb; ++bb) a0 += (double)pr[(size_t)bb * ncol + j];
+        sums[j] = (a0 + a1) + (a2 + a3);
+      }
+    }
+    __syncthreads();
+    for (int c = JPB_TID; c < C; c += JPB_NT) {
+      if (MODE == 0) {
+        const double mean = sums[c] / (double)tail.rows;
+        double var = sums[C + c] / (double)tail.rows - mean * mean;
+        if (var < 0.0) var = 0.0;
+        tail.stat[c] = (float)mean;
+        tail.stat[C + c] = (float)(1.0 / sqrt(var + (double)tail.eps));
+        if (tail.running_mean) {
+          const double unb = tail.rows > 1 ? var * (double)tail.rows / (double)(tail.rows - 1) : var;
+          tail.running_mean[c] = (float)((1.0 - tail.momentum) * tail.running_mean[c] + tail.momentum * mean);
+          tail.running_var[c] = (float)((1.0 - tail.momentum) * tail.running_var[c] + tail.momentum * unb);
+        }
+      } else {
+        if (tail.accumulate) { tail.dbeta[c] += (float)sums[c]; tail.dgamma[c] += (float)sums[C + c]; }
+        else { tail.dbeta[c] = (float)sums[c]; tail.dgamma[c] = (float)sums[C + c]; }
+      }
+    }
+    if (JPB_TID == 0) {
+      if (MODE == 0 && tail.num_batches_tracked) tail.num_batches_tracked[0] += tail.nbt_inc;
+      *bn_ticket(ws, C) = 0;
     }
   }
 }
@@ -155,14 +213,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* x, const
   }
 }
 
-// dgamma = s2, dbeta = s1
-__global__ void bn_param_grad_kernel(const double* acc, int C, float* dgamma, float* dbeta) {
-  for (int c = blockIdx.x * JPB_NT + JPB_TID; c < C; c += gridDim.x * JPB_NT) {
-    dbeta[c] = (float)acc[c];
-    dgamma[c] = (float)acc[C + c];
-  }
-}
-
 inline unsigned bn_grid(long long work, int per_block, int cap) {
   long long g = (work + per_block - 1) / per_block;
   if (g > cap) g = cap;
@@ -171,16 +221,18 @@ inline unsigned bn_grid(long long work, int per_block, int cap) {
 
 }  // namespace
 
-extern "C" long long jpb_bn_workspace_doubles(int C) { return (long long)2 * C * (1 + BN_MAX_BLOCKS); }
+extern "C" long long jpb_bn_workspace_doubles(int C) { return 2 + (long long)2 * C + ((long long)BN_MAX_BLOCKS * 2 * C * 4 + 7) / 8; }
 
 extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                                float momentum, float eps, int relu, float* y, float* stat, double* acc, long long rows, int C, void* stream) {
-  if (!x || !gamma || !beta || !y || !stat || !acc || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
+                                long long* num_batches_tracked, int nbt_inc, float momentum, float eps, int relu, float* y, float* stat,
+                                double* ws, long long rows, int C, void* stream) {
+  if (!x || !gamma || !beta || !y || !stat || !ws || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
-  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, acc);
-  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 8, 148)), dim3(256), 0, st, acc, (int)nb, C);
-  JPB_LAUNCH(bn_finalize_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, rows, C, eps, momentum, stat, running_mean, running_var);
+  BnTail t = {};
+  t.rows = rows; t.eps = eps; t.momentum = momentum; t.stat = stat; t.running_mean = running_mean; t.running_var = running_var;
+  t.num_batches_tracked = num_batches_tracked; t.nbt_inc = nbt_inc;
+  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, ws, t);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, res, stat, gamma, beta, y, n4, C, relu);
   return jpb_status();
@@ -195,14 +247,14 @@ extern "C" int jpb_bn_eval_fwd(const float* x, const float* res, const float* ga
 }
 
 extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
-                                float* dres, float* dgamma, float* dbeta, double* acc, long long rows, int C, void* stream) {
-  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !acc || (relu && !y) || (C & 3)) return JPB_ERR_ARG;
+                                float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream) {
+  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !ws || (relu && !y) || (C & 3)) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
-  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, acc);
-  JPB_LAUNCH(bn_reduce_partials_kernel, dim3(bn_grid(2 * C, 8, 148)), dim3(256), 0, st, acc, (int)nb, C);
-  JPB_LAUNCH(bn_param_grad_kernel, dim3(bn_grid(C, 256, 8)), dim3(256), 0, st, acc, C, dgamma, dbeta);
+  BnTail t = {};
+  t.rows = rows; t.dgamma = dgamma; t.dbeta = dbeta; t.accumulate = accumulate;
+  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, ws, t);
   const long long n4 = rows * C / 4;
-  JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, acc, dx, dres, rows, n4, C, relu);
+  JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, ws + 2, dx, dres, rows, n4, C, relu);
   return jpb_status();
 }

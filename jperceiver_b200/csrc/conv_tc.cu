@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
     tc_fence_after();
     const int k = mt * 128 + warp * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool use_atomic = gridDim.z > 1;
+    const bool use_atomic = gridDim.z > 1 || a.accumulate;
     for (int j = 0; j < NT; j += 16) {
       float v[16];
       tmem_ld16(taddr + (uint32_t)j, v);

@@ -33,10 +33,11 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 v 
 #define __launch_bounds__(...)
 #define __syncthreads() ((void)0)
 #define __syncwarp() ((void)0)
+#define __threadfence() ((void)0)
 #define __ldg(p) (*(p))
 static std::vector<unsigned char> jpb_emu_dynsmem;
 #define JPB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(jpb_emu_dynsmem.data())
-template <typename T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = o + (T)v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }

@@ -375,43 +375,74 @@ def _clast(t):
     return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
 
 
+_BN_WS: dict = {}
+# Set by TrainEngine.step: parameter gradients are ADDED straight into ``param.grad`` (views of the flat gradient buffer)
+# by the backward kernels and autograd receives None for them — no per-parameter AccumulateGrad add / zero-fill launches.
+DIRECT_GRAD = False
+
+
+def direct_grad_target(p):
+    """``p.grad`` when the backward kernels may accumulate into it directly (engine step, dense fp32 gradient present)."""
+    if not DIRECT_GRAD or p is None:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or g.shape != p.shape or g.stride() != p.stride():
+        return None
+    return g
+
+
+def _bn_workspace(C, device):
+    """One zero-initialised workspace per device, shared by every BatchNorm launch (they are stream-ordered)."""
+    need = _lib.lib().jpb_bn_workspace_doubles(max(C, 512))
+    ws = _BN_WS.get(device)
+    if ws is None or ws.numel() < need:
+        ws = _BN_WS[device] = torch.zeros(need, dtype=torch.float64, device=device)
+    return ws
+
+
 class _BNTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, nbt, nbt_inc):
         x = _clast(x)
         res = _clast(res) if res is not None else None
         B, Cc, H, W = x.shape
         rows = B * H * W
         y = torch.empty_like(x, memory_format=torch.channels_last)
         stat = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
-        acc = torch.empty(_lib.lib().jpb_bn_workspace_doubles(Cc), dtype=torch.float64, device=x.device)
+        ws = _bn_workspace(Cc, x.device)
         check(_launch("bn_fwd", x, lambda: _lib.lib().jpb_bn_train_fwd(
-            ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(running_mean), ptr(running_var), float(momentum), float(eps),
-            int(relu), ptr(y), ptr(stat), ptr(acc), rows, Cc, stream_of(x))), "jpb_bn_train_fwd")
-        ctx.save_for_backward(x, y if relu else None, stat, gamma)
+            ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(running_mean), ptr(running_var),
+            ptr(nbt) if nbt is not None else None, int(nbt_inc), float(momentum), float(eps),
+            int(relu), ptr(y), ptr(stat), ptr(ws), rows, Cc, stream_of(x))), "jpb_bn_train_fwd")
+        ctx.save_for_backward(x, y if relu else None, stat, gamma, beta)
         ctx.cfg = (rows, Cc, int(relu), res is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, y, stat, gamma = ctx.saved_tensors
+        x, y, stat, gamma, beta = ctx.saved_tensors
         rows, Cc, relu, has_res = ctx.cfg
         gy = _clast(gy)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and relu) else None
-        dgamma = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        acc = torch.empty(_lib.lib().jpb_bn_workspace_doubles(Cc), dtype=torch.float64, device=x.device)
+        tg, tb = direct_grad_target(gamma), direct_grad_target(beta)
+        direct = tg is not None and tb is not None
+        dgamma = tg if direct else torch.empty(Cc, dtype=torch.float32, device=x.device)
+        dbeta = tb if direct else torch.empty(Cc, dtype=torch.float32, device=x.device)
+        ws = _bn_workspace(Cc, x.device)
         check(_launch("bn_bwd", x, lambda: _lib.lib().jpb_bn_train_bwd(
-            ptr(x), ptr(gy), ptr(y), ptr(stat), ptr(gamma.detach()), relu, ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta), ptr(acc), rows, Cc,
-            stream_of(x))), "jpb_bn_train_bwd")
+            ptr(x), ptr(gy), ptr(y), ptr(stat), ptr(gamma.detach()), relu, ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta), int(direct),
+            ptr(ws), rows, Cc, stream_of(x))), "jpb_bn_train_bwd")
         if has_res and not relu:
             dres = gy
-        return dx, dres, dgamma, dbeta, None, None, None, None, None
+        if direct:
+            return dx, dres, None, None, None, None, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def batchnorm_train(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu):
-    return _BNTrain.apply(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu)
+def batchnorm_train(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, num_batches_tracked=None, nbt_inc=0):
+    """``num_batches_tracked`` (int64 [1] device tensor) is advanced by ``nbt_inc`` inside the statistics kernel."""
+    return _BNTrain.apply(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, num_batches_tracked, nbt_inc)
 
 
 def batchnorm_eval(x, res, gamma, beta, running_mean, running_var, eps, relu):

@@ -66,9 +66,12 @@ def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1
         from . import functional as JF
         if training:
             k = getattr(bn, "stat_updates", 1)
-            bn.num_batches_tracked += k
+            nbt = bn.num_batches_tracked
+            if not (torch.is_tensor(nbt) and nbt.is_cuda and nbt.dtype == torch.int64):
+                bn.num_batches_tracked += k
+                nbt = None
             return JF.batchnorm_train(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                      1.0 - (1.0 - momentum) ** k, eps, relu)
+                                      1.0 - (1.0 - momentum) ** k, eps, relu, nbt, k)
         return JF.batchnorm_eval(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, eps, relu)
     if training:
         # ``stat_updates`` = 2 on the road-head BNs reproduces the reference's duplicated forward pass

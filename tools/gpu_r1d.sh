@@ -9,3 +9,4 @@ d=json.loads(open('gpurun_out/bench_n1.json').read())
 print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['roofline']['frac'])
 for k,v in d['kernels'].items(): print(k, v)
 "
+timeout 300 python tools/profile_step.py > gpurun_out/profile_step.txt 2>&1; head -45 gpurun_out/profile_step.txt
