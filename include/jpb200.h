@@ -178,6 +178,7 @@ typedef struct JpbConvArgs {
                                            the K blocks so that taps sharing input pixels are consecutive */
   int l1_gather;                        /* 1: gather through L1 (cp.async.ca) — pays off with the K-block order above */
   long long* dbg;                       /* debug only: [512 CTAs][6 warps][8] globaltimer stamps (tools/conv_timeline.py), or NULL */
+  int dbg_skip;                         /* timing experiments only (results are wrong): bit 0 = no A gather, bit 1 = no weight TMA */
 } JpbConvArgs;
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
 

@@ -24,6 +24,7 @@ import os as _os
 # K-block order of the forward / data-gradient GEMM: "cb" = channel-block major (the taps of one 32-channel block are
 # consecutive, so their gathers re-read the same pixels and hit L1), "tap" = the natural weight order
 KORDER = _os.environ.get("JPB_CONV_KORDER", "cb")
+DBG_SKIP = int(_os.environ.get('JPB_CONV_SKIP', '0'))   # timing experiments (wrong results): 1 no A gather, 2 no weight TMA
 DBG_STAMPS = None   # int64 [512, 6, 8] device tensor: per-CTA timeline of the next forward launches (tools/conv_timeline.py)
 L1_GATHER = int(_os.environ.get("JPB_CONV_L1", "1"))
 
@@ -416,6 +417,7 @@ class _ConvTC(torch.autograd.Function):
         a.out = ptr(out)
         if DBG_STAMPS is not None:
             a.dbg = ptr(DBG_STAMPS)
+        a.dbg_skip = DBG_SKIP
         tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
         check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd")
         ctx.cfg = cfg

@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         const bool live = e.x >= 0;
         const float* base = reinterpret_cast<const float*>((uintptr_t)lds64(srcs_u32 + (uint32_t)(live ? (e.x & 0xff) : 0) * (uint32_t)sizeof(SrcDev))) + e.z;
         const uint32_t offs = soff_u32 + (uint32_t)(((live ? (e.x >> 8) : 0) * BM + rbase) * 4);
-        if (!live || e.w == 16) {
+        if (a.dbg_skip & 1) {
+          // timing experiment: no A traffic
+        } else if (!live || e.w == 16) {
           if (use_ca) {
             for (int i = 0; i < 8; ++i) {
               const int off = lds32(offs + 64u * (uint32_t)i);
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (a.dbg_skip & 2) { mbar_arrive(&full_bar[s]); continue; }   // timing experiment: no B traffic
         mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
         const int kr = kb0 + JPB_KROT(kb);
         tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kr] : kr * BK, n0);
