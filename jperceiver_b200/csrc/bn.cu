@@ -13,12 +13,13 @@ namespace {
 
 constexpr int BN_MAX_BLOCKS = 148 * 2;
 
-// Workspace layout (jpb_bn_workspace_doubles): one int ticket counter in the first 16 bytes (zero at allocation; every
-// launch leaves it at zero again; its position does not depend on C, so launches with different C can share the workspace)
-// | [2C] doubles final column sums | [BN_MAX_BLOCKS][2C] float per-block partials.
-__device__ __forceinline__ int* bn_ticket(double* ws, int) { return reinterpret_cast<int*>(ws); }
+constexpr int BN_MAX_C = 2048;
+// Workspace layout (jpb_bn_workspace_doubles): one int ticket counter in the first 16 bytes | final[2 * BN_MAX_C] column sums
+// of the last launch (read by the backward apply pass) | running[2 * BN_MAX_C] accumulators.  Ticket and accumulators are zero
+// at allocation and every launch leaves them at zero again, so launches of any C can share one workspace on a stream.
+__device__ __forceinline__ int* bn_ticket(double* ws) { return reinterpret_cast<int*>(ws); }
 __device__ __forceinline__ double* bn_sums(double* ws) { return ws + 2; }
-__device__ __forceinline__ float* bn_partials(double* ws, int C) { return reinterpret_cast<float*>(ws + 2 + 2 * C); }
+__device__ __forceinline__ double* bn_running(double* ws) { return ws + 2 + 2 * BN_MAX_C; }
 
 struct BnTail {   // what the last block to finish does after folding the partials (one launch instead of three)
   long long rows;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
   const int Ct = C4 < 256 ? C4 : 256;               // float4 channel groups covered per pass
   const int lanes_r = 256 / Ct > 0 ? 256 / Ct : 1;  // row lanes
   const int U = Ct * lanes_r;
-  float* out = bn_partials(ws, C) + (size_t)blockIdx.x * 2 * C;
+  double* run = bn_running(ws);
   for (int cbase = 0; cbase < C4; cbase += Ct) {
     for (int u = JPB_TID; u < U; u += JPB_NT) {
       const int c4 = cbase + u % Ct, lr = u / Ct;
@@ -92,58 +93,24 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
       if (c < C) {
         float a1 = 0.f, a2 = 0.f;
         for (int lr = 0; lr < lanes_r; ++lr) { a1 += part[k * 256 + lr * Ct + cl]; a2 += part[(4 + k) * 256 + lr * Ct + cl]; }
-        out[c] = a1;
-        out[C + c] = a2;
+        // <= 296 blocks per address: the double-precision reductions in L2 cost less than a pass over per-block partials
+        if (r1 > r0) { atomicAdd(&run[c], (double)a1); atomicAdd(&run[C + c], (double)a2); }
       }
     }
     __syncthreads();
   }
-  // ---- last block: fold the partials, finalise
+  // ---- last block to finish: publish the sums, re-zero the accumulators, finalise
   __threadfence();
   __syncthreads();
-  if (JPB_TID == 0) s_last = (atomicAdd(bn_ticket(ws, C), 1) == (int)gridDim.x - 1) ? 1 : 0;
+  if (JPB_TID == 0) s_last = (atomicAdd(bn_ticket(ws), 1) == (int)gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   {
-    const int ncol = 2 * C, nb = (int)gridDim.x;
     double* sums = bn_sums(ws);
-    const float* pr = bn_partials(ws, C);
-    double* sred = reinterpret_cast<double*>(part);    // [G][ncol] doubles, G*ncol <= NT
-    const int G = (int)JPB_NT / ncol;                  // column groups that split the blocks (0 when ncol > NT)
-    if (G >= 2) {
-      for (int t = JPB_TID; t < G * ncol; t += JPB_NT) {
-        const int j = t % ncol, g = t / ncol;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // independent chains: the loads pipeline instead of serialising
-        int bb = g;
-        for (; bb + 3 * G < nb; bb += 4 * G) {
-          a0 += (double)pr[(size_t)bb * ncol + j];
-          a1 += (double)pr[(size_t)(bb + G) * ncol + j];
-          a2 += (double)pr[(size_t)(bb + 2 * G) * ncol + j];
-          a3 += (double)pr[(size_t)(bb + 3 * G) * ncol + j];
-        }
-        for (; bb < nb; bb += G) a0 += (double)pr[(size_t)bb * ncol + j];
-        sred[g * ncol + j] = (a0 + a1) + (a2 + a3);
-      }
-      __syncthreads();
-      for (int j = JPB_TID; j < ncol; j += JPB_NT) {
-        double acc = 0.0;
-        for (int g = 0; g < G; ++g) acc += sred[g * ncol + j];
-        sums[j] = acc;
-      }
-    } else {
-      for (int j = JPB_TID; j < ncol; j += JPB_NT) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int bb = 0;
-        for (; bb + 3 < nb; bb += 4) {
-          a0 += (double)pr[(size_t)bb * ncol + j];
-          a1 += (double)pr[(size_t)(bb + 1) * ncol + j];
-          a2 += (double)pr[(size_t)(bb + 2) * ncol + j];
-          a3 += (double)pr[(size_t)(bb + 3) * ncol + j];
-        }
-        for (; bb < nb; ++bb) a0 += (double)pr[(size_t)bb * ncol + j];
-        sums[j] = (a0 + a1) + (a2 + a3);
-      }
+    for (int j = JPB_TID; j < 2 * C; j += JPB_NT) {
+      sums[j] = atomicAdd(&run[j], 0.0);   // read through L2 (the other blocks' reductions never touched this SM's L1)
+      run[j] = 0.0;
     }
     __syncthreads();
     for (int c = JPB_TID; c < C; c += JPB_NT) {
@@ -165,7 +132,7 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
     }
     if (JPB_TID == 0) {
       if (MODE == 0 && tail.num_batches_tracked) tail.num_batches_tracked[0] += tail.nbt_inc;
-      *bn_ticket(ws, C) = 0;
+      *bn_ticket(ws) = 0;
     }
   }
 }
@@ -213,6 +180,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* x, const
   }
 }
 
+// blocks of the column-sum kernels: every thread should own >= 4 rows, at most BN_MAX_BLOCKS blocks
+inline unsigned bn_colsum_grid(long long rows, int C) {
+  const int C4 = C >> 2, Ct = C4 < 256 ? C4 : 256;
+  const int lanes_r = 256 / Ct > 0 ? 256 / Ct : 1;
+  long long g = (rows + 4LL * lanes_r - 1) / (4LL * lanes_r);
+  if (g > BN_MAX_BLOCKS) g = BN_MAX_BLOCKS;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
 inline unsigned bn_grid(long long work, int per_block, int cap) {
   long long g = (work + per_block - 1) / per_block;
   if (g > cap) g = cap;
@@ -221,14 +197,14 @@ inline unsigned bn_grid(long long work, int per_block, int cap) {
 
 }  // namespace
 
-extern "C" long long jpb_bn_workspace_doubles(int C) { return 2 + (long long)2 * C + ((long long)BN_MAX_BLOCKS * 2 * C * 4 + 7) / 8; }
+extern "C" long long jpb_bn_workspace_doubles(int C) { (void)C; return 2 + (long long)4 * BN_MAX_C; }
 
 extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                 long long* num_batches_tracked, int nbt_inc, float momentum, float eps, int relu, float* y, float* stat,
                                 double* ws, long long rows, int C, void* stream) {
-  if (!x || !gamma || !beta || !y || !stat || !ws || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
+  if (!x || !gamma || !beta || !y || !stat || !ws || rows < 1 || C < 4 || (C & 3) || C > BN_MAX_C) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
+  const unsigned nb = bn_colsum_grid(rows, C);
   BnTail t = {};
   t.rows = rows; t.eps = eps; t.momentum = momentum; t.stat = stat; t.running_mean = running_mean; t.running_var = running_var;
   t.num_batches_tracked = num_batches_tracked; t.nbt_inc = nbt_inc;
@@ -248,9 +224,9 @@ extern "C" int jpb_bn_eval_fwd(const float* x, const float* res, const float* ga
 
 extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
                                 float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream) {
-  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !ws || (relu && !y) || (C & 3)) return JPB_ERR_ARG;
+  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !ws || (relu && !y) || (C & 3) || C > BN_MAX_C) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned nb = bn_grid(rows, 128, BN_MAX_BLOCKS);
+  const unsigned nb = bn_colsum_grid(rows, C);
   BnTail t = {};
   t.rows = rows; t.dgamma = dgamma; t.dbeta = dbeta; t.accumulate = accumulate;
   JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, ws, t);

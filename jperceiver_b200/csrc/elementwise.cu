@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* dy, const flo
   if (C >= 32) {
     for (int c = JPB_TID; c < C; c += JPB_NT) {
       float s = 0.f;
+#pragma unroll 4
       for (long long r = r0; r < r1; ++r) {
         const long long i = r * C + c;
         const float g = act_grad(dy[i], y ? y[i] : 0.f, act);
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* dy, const flo
 
 extern "C" int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int C, int act, float* dbias, void* stream) {
   if (!dy || rows < 1 || C < 1 || (act != 0 && !y) || (!dz && !dbias)) return JPB_ERR_ARG;
-  long long blocks = rows / 64 + 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  long long blocks = rows / 16 + 1;   // small-extent layers (rows = 480..5120) need many short slabs, not 8 blocks of 64 serial rows
+  if (blocks > 148 * 8) blocks = 148 * 8;
   JPB_LAUNCH(act_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, dy, y, dz, rows, C, act, dbias);
   return jpb_status();
 }
