@@ -231,8 +231,7 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     pk, pk_src = peaks()
     ms_step = ms / args.steps
@@ -280,8 +279,17 @@ def run_ours(args):
         r = cpu_reference_run(1, 1, batch=1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit.  Tearing the NCCL communicator down while the captured step graph (which holds NCCL kernels) is still
+    alive blocked the processes after the result line had been printed; every rank has finished its collectives here, so
+    flush and leave without the teardown."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
