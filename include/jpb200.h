@@ -255,6 +255,22 @@ typedef struct JpbAdamArgs {
 int jpb_sumsq(const float* g, long long n, double* acc, void* stream);
 int jpb_adam_step(float* p, const float* g, float* m, float* v, long long n, const JpbAdamArgs* args, void* stream);
 
+/* ---- input prologue of the three ResNet trunks: out[b][y][x][0..Cpad) = ((resize(im) - 0.45) / 0.225, zero padding), NHWC.
+ * im0 / im1: [B,3,Hs,Ws] NCHW frames (im1 NULL for a single frame, else the pair is concatenated: pose_encoder.py:84-86,
+ * net.py:633-638); bilinear resize (align_corners=False) when (Ho,Wo) != (Hs,Ws); Cpad = 4 (one frame) or 8 (a pair). */
+int jpb_image_prep(const float* im0, const float* im1, float* out, int B, int Hs, int Ws, int Ho, int Wo, int Cpad, void* stream);
+
+/* ---- nn.Dropout(p) (depth_decoder.py:47-48): y = x * keep / (1-p); keep from `mask` ([n] of 0/1) when given, else from the
+ * counter-based draw (seed, stream_id + 4096*step[0], element index) — the same call with dy as x is the backward.     */
+int jpb_dropout(const float* x, const float* mask, float* y, long long n, float p, uint64_t seed, uint64_t stream_id,
+                const long long* step, void* stream);
+
+/* ---- pose head: x [B][hw][C>=6] (PoseDecoder output, NHWC) -> spatial mean * 0.01 -> axis-angle / translation ->
+ * cam_T_cam [B][4][4] (pose_decoder.py:22-26, net.py:704-756; invert != 0 for the frame before the target).  mean6 [B][6]
+ * is written by the forward and read by the backward, which fills gx [B][hw][C] from gT [B][4][4].                    */
+int jpb_pose_head_fwd(const float* x, float* T, float* mean6, int B, int hw, int C, int invert, void* stream);
+int jpb_pose_head_bwd(const float* gT, const float* mean6, float* gx, int B, int hw, int C, int invert, void* stream);
+
 /* ---- batched weight re-layout for the data-gradient GEMMs (autograd's convolution_backward re-lays out each weight
  * separately): dst [Cin][taps][N] = src [N][taps][Cin] with the tap order reversed, for `nent` layers in one launch.
  * entries_dev: device array; block_start = exclusive prefix sum of taps*ceil(N/32)*ceil(Cin/32); nblocks = the total. */

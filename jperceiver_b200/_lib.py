@@ -128,6 +128,10 @@ class _Signatures:
     jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
     jpb_finalize = [P, P, F, P, I, V]
     jpb_weight_flipT = [P, I, I, V]
+    jpb_image_prep = [P, P, P, I, I, I, I, I, I, V]
+    jpb_dropout = [P, P, P, C.c_longlong, F, C.c_uint64, C.c_uint64, P, V]
+    jpb_pose_head_fwd = [P, P, P, I, I, I, I, V]
+    jpb_pose_head_bwd = [P, P, P, I, I, I, I, V]
     jpb_area_pyramid = [P, I, I, I, C.POINTER(Pyramid), V]
     jpb_smooth_fwd = [P, P, I, I, I, I, F, P, P, V]
     jpb_smooth_bwd = [P, P, I, I, I, I, F, P, P, P, V]

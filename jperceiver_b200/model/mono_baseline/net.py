@@ -124,6 +124,7 @@ class Baseline(nn.Module):
             raise JF._lib.JpbError("Baseline.forward needs CUDA tensors: jperceiver_b200 has no CPU path")
         JF._lib.lib()  # fail loudly if the CUDA library is missing
         depth_feature = self.DepthEncoder(inputs[("color_aug", 0, 0)])
+        self.DepthDecoder.step_counter = getattr(self, "step_counter", None)
         outputs = dict(self.DepthDecoder(depth_feature))
         if o["type"] != "static_eigen":
             outputs.update(self.predict_layouts(inputs, depth_feature))

@@ -122,8 +122,9 @@ class DepthDecoder(nn.Module):
     def forward(self, input_features, frame_id=0):
         l0, l1, l2, l3, l4 = input_features
         m4, m3 = self.drop_masks if self.drop_masks is not None else (None, None)
-        l4 = ops.dropout(l4, self.drop_p, self.training, m4)
-        l3 = ops.dropout(l3, self.drop_p, self.training, m3)
+        step = getattr(self, "step_counter", None)   # device step counter (set by Baseline.forward): fresh masks under graph replay
+        l4 = ops.dropout(l4, self.drop_p, self.training, m4, step=step)
+        l3 = ops.dropout(l3, self.drop_p, self.training, m3, step=step)
         self.outputs = {}
         skips = {3: l3, 2: l2, 1: l1}
         x = ops.conv2d(l4, self.reduce4.conv.weight)

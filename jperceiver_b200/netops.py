@@ -20,7 +20,10 @@ BACKEND = {
     "conv2d": "jpb",        # tcgen05 implicit GEMM: forward, dgrad, wgrad (csrc/conv_tc.cu) + epilogue backward (elementwise.cu)
     "maxpool": "jpb",       # csrc/pool.cu
     "batchnorm": "jpb",     # csrc/bn.cu: batch statistics + normalise + residual + ReLU fused, fwd and bwd
-    "dropout": "torch", "image_prep": "torch", "cvp_mlp": "torch", "cct_attention": "torch", "pose_head": "torch",
+    "dropout": "jpb",       # csrc/heads.cu: counter-based keep mask, one launch per direction
+    "image_prep": "jpb",    # csrc/heads.cu: normalise + bilinear resize + pair concatenation + NHWC/channel padding in one launch
+    "pose_head": "jpb",     # csrc/heads.cu: spatial mean + Rodrigues + 4x4 assembly, forward and hand-derived backward
+    "cvp_mlp": "torch", "cct_attention": "torch",
 }
 
 
@@ -93,21 +96,65 @@ def maxpool(x, k, stride, pad):
     return F.max_pool2d(x, k, stride, pad)
 
 
-def dropout(x, p, training, mask=None):
-    """nn.Dropout; ``mask`` (0/1 keep tensor) overrides the random draw (parity tests)."""
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, mask, seed, stream_id, step):
+        from ._lib import check, ptr, stream_of
+        xc = x.contiguous(memory_format=CL) if x.dim() == 4 else x.contiguous()
+        y = torch.empty_like(xc)
+        if mask is not None:
+            mask = mask.to(torch.float32).expand_as(x)
+            mask = mask.contiguous(memory_format=CL) if x.dim() == 4 else mask.contiguous()
+        ctx.args = (float(p), mask, int(seed), int(stream_id), step)
+        check(_lib.lib().jpb_dropout(ptr(xc), ptr(mask) if mask is not None else None, ptr(y), xc.numel(), float(p), int(seed),
+                                     int(stream_id), ptr(step) if step is not None else None, stream_of(xc)), "jpb_dropout")
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from ._lib import check, ptr, stream_of
+        p, mask, seed, stream_id, step = ctx.args
+        g = gy.contiguous(memory_format=CL) if gy.dim() == 4 else gy.contiguous()
+        gx = torch.empty_like(g)
+        check(_lib.lib().jpb_dropout(ptr(g), ptr(mask) if mask is not None else None, ptr(gx), g.numel(), p, seed, stream_id,
+                                     ptr(step) if step is not None else None, stream_of(g)), "jpb_dropout(bwd)")
+        return gx, None, None, None, None, None
+
+
+_DROPOUT_CALLS = [0]
+
+
+def dropout(x, p, training, mask=None, step=None, seed=0):
+    """nn.Dropout; ``mask`` (0/1 keep tensor) overrides the random draw (parity tests).  The keep mask is a counter-based
+    draw keyed on (seed, call index, device step counter, element): no mask tensor is stored, the backward regenerates it,
+    and a replayed CUDA graph still sees a fresh mask every step."""
     if not training or p == 0.0:
         return x
-    if mask is None:
-        mask = (torch.rand_like(x) >= p).to(x.dtype)
-    return x * mask * (1.0 / (1.0 - p))
+    _need_cuda(x)
+    if BACKEND["dropout"] != "jpb":
+        if mask is None:
+            mask = (torch.rand_like(x) >= p).to(x.dtype)
+        return x * mask * (1.0 / (1.0 - p))
+    _DROPOUT_CALLS[0] = (_DROPOUT_CALLS[0] + 1) % 4096
+    return _Dropout.apply(x, p, mask, seed, 1000 + _DROPOUT_CALLS[0], step)
 
 
 def image_prep(images, out_hw=None):
     """``(x - 0.45) / 0.225`` of one or two NCHW frames (concatenated along channels), optionally after a
-    bilinear resize (align_corners=False), emitted channels-last."""
+    bilinear resize (align_corners=False), emitted channels-last with the channels zero-padded to 4 / 8."""
     if not isinstance(images, (list, tuple)):
         images = [images]
     _need_cuda(images[0])
+    if BACKEND["image_prep"] == "jpb" and len(images) <= 2 and all(im.shape[1] == 3 and im.dtype == torch.float32 for im in images):
+        from ._lib import check, ptr, stream_of
+        ims = [im.contiguous() for im in images]
+        B, _, Hs, Ws = ims[0].shape
+        Ho, Wo = (Hs, Ws) if out_hw is None else tuple(out_hw)
+        Cpad = 4 * len(ims)
+        out = torch.empty((B, Cpad, Ho, Wo), dtype=torch.float32, device=ims[0].device, memory_format=CL)
+        check(_lib.lib().jpb_image_prep(ptr(ims[0]), ptr(ims[1]) if len(ims) == 2 else None, ptr(out), B, Hs, Ws, Ho, Wo, Cpad,
+                                        stream_of(out)), "jpb_image_prep")
+        return out
     outs = []
     for im in images:
         if out_hw is not None and tuple(im.shape[2:]) != tuple(out_hw):
@@ -158,10 +205,40 @@ def cct_attention(front, cross, front_hat, dfeat, p):
     return (out + attn @ vd).contiguous(memory_format=CL), S, attn
 
 
+class _PoseHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, invert):
+        from ._lib import check, ptr, stream_of
+        xc = x.contiguous(memory_format=CL)
+        B, Cc, h, w = xc.shape
+        T = torch.empty(B, 4, 4, dtype=torch.float32, device=x.device)
+        mean6 = torch.empty(B, 6, dtype=torch.float32, device=x.device)
+        check(_lib.lib().jpb_pose_head_fwd(ptr(xc), ptr(T), ptr(mean6), B, h * w, Cc, int(invert), stream_of(xc)), "jpb_pose_head_fwd")
+        ctx.save_for_backward(mean6)
+        ctx.geom = (B, Cc, h, w, int(invert))
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        from ._lib import check, ptr, stream_of
+        (mean6,) = ctx.saved_tensors
+        B, Cc, h, w, invert = ctx.geom
+        gT = gT.contiguous()
+        gx = torch.empty((B, Cc, h, w), dtype=torch.float32, device=gT.device, memory_format=CL)
+        check(_lib.lib().jpb_pose_head_bwd(ptr(gT), ptr(mean6), ptr(gx), B, h * w, Cc, invert, stream_of(gT)), "jpb_pose_head_bwd")
+        return gx, None
+
+
 def pose_head(x, invert):
     """Spatial mean of the 6-channel PoseDecoder output, x0.01, Rodrigues, 4x4 assembly
     (pose_decoder.py:22-26, net.py:704-756)."""
     _need_cuda(x)
+    if BACKEND["pose_head"] == "jpb" and x.dtype == torch.float32 and x.shape[1] >= 6:
+        return _PoseHead.apply(x, bool(invert))
+    return _pose_head_torch(x, invert)
+
+
+def _pose_head_torch(x, invert):
     v = 0.01 * x.mean(3).mean(2)
     aa, t = v[:, :3], v[:, 3:]
     B = aa.shape[0]

@@ -1,0 +1,96 @@
+"""Parity of the small fused operators around the trunks (csrc/heads.cu) with the plain PyTorch formulation of the
+reference lines they replace: input prologue (ResnetEncoder.py:99, net.py:633-638), dropout (depth_decoder.py:47-48),
+pose head (pose_decoder.py:22-26, net.py:704-756) incl. its hand-derived backward; and the KAT2 vector of SURVEY.md §8c.
+``[emu]`` = host emulation of the same sources (CPU container), ``[gpu]`` = the C ABI on cuda:0."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu import build_emulation  # noqa: E402
+
+from jperceiver_b200 import _lib, netops as ops  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def dev(request):
+    _lib._handle, _lib._emulated = None, False
+    if request.param == "emu":
+        _lib.use_library(build_emulation(), emulated=True)
+        yield torch.device("cpu")
+    else:
+        assert torch.cuda.is_available(), "gpu-marked test needs a CUDA device"
+        _lib.lib()
+        yield torch.device("cuda:0")
+    _lib._handle, _lib._emulated = None, False
+
+
+@pytest.mark.parametrize("pair,out_hw", [(False, None), (True, (24, 40)), (False, (32, 32)), (True, None)])
+def test_image_prep_vs_torch(dev, pair, out_hw):
+    g = torch.Generator().manual_seed(0)
+    ims = [torch.rand(2, 3, 20, 36, generator=g) for _ in range(2 if pair else 1)]
+    got = ops.image_prep([im.to(dev) for im in ims], out_hw)
+    ref = []
+    for im in ims:
+        if out_hw is not None:
+            im = F.interpolate(im, list(out_hw), mode="bilinear", align_corners=False)
+        ref.append((im - 0.45) / 0.225)
+    ref = torch.cat(ref, 1)
+    C = ref.shape[1]
+    assert got.shape[1] == (8 if pair else 4) and got.is_contiguous(memory_format=torch.channels_last)
+    assert (got[:, :C].cpu() - ref).abs().max().item() < 2e-6       # bilinear weights in a different association order
+    assert got[:, C:].abs().max().item() == 0.0                      # zero channel padding
+
+
+def test_dropout_mask_and_counter_draw(dev):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 8, 6, 10, generator=g).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    mask = (torch.rand(2, 8, 6, 10, generator=g) >= 0.5).float().to(dev)
+    y = ops.dropout(x, 0.5, True, mask)
+    assert (y - x * mask * 2.0).abs().max().item() == 0.0
+    gy = torch.randn(y.shape, generator=g).to(dev)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    assert (gx - gy * mask * 2.0).abs().max().item() == 0.0
+    # counter-based draw: every element is 0 or 2x, about half are kept, the backward regenerates the same mask
+    big = torch.ones(4, 64, 16, 16, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yb = ops.dropout(big, 0.5, True)
+    vals = torch.unique(yb.detach().cpu())
+    assert set(vals.tolist()) <= {0.0, 2.0}
+    keep = (yb.detach() > 0).float().mean().item()
+    assert 0.47 < keep < 0.53
+    (gb,) = torch.autograd.grad(yb, big, torch.ones_like(yb))
+    assert (gb - yb.detach()).abs().max().item() == 0.0
+    assert ops.dropout(big, 0.5, False) is big and ops.dropout(big, 0.0, True) is big
+
+
+@pytest.mark.parametrize("invert", [False, True])
+def test_pose_head_forward_backward_vs_torch(dev, invert):
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(3, 6, 6, 20, generator=g) * 3 + 1.0)
+    x0 = x.clone().requires_grad_(True)
+    ref = ops._pose_head_torch(x0, invert)
+    G = torch.randn(3, 4, 4, generator=g)
+    (g0,) = torch.autograd.grad(ref, x0, G)
+    x1 = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got = ops.pose_head(x1, invert)
+    assert (got.cpu() - ref).abs().max().item() < 2e-6
+    (g1,) = torch.autograd.grad(got, x1, G.to(dev))
+    assert (g1.cpu() - g0).abs().max().item() <= 1e-5 * g0.abs().max().item() + 1e-12
+
+
+def test_pose_head_kat2(dev):
+    """transformation_from_parameters(aa=[.01,-.02,.03], t=[.1,-.05,.2]) — feed a constant map whose
+    mean x 0.01 equals those parameters."""
+    kat = np.load(os.path.join(GOLDEN, "kat.npz"))
+    v = torch.tensor([.01, -.02, .03, .1, -.05, .2]) * 100.0
+    x = v.view(1, 6, 1, 1).expand(1, 6, 4, 5).contiguous().to(dev)
+    fwd = ops.pose_head(x, False).cpu().numpy()[0]
+    inv = ops.pose_head(x, True).cpu().numpy()[0]
+    assert np.abs(fwd - kat["kat2_fwd"].reshape(4, 4)).max() < 2e-6
+    assert np.abs(inv - kat["kat2_inv"].reshape(4, 4)).max() < 2e-6
