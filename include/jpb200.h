@@ -271,6 +271,28 @@ int jpb_dropout(const float* x, const float* mask, float* y, long long n, float 
 int jpb_pose_head_fwd(const float* x, float* T, float* mean6, int B, int hw, int C, int invert, void* stream);
 int jpb_pose_head_bwd(const float* gT, const float* mean6, float* gx, int B, int hw, int C, int invert, void* stream);
 
+/* ---- cross-view transformer core (CrossViewTransformer.py:45-92) around its convolutions; all tensors NHWC [B][n][.],
+ * n = h*w positions, n <= 256.  select: S[j] = max_i <k_i, q_j> (arg = first maximiser), T[j] = v[arg[j]], attn/argd the same
+ * max for the depth pair.  combine: out = front + fused * S + attn @ vd (the reference's broadcast (h x w)(h x w) product over
+ * channels; h == w).  The backward entry points return the gradients of every tensor input (g w.r.t. front is g itself). */
+int jpb_cct_select_fwd(const float* q, const float* k, const float* v, const float* qd, const float* kd, float* T, float* S, int* arg,
+                       float* attn, int* argd, int B, int n, int Cq, int C, void* stream);
+int jpb_cct_select_bwd(const float* q, const float* k, const float* qd, const float* kd, const int* arg, const int* argd, const float* gT,
+                       const float* gS, const float* gattn, float* gq, float* gk, float* gv, float* gqd, float* gkd, int B, int n, int Cq,
+                       int C, void* stream);
+int jpb_cct_combine_fwd(const float* front, const float* fused, const float* S, const float* attn, const float* vd, float* out, int B,
+                        int h, int w, int C, void* stream);
+int jpb_cct_combine_bwd(const float* g, const float* fused, const float* S, const float* attn, const float* vd, float* gfused, float* gS,
+                        float* gattn, float* gvd, int B, int h, int w, int C, void* stream);
+
+/* ---- CycledViewProjection transform module (CycledViewProjection.py:27-67): y2 = relu(W2 relu(W1 x + b1) + b2) over the n
+ * positions of every (sample, channel); x, y1, y2, g, dz1, dz2, dx: NHWC [B][n][C]; W: [n][n] (out, in).  The backward ADDS
+ * the parameter gradients into dW1/db1/dW2/db2 (zero-filled by the caller, or the flat gradient buffer).              */
+int jpb_cvp_mlp_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y1, float* y2, int B, int n,
+                    int C, void* stream);
+int jpb_cvp_mlp_bwd(const float* x, const float* W1, const float* W2, const float* y1, const float* y2, const float* g, float* dz2, float* dz1,
+                    float* dx, float* dW1, float* db1, float* dW2, float* db2, int B, int n, int C, void* stream);
+
 /* ---- batched weight re-layout for the data-gradient GEMMs (autograd's convolution_backward re-lays out each weight
  * separately): dst [Cin][taps][N] = src [N][taps][Cin] with the tap order reversed, for `nent` layers in one launch.
  * entries_dev: device array; block_start = exclusive prefix sum of taps*ceil(N/32)*ceil(Cin/32); nblocks = the total. */

@@ -128,6 +128,12 @@ class _Signatures:
     jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
     jpb_finalize = [P, P, F, P, I, V]
     jpb_weight_flipT = [P, I, I, V]
+    jpb_cct_select_fwd = [P] * 10 + [I, I, I, I, V]
+    jpb_cct_select_bwd = [P] * 14 + [I, I, I, I, V]
+    jpb_cct_combine_fwd = [P] * 6 + [I, I, I, I, V]
+    jpb_cct_combine_bwd = [P] * 9 + [I, I, I, I, V]
+    jpb_cvp_mlp_fwd = [P] * 7 + [I, I, I, V]
+    jpb_cvp_mlp_bwd = [P] * 13 + [I, I, I, V]
     jpb_image_prep = [P, P, P, I, I, I, I, I, I, V]
     jpb_dropout = [P, P, P, C.c_longlong, F, C.c_uint64, C.c_uint64, P, V]
     jpb_pose_head_fwd = [P, P, P, I, I, I, I, V]

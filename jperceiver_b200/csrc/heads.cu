@@ -205,3 +205,213 @@ extern "C" int jpb_pose_head_bwd(const float* gT, const float* mean6, float* gx,
   JPB_LAUNCH(pose_head_bwd_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, gT, mean6, gx, B, hw, C, invert);
   return jpb_status();
 }
+
+// =====================================================================================================================
+// Cross-view transformer core and cycled view projection (CrossViewTransformer.py:45-92, CycledViewProjection.py:11-67).
+// The 1x1 / 3x3 convolutions around them stay tensor-core launches; everything between them — the n x n energies, the hard
+// max / arg-max over front positions, the gather of the projected values, the S-weighted residual and the broadcast
+// (h x w)·(h x w) matrix product with the depth values — is one launch per stage instead of ~20 library kernels per head.
+// All tensors are NHWC: x[b][j][c] with j = row * w + col the position ("token") index, n = h * w <= JPB_CCT_MAX_N.
+namespace {
+
+constexpr int JPB_CCT_MAX_N = 256;
+
+constexpr int CCT_JT = 8;   // positions per block: grid = (B, ceil(n / CCT_JT)[, 2]) so the 4-sample batch still fills tens of SMs
+
+// S[j] = max_i <k_i, q_j>, arg[j] = first maximising i; T[j][:] = v[arg[j]][:]; blockIdx.z = 1: the same max for the depth
+// pair (attn, argd)
+__global__ void __launch_bounds__(128) cct_select_fwd_kernel(const float* q, const float* k, const float* v, const float* qd, const float* kd,
+                                                            float* T, float* S, int* arg, float* attn, int* argd, int n, int Cq, int C) {
+  __shared__ int s_arg[CCT_JT];
+  const int b = blockIdx.x, j0 = blockIdx.y * CCT_JT, depth = blockIdx.z;
+  const float* Q = (depth ? qd : q) + (size_t)b * n * Cq;
+  const float* K = (depth ? kd : k) + (size_t)b * n * Cq;
+  for (int t = JPB_TID; t < CCT_JT; t += JPB_NT) {
+    const int j = j0 + t;
+    if (j >= n) continue;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int i = 0; i < n; ++i) {
+      float e = 0.f;
+      for (int c = 0; c < Cq; ++c) e += K[(size_t)i * Cq + c] * Q[(size_t)j * Cq + c];
+      if (e > best || i == 0) { best = e; bi = i; }
+    }
+    if (depth) { attn[b * n + j] = best; argd[b * n + j] = bi; }
+    else { S[b * n + j] = best; arg[b * n + j] = bi; s_arg[t] = bi; }
+  }
+  if (depth) return;
+  __syncthreads();
+  for (int t = JPB_TID; t < CCT_JT * C; t += JPB_NT) {
+    const int jj = t / C, c = t - jj * C;
+    if (j0 + jj < n) T[((size_t)b * n + j0 + jj) * C + c] = v[((size_t)b * n + s_arg[jj]) * C + c];
+  }
+}
+
+// gv[i][c] = sum_{j: arg[j]=i} gT[j][c];  gq[j][:] = gS[j] k[arg[j]][:];  gk[i][:] = sum_{j: arg[j]=i} gS[j] q[j][:]  (+ depth pair)
+__global__ void __launch_bounds__(128) cct_select_bwd_kernel(const float* q, const float* k, const float* qd, const float* kd, const int* arg,
+                                                            const int* argd, const float* gT, const float* gS, const float* gattn, float* gq,
+                                                            float* gk, float* gv, float* gqd, float* gkd, int n, int Cq, int C) {
+  const int b = blockIdx.x, i0 = blockIdx.y * CCT_JT;
+  const int* ab = arg + b * n;
+  const int* adb = argd + b * n;
+  for (int t = JPB_TID; t < CCT_JT * C; t += JPB_NT) {
+    const int i = i0 + t / C, c = t % C;
+    if (i >= n) continue;
+    float s = 0.f;
+    for (int j = 0; j < n; ++j)
+      if (ab[j] == i) s += gT[((size_t)b * n + j) * C + c];
+    gv[((size_t)b * n + i) * C + c] = s;
+  }
+  for (int t = JPB_TID; t < 2 * CCT_JT * Cq; t += JPB_NT) {
+    const int depth = t / (CCT_JT * Cq), r = t - depth * CCT_JT * Cq;
+    const int j = i0 + r / Cq, c = r % Cq;
+    if (j >= n) continue;
+    const float* Q = (depth ? qd : q) + (size_t)b * n * Cq;
+    const float* K = (depth ? kd : k) + (size_t)b * n * Cq;
+    const float* g = (depth ? gattn : gS) + b * n;
+    const int* a = depth ? adb : ab;
+    float* GQ = (depth ? gqd : gq) + (size_t)b * n * Cq;
+    float* GK = (depth ? gkd : gk) + (size_t)b * n * Cq;
+    GQ[(size_t)j * Cq + c] = g[j] * K[(size_t)a[j] * Cq + c];
+    float s = 0.f;                       // here j plays the role of the front position i
+    for (int jj = 0; jj < n; ++jj)
+      if (a[jj] == j) s += g[jj] * Q[(size_t)jj * Cq + c];
+    GK[(size_t)j * Cq + c] = s;
+  }
+}
+
+// out[(r,s)][c] = front + fused * S[(r,s)] + sum_t attn[(r,t)] * vd[(t,s)][c]
+__global__ void __launch_bounds__(128) cct_combine_fwd_kernel(const float* front, const float* fused, const float* S, const float* attn,
+                                                             const float* vd, float* out, int h, int w, int C) {
+  const int b = blockIdx.x, n = h * w, j0 = blockIdx.y * CCT_JT;
+  for (int t = JPB_TID; t < CCT_JT * C; t += JPB_NT) {
+    const int j = j0 + t / C, c = t % C;
+    if (j >= n) continue;
+    const int r = j / w, s = j - r * w;
+    const size_t o = ((size_t)b * n + j) * C + c;
+    float m = 0.f;
+    for (int tt = 0; tt < w; ++tt) m += attn[b * n + r * w + tt] * vd[((size_t)b * n + tt * w + s) * C + c];
+    out[o] = front[o] + fused[o] * S[b * n + j] + m;
+  }
+}
+
+// backward of the combine stage: gfused = g*S, gS = <g, fused>_c, gattn[(r,t)] = sum_{s,c} g[(r,s)][c] vd[(t,s)][c],
+// gvd[(t,s)][c] = sum_r attn[(r,t)] g[(r,s)][c]     (the gradient w.r.t. front is g itself)
+__global__ void __launch_bounds__(128) cct_combine_bwd_kernel(const float* g, const float* fused, const float* S, const float* attn, const float* vd,
+                                                             float* gfused, float* gS, float* gattn, float* gvd, int h, int w, int C) {
+  const int b = blockIdx.x, n = h * w, j0 = blockIdx.y * CCT_JT;
+  for (int t = JPB_TID; t < CCT_JT * C; t += JPB_NT) {
+    const int j = j0 + t / C, c = t % C;
+    if (j >= n) continue;
+    const int tt = j / w, s = j - tt * w;          // j = (t, s) as an index of vd
+    const size_t o = ((size_t)b * n + j) * C + c;
+    gfused[o] = g[o] * S[b * n + j];
+    float m = 0.f;
+    for (int r = 0; r < h; ++r) m += attn[b * n + r * w + tt] * g[((size_t)b * n + r * w + s) * C + c];
+    gvd[o] = m;
+  }
+  for (int t = JPB_TID; t < 2 * CCT_JT; t += JPB_NT) {
+    const int which = t / CCT_JT, j = j0 + t % CCT_JT;
+    if (j >= n) continue;
+    if (which == 0) {
+      float s1 = 0.f;
+      for (int c = 0; c < C; ++c) s1 += g[((size_t)b * n + j) * C + c] * fused[((size_t)b * n + j) * C + c];
+      gS[b * n + j] = s1;
+    } else {
+      const int r = j / w, tt = j - r * w;         // j = (r, t) as an index of attn
+      float s2 = 0.f;
+      for (int s = 0; s < w; ++s)
+        for (int c = 0; c < C; ++c) s2 += g[((size_t)b * n + r * w + s) * C + c] * vd[((size_t)b * n + tt * w + s) * C + c];
+      gattn[b * n + j] = s2;
+    }
+  }
+}
+
+// CycledViewProjection's transform module: per (sample, channel) a 2-layer MLP over the n positions; x, y: [B][n][C].
+// One generic stage, block = (sample, output position), thread = channel:
+//   TRANS = 0:  y[b][o][c] = relu(sum_i W[o][i] x[b][i][c] + bias[o])                         (forward layer)
+//   TRANS = 1:  y[b][i][c] = [gate[b][i][c] > 0] * sum_o W[o][i] x[b][o][c]                   (backward through a layer)
+template <int TRANS>
+__global__ void __launch_bounds__(128) cvp_stage_kernel(const float* x, const float* W, const float* bias, const float* gate, float* y, int n, int C) {
+  const int b = blockIdx.x, o = blockIdx.y;
+  for (int c = JPB_TID; c < C; c += JPB_NT) {
+    float s = (!TRANS && bias) ? bias[o] : 0.f;
+    for (int i = 0; i < n; ++i) s += (TRANS ? W[i * n + o] : W[o * n + i]) * x[((size_t)b * n + i) * C + c];
+    const size_t idx = ((size_t)b * n + o) * C + c;
+    if (TRANS) y[idx] = (!gate || gate[idx] > 0.f) ? s : 0.f;
+    else y[idx] = s > 0.f ? s : 0.f;
+  }
+}
+
+// dz = g * [y > 0]
+__global__ void __launch_bounds__(256) relu_gate_kernel(const float* g, const float* y, float* dz, long long nel) {
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < nel; i += (long long)gridDim.x * JPB_NT) dz[i] = y[i] > 0.f ? g[i] : 0.f;
+}
+
+// dW[o][i] += sum_{b,c} dz[b][o][c] * xin[b][i][c];  db[o] += sum_{b,c} dz[b][o][c]      block = output position o, thread = i
+__global__ void __launch_bounds__(128) cvp_wgrad_kernel(const float* dz, const float* xin, float* dW, float* db, int B, int n, int C) {
+  const int o = blockIdx.x;
+  for (int i = JPB_TID; i <= n; i += JPB_NT) {      // i == n: the bias column
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float* zr = dz + ((size_t)b * n + o) * C;
+      const float* xr = xin + ((size_t)b * n + (i < n ? i : 0)) * C;
+      if (i < n) for (int c = 0; c < C; ++c) s += zr[c] * xr[c];
+      else for (int c = 0; c < C; ++c) s += zr[c];
+    }
+    if (i < n) dW[o * n + i] += s; else db[o] += s;
+  }
+}
+
+}  // namespace
+
+extern "C" int jpb_cct_select_fwd(const float* q, const float* k, const float* v, const float* qd, const float* kd, float* T, float* S, int* arg,
+                                  float* attn, int* argd, int B, int n, int Cq, int C, void* stream) {
+  if (!q || !k || !v || !qd || !kd || !T || !S || !arg || !attn || !argd || B < 1 || n < 1 || n > JPB_CCT_MAX_N) return JPB_ERR_ARG;
+  JPB_LAUNCH(cct_select_fwd_kernel, dim3(B, (n + CCT_JT - 1) / CCT_JT, 2), dim3(128), 0, (cudaStream_t)stream, q, k, v, qd, kd, T, S, arg, attn, argd, n, Cq, C);
+  return jpb_status();
+}
+
+extern "C" int jpb_cct_select_bwd(const float* q, const float* k, const float* qd, const float* kd, const int* arg, const int* argd, const float* gT,
+                                  const float* gS, const float* gattn, float* gq, float* gk, float* gv, float* gqd, float* gkd, int B, int n, int Cq,
+                                  int C, void* stream) {
+  if (!q || !k || !qd || !kd || !arg || !argd || !gT || !gS || !gattn || !gq || !gk || !gv || !gqd || !gkd || n > JPB_CCT_MAX_N) return JPB_ERR_ARG;
+  JPB_LAUNCH(cct_select_bwd_kernel, dim3(B, (n + CCT_JT - 1) / CCT_JT), dim3(128), 0, (cudaStream_t)stream, q, k, qd, kd, arg, argd, gT, gS, gattn, gq, gk, gv, gqd, gkd, n, Cq, C);
+  return jpb_status();
+}
+
+extern "C" int jpb_cct_combine_fwd(const float* front, const float* fused, const float* S, const float* attn, const float* vd, float* out, int B,
+                                   int h, int w, int C, void* stream) {
+  if (!front || !fused || !S || !attn || !vd || !out || B < 1 || h != w) return JPB_ERR_ARG;   // attn @ vd needs square maps (as the reference)
+  JPB_LAUNCH(cct_combine_fwd_kernel, dim3(B, (h * w + CCT_JT - 1) / CCT_JT), dim3(128), 0, (cudaStream_t)stream, front, fused, S, attn, vd, out, h, w, C);
+  return jpb_status();
+}
+
+extern "C" int jpb_cct_combine_bwd(const float* g, const float* fused, const float* S, const float* attn, const float* vd, float* gfused, float* gS,
+                                   float* gattn, float* gvd, int B, int h, int w, int C, void* stream) {
+  if (!g || !fused || !S || !attn || !vd || !gfused || !gS || !gattn || !gvd || B < 1 || h != w) return JPB_ERR_ARG;
+  JPB_LAUNCH(cct_combine_bwd_kernel, dim3(B, (h * w + CCT_JT - 1) / CCT_JT), dim3(128), 0, (cudaStream_t)stream, g, fused, S, attn, vd, gfused, gS, gattn, gvd, h, w, C);
+  return jpb_status();
+}
+
+extern "C" int jpb_cvp_mlp_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y1, float* y2, int B, int n,
+                               int C, void* stream) {
+  if (!x || !W1 || !b1 || !W2 || !b2 || !y1 || !y2 || B < 1 || n < 1) return JPB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  JPB_LAUNCH(cvp_stage_kernel<0>, dim3(B, n), dim3(128), 0, st, x, W1, b1, nullptr, y1, n, C);
+  JPB_LAUNCH(cvp_stage_kernel<0>, dim3(B, n), dim3(128), 0, st, y1, W2, b2, nullptr, y2, n, C);
+  return jpb_status();
+}
+
+extern "C" int jpb_cvp_mlp_bwd(const float* x, const float* W1, const float* W2, const float* y1, const float* y2, const float* g, float* dz2, float* dz1,
+                               float* dx, float* dW1, float* db1, float* dW2, float* db2, int B, int n, int C, void* stream) {
+  if (!x || !W1 || !W2 || !y1 || !y2 || !g || !dz2 || !dz1 || !dx || !dW1 || !db1 || !dW2 || !db2 || B < 1) return JPB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nel = (long long)B * n * C;
+  JPB_LAUNCH(relu_gate_kernel, dim3((unsigned)((nel + 255) / 256)), dim3(256), 0, st, g, y2, dz2, nel);
+  JPB_LAUNCH(cvp_stage_kernel<1>, dim3(B, n), dim3(128), 0, st, dz2, W2, nullptr, y1, dz1, n, C);
+  JPB_LAUNCH(cvp_stage_kernel<1>, dim3(B, n), dim3(128), 0, st, dz1, W1, nullptr, nullptr, dx, n, C);
+  JPB_LAUNCH(cvp_wgrad_kernel, dim3(n), dim3(128), 0, st, dz2, y1, dW2, db2, B, n, C);
+  JPB_LAUNCH(cvp_wgrad_kernel, dim3(n), dim3(128), 0, st, dz1, x, dW1, db1, B, n, C);
+  return jpb_status();
+}

@@ -23,7 +23,8 @@ BACKEND = {
     "dropout": "jpb",       # csrc/heads.cu: counter-based keep mask, one launch per direction
     "image_prep": "jpb",    # csrc/heads.cu: normalise + bilinear resize + pair concatenation + NHWC/channel padding in one launch
     "pose_head": "jpb",     # csrc/heads.cu: spatial mean + Rodrigues + 4x4 assembly, forward and hand-derived backward
-    "cvp_mlp": "torch", "cct_attention": "torch",
+    "cvp_mlp": "jpb",       # csrc/heads.cu: both Linear+ReLU layers of a transform module in one launch per direction
+    "cct_attention": "jpb", # csrc/heads.cu: energies + hard max/arg-max + gather, and the S-weighted residual + attn @ value_d
 }
 
 
@@ -172,14 +173,118 @@ def resize_bilinear(x, out_hw):
     return F.interpolate(x, list(out_hw), mode="bilinear", align_corners=False)
 
 
+def _nhwc(t):
+    return t if t.is_contiguous(memory_format=CL) else t.contiguous(memory_format=CL)
+
+
+class _CvpMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2):
+        from ._lib import check, ptr, stream_of
+        x = _nhwc(x)
+        B, Cc, h, w = x.shape
+        n = h * w
+        W1c, W2c = W1.detach().contiguous(), W2.detach().contiguous()
+        y1, y2 = torch.empty_like(x, memory_format=CL), torch.empty_like(x, memory_format=CL)
+        check(_lib.lib().jpb_cvp_mlp_fwd(ptr(x), ptr(W1c), ptr(b1.detach()), ptr(W2c), ptr(b2.detach()), ptr(y1), ptr(y2), B, n, Cc,
+                                         stream_of(x)), "jpb_cvp_mlp_fwd")
+        ctx.save_for_backward(x, W1c, W2c, y1, y2, W1, b1, W2, b2)
+        return y2
+
+    @staticmethod
+    def backward(ctx, g):
+        from ._lib import check, ptr, stream_of
+        from .functional import direct_grad_target
+        x, W1c, W2c, y1, y2, W1, b1, W2, b2 = ctx.saved_tensors
+        B, Cc, h, w = x.shape
+        g = _nhwc(g)
+        dz2, dz1, dx = (torch.empty_like(x, memory_format=CL) for _ in range(3))
+        targets = [direct_grad_target(p) for p in (W1, b1, W2, b2)]
+        direct = all(t is not None and t.is_contiguous() for t in targets)
+        dW1, db1, dW2, db2 = targets if direct else [torch.zeros_like(p) for p in (W1, b1, W2, b2)]
+        check(_lib.lib().jpb_cvp_mlp_bwd(ptr(x), ptr(W1c), ptr(W2c), ptr(y1), ptr(y2), ptr(g), ptr(dz2), ptr(dz1), ptr(dx), ptr(dW1), ptr(db1),
+                                         ptr(dW2), ptr(db2), B, h * w, Cc, stream_of(x)), "jpb_cvp_mlp_bwd")
+        if direct:
+            return dx, None, None, None, None
+        return dx, dW1, db1, dW2, db2
+
+
 def cvp_mlp(x, fc0, fc2):
     """Per-channel MLP over the flattened (h*w) positions: Linear+ReLU twice (CycledViewProjection.py:27-67)."""
     _need_cuda(x)
+    if BACKEND["cvp_mlp"] == "jpb" and x.dtype == torch.float32:
+        return _CvpMlp.apply(x, fc0.weight, fc0.bias, fc2.weight, fc2.bias)
     B, C, h, w = x.shape
     y = x.reshape(B, C, h * w)  # logical NCHW order, as the reference's .view does
     y = F.relu(F.linear(y, fc0.weight, fc0.bias))
     y = F.relu(F.linear(y, fc2.weight, fc2.bias))
     return y.reshape(B, C, h, w).contiguous(memory_format=CL)
+
+
+class _CctSelect(torch.autograd.Function):
+    """(q, k, v, qd, kd) -> (T, S, attn): energies, hard max / arg-max over front positions, gather of the projected values."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, qd, kd):
+        from ._lib import check, ptr, stream_of
+        q, k, v, qd, kd = (_nhwc(t) for t in (q, k, v, qd, kd))
+        B, Cq, h, w = q.shape
+        Cc, n = v.shape[1], h * w
+        dev = q.device
+        T = torch.empty_like(v, memory_format=CL)
+        S = torch.empty(B, 1, h, w, dtype=torch.float32, device=dev)
+        attn = torch.empty(B, 1, h, w, dtype=torch.float32, device=dev)
+        arg = torch.empty(B, n, dtype=torch.int32, device=dev)
+        argd = torch.empty(B, n, dtype=torch.int32, device=dev)
+        check(_lib.lib().jpb_cct_select_fwd(ptr(q), ptr(k), ptr(v), ptr(qd), ptr(kd), ptr(T), ptr(S), ptr(arg), ptr(attn), ptr(argd), B, n, Cq, Cc,
+                                            stream_of(q)), "jpb_cct_select_fwd")
+        ctx.save_for_backward(q, k, qd, kd, arg, argd)
+        ctx.geom = (B, n, Cq, Cc, h, w)
+        ctx.mark_non_differentiable(arg, argd)
+        return T, S, attn
+
+    @staticmethod
+    def backward(ctx, gT, gS, gattn):
+        from ._lib import check, ptr, stream_of
+        q, k, qd, kd, arg, argd = ctx.saved_tensors
+        B, n, Cq, Cc, h, w = ctx.geom
+        dev = q.device
+        gT = _nhwc(gT) if gT is not None else torch.zeros((B, Cc, h, w), dtype=torch.float32, device=dev, memory_format=CL)
+        gS = gS.contiguous() if gS is not None else torch.zeros(B, n, dtype=torch.float32, device=dev)
+        gattn = gattn.contiguous() if gattn is not None else torch.zeros(B, n, dtype=torch.float32, device=dev)
+        gq, gk, gqd, gkd = (torch.empty_like(q, memory_format=CL) for _ in range(4))
+        gv = torch.empty((B, Cc, h, w), dtype=torch.float32, device=dev, memory_format=CL)
+        check(_lib.lib().jpb_cct_select_bwd(ptr(q), ptr(k), ptr(qd), ptr(kd), ptr(arg), ptr(argd), ptr(gT), ptr(gS), ptr(gattn), ptr(gq), ptr(gk),
+                                            ptr(gv), ptr(gqd), ptr(gkd), B, n, Cq, Cc, stream_of(q)), "jpb_cct_select_bwd")
+        return gq, gk, gv, gqd, gkd
+
+
+class _CctCombine(torch.autograd.Function):
+    """out = front + fused * S + attn @ value_d."""
+
+    @staticmethod
+    def forward(ctx, front, fused, S, attn, vd):
+        from ._lib import check, ptr, stream_of
+        front, fused, vd = _nhwc(front), _nhwc(fused), _nhwc(vd)
+        S, attn = S.contiguous(), attn.contiguous()
+        B, Cc, h, w = front.shape
+        out = torch.empty_like(front, memory_format=CL)
+        check(_lib.lib().jpb_cct_combine_fwd(ptr(front), ptr(fused), ptr(S), ptr(attn), ptr(vd), ptr(out), B, h, w, Cc, stream_of(front)),
+              "jpb_cct_combine_fwd")
+        ctx.save_for_backward(fused, S, attn, vd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from ._lib import check, ptr, stream_of
+        fused, S, attn, vd = ctx.saved_tensors
+        B, Cc, h, w = fused.shape
+        g = _nhwc(g)
+        gfused, gvd = torch.empty_like(fused, memory_format=CL), torch.empty_like(vd, memory_format=CL)
+        gS, gattn = torch.empty_like(S), torch.empty_like(attn)
+        check(_lib.lib().jpb_cct_combine_bwd(ptr(g), ptr(fused), ptr(S), ptr(attn), ptr(vd), ptr(gfused), ptr(gS), ptr(gattn), ptr(gvd), B, h, w, Cc,
+                                             stream_of(g)), "jpb_cct_combine_bwd")
+        return g, gfused, gS, gattn, gvd
 
 
 def cct_attention(front, cross, front_hat, dfeat, p):
@@ -189,6 +294,16 @@ def cct_attention(front, cross, front_hat, dfeat, p):
     _need_cuda(front)
     B, C, a, b = front.shape
     n = a * b
+    if BACKEND["cct_attention"] == "jpb" and a == b and n <= 256:
+        q = conv2d(cross, p.query_conv.weight, p.query_conv.bias)
+        k = conv2d(front, p.key_conv.weight, p.key_conv.bias)
+        v = conv2d(front_hat, p.value_conv.weight, p.value_conv.bias)
+        qd = conv2d(cross, p.query_conv_depth.weight, p.query_conv_depth.bias)
+        kd = conv2d(front, p.key_conv_depth.weight, p.key_conv_depth.bias)
+        vd = conv2d(dfeat, p.value_conv_depth.weight, p.value_conv_depth.bias)
+        T, S, attn = _CctSelect.apply(q, k, v, qd, kd)
+        fused = conv2d([(front, False), (T, False)], p.f_conv.weight, p.f_conv.bias, pad=1)
+        return _CctCombine.apply(front, fused, S, attn, vd), S, attn
     q = conv2d(cross, p.query_conv.weight, p.query_conv.bias).reshape(B, -1, n)
     k = conv2d(front, p.key_conv.weight, p.key_conv.bias).reshape(B, -1, n).permute(0, 2, 1)
     energy = torch.bmm(k, q)

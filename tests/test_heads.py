@@ -94,3 +94,61 @@ def test_pose_head_kat2(dev):
     inv = ops.pose_head(x, True).cpu().numpy()[0]
     assert np.abs(fwd - kat["kat2_fwd"].reshape(4, 4)).max() < 2e-6
     assert np.abs(inv - kat["kat2_inv"].reshape(4, 4)).max() < 2e-6
+
+
+def test_cvp_mlp_forward_backward_vs_torch(dev):
+    g = torch.Generator().manual_seed(3)
+    B, C, h = 2, 12, 4
+    n = h * h
+    x = torch.randn(B, C, h, h, generator=g)
+    fc0, fc2 = torch.nn.Linear(n, n), torch.nn.Linear(n, n)
+    with torch.no_grad():
+        for p in list(fc0.parameters()) + list(fc2.parameters()):
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    x0 = x.clone().requires_grad_(True)
+    ref = F.relu(F.linear(F.relu(F.linear(x0.reshape(B, C, n), fc0.weight, fc0.bias)), fc2.weight, fc2.bias)).reshape(B, C, h, h)
+    G = torch.randn(ref.shape, generator=g)
+    gref = torch.autograd.grad(ref, [x0, fc0.weight, fc0.bias, fc2.weight, fc2.bias], G)
+    import copy
+    f0, f2 = copy.deepcopy(fc0).to(dev), copy.deepcopy(fc2).to(dev)
+    x1 = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got = ops.cvp_mlp(x1, f0, f2)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5
+    ggot = torch.autograd.grad(got, [x1, f0.weight, f0.bias, f2.weight, f2.bias], G.to(dev))
+    for a, b in zip(gref, ggot):
+        assert (a - b.cpu()).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1.0)
+
+
+class _P:   # parameter holder with the attribute names CrossViewTransformer uses
+    pass
+
+
+def test_cct_attention_forward_backward_vs_torch(dev):
+    """The fused cross-view-transformer core against the library formulation (bmm / max / gather / broadcast matmul) with the
+    same tensor-core convolutions around it (host emulation runs those through the library convolution)."""
+    g = torch.Generator().manual_seed(4)
+    B, C, h = 2, 16, 4
+    mk = lambda *s: torch.randn(*s, generator=g)
+    tensors = [mk(B, C, h, h) for _ in range(4)]
+    p = _P()
+    for name, co, ci, k in (("query_conv", C // 8, C, 1), ("key_conv", C // 8, C, 1), ("value_conv", C, C, 1), ("f_conv", C, 2 * C, 3),
+                            ("query_conv_depth", C // 8, C, 1), ("key_conv_depth", C // 8, C, 1), ("value_conv_depth", C, C, 1)):
+        m = torch.nn.Conv2d(ci, co, k)
+        with torch.no_grad():
+            m.weight.copy_(mk(*m.weight.shape) * 0.3); m.bias.copy_(mk(*m.bias.shape) * 0.1)
+        setattr(p, name, m.to(dev).to(memory_format=torch.channels_last))
+    res = {}
+    for backend in ("torch", "jpb"):
+        ops.BACKEND["cct_attention"] = backend
+        ins = [t.clone().to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in tensors]
+        out, S, attn = ops.cct_attention(*ins, p)
+        G = torch.Generator().manual_seed(9)
+        go = torch.randn(out.shape, generator=G).to(dev)
+        loss = (out * go).sum() + (S * 0.7).sum() - (attn * 0.3).sum()
+        params = [getattr(p, n_).weight for n_ in ("query_conv", "key_conv", "value_conv", "f_conv", "key_conv_depth", "value_conv_depth")]
+        grads = torch.autograd.grad(loss, ins + params)
+        res[backend] = [out.detach().cpu(), S.detach().cpu(), attn.detach().cpu()] + [t.cpu() for t in grads]
+    ops.BACKEND["cct_attention"] = "jpb"
+    for a, b in zip(res["torch"], res["jpb"]):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1.0)
