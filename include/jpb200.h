@@ -179,6 +179,8 @@ typedef struct JpbConvArgs {
   int l1_gather;                        /* 1: gather through L1 (cp.async.ca) — pays off with the K-block order above */
   long long* dbg;                       /* debug only: [512 CTAs][6 warps][8] globaltimer stamps (tools/conv_timeline.py), or NULL */
   int dbg_skip;                         /* timing experiments only (results are wrong): bit 0 = no A gather, bit 1 = no weight TMA */
+  double* stats;                        /* optional BatchNorm statistics fused into the epilogue: stats[c] += sum over rows of
+                                           out[.][c], stats[N + c] += sum of squares (jpb_bn_stats_accumulator; no split-K, N % 4 == 0) */
 } JpbConvArgs;
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
 
@@ -226,9 +228,12 @@ int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int 
  * finalises (statistics + running_* update + num_batches_tracked += nbt_inc, or the affine gradients), then the apply pass.
  * accumulate != 0: dgamma/dbeta are added to (they alias the flat gradient buffer) instead of overwritten.          */
 long long jpb_bn_workspace_doubles(int C);
+/* the accumulators inside a BatchNorm workspace that a convolution epilogue (JpbConvArgs.stats) may add into; the next
+ * jpb_bn_train_fwd on the same workspace must then be called with stats_ready != 0 (it skips its own statistics pass). */
+double* jpb_bn_stats_accumulator(double* ws);
 int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
                      long long* num_batches_tracked, int nbt_inc, float momentum, float eps, int relu, float* y, float* stat,
-                     double* ws, long long rows, int C, void* stream);
+                     double* ws, long long rows, int C, int stats_ready, void* stream);
 int jpb_bn_eval_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* stat, int relu, float* y,
                     long long rows, int C, void* stream);
 int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,

@@ -81,7 +81,7 @@ class ConvArgs(C.Structure):
         ("dst", C.c_void_p * 3), ("dst_C", C.c_int * 3), ("dst_H", C.c_int * 3), ("dst_W", C.c_int * 3), ("dst_up", C.c_int * 3),
         ("ndst", C.c_int), ("fold_pad", C.c_int), ("fold_reflect", C.c_int), ("fold_H", C.c_int), ("fold_W", C.c_int),
         ("ntaps", C.c_int), ("kw", C.c_int), ("ksplit", C.c_int), ("kcol", C.c_void_p), ("l1_gather", C.c_int),
-        ("dbg", C.c_void_p), ("dbg_skip", C.c_int),
+        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p),
     ]
 
 
@@ -112,6 +112,8 @@ def _declare(h):
     h.jpb_build_info.restype = C.c_char_p
     h.jpb_bn_workspace_doubles.restype = C.c_longlong
     h.jpb_bn_workspace_doubles.argtypes = [C.c_int]
+    h.jpb_bn_stats_accumulator.restype = C.c_void_p
+    h.jpb_bn_stats_accumulator.argtypes = [C.c_void_p]
     for name in dir(_Signatures):
         if name.startswith("jpb_"):
             if not hasattr(h, name) and name in EMU_MISSING:
@@ -156,7 +158,7 @@ class _Signatures:
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]
-    jpb_bn_train_fwd = [P, P, P, P, P, P, P, I, F, F, I, P, P, P, C.c_longlong, I, V]
+    jpb_bn_train_fwd = [P, P, P, P, P, P, P, I, F, F, I, P, P, P, C.c_longlong, I, I, V]
     jpb_bn_eval_fwd = [P, P, P, P, P, I, P, C.c_longlong, I, V]
     jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, I, P, C.c_longlong, I, V]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
@@ -164,7 +166,7 @@ class _Signatures:
 
 
 def exported_symbols():
-    return ["jpb_abi_version", "jpb_build_info", "jpb_bn_workspace_doubles"] + [n for n in dir(_Signatures) if n.startswith("jpb_")]
+    return ["jpb_abi_version", "jpb_build_info", "jpb_bn_workspace_doubles", "jpb_bn_stats_accumulator"] + [n for n in dir(_Signatures) if n.startswith("jpb_")]
 
 
 def lib():

@@ -376,6 +376,7 @@ class _ConvTC(torch.autograd.Function):
         ups, stride, pad, reflect, act = cfg["ups"], cfg["stride"], cfg["pad"], cfg["reflect"], cfg["act"]
         xs = [x if x.is_contiguous(memory_format=CL) else x.contiguous(memory_format=CL) for x in xs]
         if SMALLN and _is_smalln(weight, xs, stride, pad, residual):
+            STATS_FUSED[0] = False
             out = smalln_fwd(xs[0], ups[0], weight, bias, reflect, act)
             ctx.cfg = cfg
             ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)
@@ -415,6 +416,11 @@ class _ConvTC(torch.autograd.Function):
             a.residual = ptr(residual)
         a.act = ACT[act]
         a.out = ptr(out)
+        STATS_FUSED[0] = False
+        if cfg.get("bn_stats") and ks == 1 and N % 4 == 0 and N <= 2048:
+            from .functional import bn_stats_pointer
+            a.stats = bn_stats_pointer(N, dev)
+            STATS_FUSED[0] = True
         if DBG_STAMPS is not None:
             a.dbg = ptr(DBG_STAMPS)
         a.dbg_skip = DBG_SKIP
@@ -469,6 +475,9 @@ class _ConvTC(torch.autograd.Function):
         return (None, gw, gb, gr) + tuple(grads)
 
 
-def conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual):
-    cfg = dict(ups=tuple(bool(u) for u in ups), stride=stride, pad=pad, reflect=bool(reflect), act=act)
+STATS_FUSED = [False]   # set by the last forward launch: its epilogue accumulated the BatchNorm statistics of its output
+
+
+def conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual, bn_stats=False):
+    cfg = dict(ups=tuple(bool(u) for u in ups), stride=stride, pad=pad, reflect=bool(reflect), act=act, bn_stats=bool(bn_stats))
     return _ConvTC.apply(cfg, weight, bias, residual, *xs)

@@ -154,6 +154,61 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const flo
   }
 }
 
+// Forward apply when the statistics were accumulated by the producing convolution's epilogue (JpbConvArgs.stats): every block
+// derives (mean, rstd) of all channels from the double accumulators, normalises its slab, and the last block to finish
+// (ticket) writes stat / running statistics / num_batches_tracked and re-zeroes the accumulators for the next layer.
+__global__ void __launch_bounds__(256) bn_apply_from_sums_kernel(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                                                                long long n4, int C, int relu, double* ws, BnTail tail) {
+  JPB_DYN_SMEM(float, sstat);   // [2][C]
+  __shared__ int s_last;
+  const double* run = bn_running(ws);
+  for (int c = JPB_TID; c < C; c += JPB_NT) {
+    const double mean = run[c] / (double)tail.rows;
+    double var = run[C + c] / (double)tail.rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sstat[c] = (float)mean;
+    sstat[C + c] = (float)(1.0 / sqrt(var + (double)tail.eps));
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n4; i += (long long)gridDim.x * JPB_NT) {
+    const int c = (int)((i * 4) % C);
+    const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (res) { const float4 q = *reinterpret_cast<const float4*>(res + i * 4); r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
+    for (int k = 0; k < 4; ++k) {
+      float t = (o[k] - sstat[c + k]) * sstat[C + c + k] * gamma[c + k] + beta[c + k] + r[k];
+      if (relu && !(t > 0.f)) t = 0.f;
+      o[k] = t;
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (JPB_TID == 0) s_last = (atomicAdd(bn_ticket(ws), 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  double* runw = bn_running(ws);
+  for (int c = JPB_TID; c < C; c += JPB_NT) {
+    const double mean = runw[c] / (double)tail.rows;
+    double var = runw[C + c] / (double)tail.rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    tail.stat[c] = sstat[c];
+    tail.stat[C + c] = sstat[C + c];
+    if (tail.running_mean) {
+      const double unb = tail.rows > 1 ? var * (double)tail.rows / (double)(tail.rows - 1) : var;
+      tail.running_mean[c] = (float)((1.0 - tail.momentum) * tail.running_mean[c] + tail.momentum * mean);
+      tail.running_var[c] = (float)((1.0 - tail.momentum) * tail.running_var[c] + tail.momentum * unb);
+    }
+  }
+  __syncthreads();
+  for (int j = JPB_TID; j < 2 * C; j += JPB_NT) runw[j] = 0.0;
+  if (JPB_TID == 0) {
+    if (tail.num_batches_tracked) tail.num_batches_tracked[0] += tail.nbt_inc;
+    *bn_ticket(ws) = 0;
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* x, const float* dy, const float* y, const float* stat, const float* gamma,
                                                           const double* acc, float* dx, float* dres, long long rows, long long n4, int C, int relu) {
   const double inv_n = 1.0 / (double)rows;
@@ -197,17 +252,25 @@ inline unsigned bn_grid(long long work, int per_block, int cap) {
 
 }  // namespace
 
+extern "C" double* jpb_bn_stats_accumulator(double* ws) { return ws ? ws + 2 + 2 * BN_MAX_C : nullptr; }
+
 extern "C" long long jpb_bn_workspace_doubles(int C) { (void)C; return 2 + (long long)4 * BN_MAX_C; }
 
 extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                 long long* num_batches_tracked, int nbt_inc, float momentum, float eps, int relu, float* y, float* stat,
-                                double* ws, long long rows, int C, void* stream) {
+                                double* ws, long long rows, int C, int stats_ready, void* stream) {
   if (!x || !gamma || !beta || !y || !stat || !ws || rows < 1 || C < 4 || (C & 3) || C > BN_MAX_C) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned nb = bn_colsum_grid(rows, C);
   BnTail t = {};
   t.rows = rows; t.eps = eps; t.momentum = momentum; t.stat = stat; t.running_mean = running_mean; t.running_var = running_var;
   t.num_batches_tracked = num_batches_tracked; t.nbt_inc = nbt_inc;
+  if (stats_ready) {   // the producing convolution already accumulated (sum, sum of squares): one launch
+    const long long n4s = rows * C / 4;
+    JPB_LAUNCH(bn_apply_from_sums_kernel, dim3(bn_grid(n4s, 256 * 4, 148 * 8)), dim3(256), 2 * C * sizeof(float), st, x, res, gamma, beta, y, n4s, C,
+               relu, ws, t);
+    return jpb_status();
+  }
   JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, ws, t);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, res, stat, gamma, beta, y, n4, C, relu);

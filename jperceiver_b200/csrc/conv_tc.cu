@@ -158,6 +158,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// BatchNorm statistics fused into the convolution epilogue: lanes l, l+8, l+16, l+24 hold sums of the same four output
+// channels over different rows of the warp's 32-row slab; fold them and add the warp's totals (sum, sum of squares) into the
+// double-precision accumulators the BatchNorm apply pass finalises (csrc/bn.cu) — the statistics pass over the convolution
+// output disappears.  Executed by all 32 lanes.
+__device__ __forceinline__ void bn_stats_flush(double* stats, int N, int col, bool valid, int lane, float4 s1, float4 s2) {
+  float v[8] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+  }
+  if (lane < 8 && valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(stats + col + q, (double)v[q]);
+      atomicAdd(stats + N + col + q, (double)v[4 + q]);
+    }
+  }
+}
+
+// same fold, into shared memory: dst[c] (+NT: sums of squares) for the 32 columns of this pass; lanes 0-7 write 4 columns each
+__device__ __forceinline__ void bn_stats_to_smem(uint32_t dst, int NT, int lane, float4 s1, float4 s2) {
+  float v[8] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+  }
+  if (lane < 8) {
+    sts128(dst + (uint32_t)lane * 16u, make_float4(v[0], v[1], v[2], v[3]));
+    sts128(dst + (uint32_t)(NT + lane * 4) * 4u, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
 struct SrcDev {
   const float* ptr;
   int C, H, W, up;
@@ -231,30 +265,35 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   JPB_STAMP(1);
 
-  // ---- per-tile gather offsets, all 192 threads: s_off[(tap*nsrc + src)*BM + row] = element offset of the pixel that
-  // tile row `row` reads for filter tap `tap` in source `src` (padding / reflection / up-sampling / stride folded), or -1
-  {
-    const int nts = a.ntaps * a.nsrc;
-    for (int idx = tid; idx < nts * BM; idx += 192) {
-      const int ts = idx / BM, row = idx - ts * BM;
-      const int tap = ts / a.nsrc, si = ts - tap * a.nsrc;
-      const int m = m0 + row;
-      int off = -1;
-      if (m < M) {
-        const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
-        const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
-        int iy = oy * a.stride - a.pad + tap / a.kw, ix = ox * a.stride - a.pad + tap % a.kw;
-        bool ok = true;
-        if (a.in_div == 2) { ok = !((iy | ix) & 1); iy >>= 1; ix >>= 1; }   // dgrad of a stride-2 convolution
+  // ---- per-tile gather offsets: s_off[(tap*nsrc + src)*BM + row] = element offset of the pixel that tile row `row` reads for
+  // filter tap `tap` in source `src` (padding / reflection / up-sampling / stride folded), or -1.  Thread = tile row: three
+  // integer divisions per row, then the taps are walked with counters (the per-entry form with six divisions per entry cost
+  // 2.2 us of every tile's 4.7 us set-up).
+  if (tid < BM) {
+    const int m = m0 + tid;
+    const bool rowok = m < M;
+    const int HoWo = a.Ho * a.Wo;
+    const int b = rowok ? m / HoWo : 0, rem = m - b * HoWo;
+    const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
+    int tap = 0;
+    for (int ky = 0; tap < a.ntaps; ++ky)
+      for (int kx = 0; kx < a.kw && tap < a.ntaps; ++kx, ++tap) {
+        int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+        bool ok = rowok;
+        if (a.in_div == 2) { ok = ok && !((iy | ix) & 1); iy >>= 1; ix >>= 1; }   // dgrad of a stride-2 convolution
         if (a.reflect) { iy = jpb_reflect(iy, a.Hin); ix = jpb_reflect(ix, a.Win); }
         else ok = ok && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-        if (ok) {
-          if (a.src_up[si]) { iy >>= 1; ix >>= 1; }
-          off = ((b * a.src_H[si] + iy) * a.src_W[si] + ix) * a.src_C[si];
+        for (int si = 0; si < a.nsrc; ++si) {
+          int off = -1;
+          if (ok) {
+            const int sy = a.src_up[si] ? (iy >> 1) : iy, sx = a.src_up[si] ? (ix >> 1) : ix;
+            off = ((b * a.src_H[si] + sy) * a.src_W[si] + sx) * a.src_C[si];
+          }
+          sts32(soff_u32 + (uint32_t)((tap * a.nsrc + si) * BM + tid) * 4u, off);
         }
       }
-      sts32(soff_u32 + (uint32_t)idx * 4u, off);
-    }
+  } else if (tid == 128) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&wmap)) : "memory");   // descriptor fetch off the first TMA's path
   }
   __syncthreads();
   JPB_STAMP(2);
@@ -377,6 +416,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       // bias / residual / output covers whole 128-byte lines instead of 32 rows x 16 bytes.
       const uint32_t sbuf = smem_u32(smem) + (uint32_t)warp * (32 * 36 + 64) * 4u;
       const uint32_t rowptr = sbuf + 32 * 36 * 4;
+      const uint32_t sstats = smem_u32(smem) + 4u * (32 * 36 + 64) * 4u;   // [4 warps][2][NT] floats, behind the staging tiles
       sts64(rowptr + (uint32_t)lane * 8u, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull);
       __syncwarp();
       const int c4 = (lane & 7) * 4, r0 = lane >> 3;
@@ -387,6 +427,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
           sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
         __syncwarp();
         const int col = j + c4;
+        float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = make_float4(0.f, 0.f, 0.f, 0.f);   // BatchNorm statistics of this pass
         if (col < nvalid_all) {
           float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.bias) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);
@@ -404,9 +445,27 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
             o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
             if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             else *reinterpret_cast<float4*>(op) = o;
+            st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
+            st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
           }
         }
+        if (a.stats) {
+          if (NT >= 32) bn_stats_to_smem(sstats + (uint32_t)(warp * 2 * NT + j) * 4u, NT, lane, st1, st2);
+          else bn_stats_flush(a.stats, a.N, n0 + col, col < nvalid_all, lane, st1, st2);
+        }
         __syncwarp();
+      }
+      if (a.stats && NT >= 32) {
+        // fold the four epilogue warps' column sums in shared memory: 2*NT reductions per CTA instead of 8*NT
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int t = tid; t < 2 * NT; t += 128) {
+          const int cc = t % NT, which = t / NT;
+          if (cc < nvalid_all) {
+            float v = 0.f;
+            for (int ww = 0; ww < 4; ++ww) v += __int_as_float(lds32(sstats + (uint32_t)(ww * 2 * NT + which * NT + cc) * 4u));
+            atomicAdd(a.stats + (size_t)which * a.N + n0 + cc, (double)v);
+          }
+        }
       }
     } else {
     for (int j = 0; j < NT; j += 16) {
@@ -504,7 +563,8 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
   constexpr int EPI_WARP_FLOATS = 32 * 36 + 64;          // padded 32x32 tile + 32 row pointers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + 4 * EPI_WARP_FLOATS);
+  constexpr int EPI_STATS_FLOATS = NT <= 64 ? 4 * 2 * NT : 0;   // cross-warp fold of the fused BatchNorm statistics
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + 4 * EPI_WARP_FLOATS + EPI_STATS_FLOATS);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accf_bar = empty_bar + STAGES;   // [2] accumulator buffer complete (MMA -> epilogue)
   uint64_t* acce_bar = accf_bar + 2;         // [2] accumulator buffer drained (epilogue -> MMA)
@@ -531,6 +591,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&wmap)) : "memory");
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -703,6 +764,12 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
     const uint32_t sbuf = smem_u32(epi) + (uint32_t)(warp * EPI_WARP_FLOATS) * 4u;
     const uint32_t rowptr = sbuf + 32 * 36 * 4;
     const int c4 = (lane & 7) * 4, r0 = lane >> 3;
+    constexpr int RS_PASSES = NT <= 64 ? (NT + 31) / 32 : 1;
+    float run_stats[RS_PASSES][8];            // BatchNorm column sums of all tiles of this CTA (fused statistics, N <= NT <= 64)
+#pragma unroll
+    for (int pz = 0; pz < RS_PASSES; ++pz)
+#pragma unroll
+      for (int qz = 0; qz < 8; ++qz) run_stats[pz][qz] = 0.f;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       JPB_TILE_DECODE(t)
@@ -747,6 +814,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
         for (int q = 0; q < 32; q += 4)
           sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
         __syncwarp();
+        float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = make_float4(0.f, 0.f, 0.f, 0.f);   // BatchNorm statistics of this pass
         if (vec_ok) {
           if (col < nvalid) {
             for (int i = 0; i < 8; ++i) {
@@ -763,6 +831,17 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
               o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
               if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
               else *reinterpret_cast<float4*>(op) = o;
+              st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
+              st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
+            }
+          }
+          if (a.stats) {
+            if (ntiles == 1 && NT <= 64) {       // every tile of this CTA has the same columns: keep running sums
+              float* rs = run_stats[(NT <= 64) ? j / 32 : 0];
+              rs[0] += st1.x; rs[1] += st1.y; rs[2] += st1.z; rs[3] += st1.w;
+              rs[4] += st2.x; rs[5] += st2.y; rs[6] += st2.z; rs[7] += st2.w;
+            } else {
+              bn_stats_flush(a.stats, a.N, n0 + col, col < nvalid, lane, st1, st2);
             }
           }
         } else {
@@ -785,6 +864,25 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&acce_bar[buf]);
       ++it;
+    }
+    if (a.stats && ntiles == 1 && NT <= 64) {
+      // one set of reductions per CTA: warp partials -> shared memory -> 2*NT double-precision adds
+      const uint32_t sst = smem_u32(epi) + 4u * EPI_WARP_FLOATS * 4u;   // [4 warps][2][NT] floats
+#pragma unroll
+      for (int pz = 0; pz < RS_PASSES; ++pz) {
+        const float4 a1 = make_float4(run_stats[pz][0], run_stats[pz][1], run_stats[pz][2], run_stats[pz][3]);
+        const float4 a2 = make_float4(run_stats[pz][4], run_stats[pz][5], run_stats[pz][6], run_stats[pz][7]);
+        bn_stats_to_smem(sst + (uint32_t)(warp * 2 * NT + pz * 32) * 4u, NT, lane, a1, a2);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int tt = tid; tt < 2 * NT; tt += 128) {
+        const int cc = tt % NT, which = tt / NT;
+        if (cc < a.N) {
+          float v = 0.f;
+          for (int ww = 0; ww < 4; ++ww) v += __int_as_float(lds32(sst + (uint32_t)(ww * 2 * NT + which * NT + cc) * 4u));
+          atomicAdd(a.stats + (size_t)which * a.N + cc, (double)v);
+        }
+      }
     }
   }
 #undef JPB_TILE_DECODE
@@ -997,7 +1095,7 @@ EncodeTiledFn get_encode() {
 
 template <int NT, int STAGES, int MINB>
 int launch_fwd2(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
-  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 4 * (32 * 36 + 64) * 4 + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 4 * (32 * 36 + 64) * 4 + (NT <= 64 ? 4 * 2 * NT * 4 : 0) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
   static int configured = 0;
   if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
   if (smem > configured) {
@@ -1050,7 +1148,8 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   if (a->nt) nt = a->nt;
   if (nt != 16 && nt != 32 && nt != 64 && nt != 128 && nt != 256) return JPB_ERR_ARG;
   if (a->scatter && (a->ndst < 1 || a->ndst > JPB_CONV_MAX_SRC)) return JPB_ERR_ARG;
-  if (a->ksplit > 1 && (a->bias || a->residual || a->act)) return JPB_ERR_ARG;   // partial tiles cannot run the epilogue
+  if (a->ksplit > 1 && (a->bias || a->residual || a->act || a->stats)) return JPB_ERR_ARG;   // partial tiles cannot run the epilogue
+  if (a->stats && ((a->N & 3) || a->scatter)) return JPB_ERR_ARG;
   if (a->ntaps < 1 || a->kw < 1 || a->ntaps * a->nsrc > 64) return JPB_ERR_ARG;
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)a->w_cols, (cuuint64_t)a->N};

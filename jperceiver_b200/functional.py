@@ -402,7 +402,7 @@ def _bn_workspace(C, device):
 
 class _BNTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, nbt, nbt_inc):
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, nbt, nbt_inc, stats_ready=False):
         x = _clast(x)
         res = _clast(res) if res is not None else None
         B, Cc, H, W = x.shape
@@ -413,7 +413,7 @@ class _BNTrain(torch.autograd.Function):
         check(_launch("bn_fwd", x, lambda: _lib.lib().jpb_bn_train_fwd(
             ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(running_mean), ptr(running_var),
             ptr(nbt) if nbt is not None else None, int(nbt_inc), float(momentum), float(eps),
-            int(relu), ptr(y), ptr(stat), ptr(ws), rows, Cc, stream_of(x))), "jpb_bn_train_fwd")
+            int(relu), ptr(y), ptr(stat), ptr(ws), rows, Cc, int(stats_ready), stream_of(x))), "jpb_bn_train_fwd")
         ctx.save_for_backward(x, y if relu else None, stat, gamma, beta)
         ctx.cfg = (rows, Cc, int(relu), res is not None)
         return y
@@ -436,13 +436,21 @@ class _BNTrain(torch.autograd.Function):
         if has_res and not relu:
             dres = gy
         if direct:
-            return dx, dres, None, None, None, None, None, None, None, None, None
-        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
+            return dx, dres, None, None, None, None, None, None, None, None, None, None
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
-def batchnorm_train(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, num_batches_tracked=None, nbt_inc=0):
-    """``num_batches_tracked`` (int64 [1] device tensor) is advanced by ``nbt_inc`` inside the statistics kernel."""
-    return _BNTrain.apply(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, num_batches_tracked, nbt_inc)
+def batchnorm_train(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, num_batches_tracked=None, nbt_inc=0,
+                    stats_ready=False):
+    """``num_batches_tracked`` (int64 [1] device tensor) is advanced by ``nbt_inc`` inside the statistics kernel.
+    ``stats_ready``: the convolution that produced ``x`` already accumulated its column sums (``bn_stats_pointer``)."""
+    return _BNTrain.apply(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, num_batches_tracked, nbt_inc, stats_ready)
+
+
+def bn_stats_pointer(C, device):
+    """Device address of the statistics accumulators of the shared BatchNorm workspace (for JpbConvArgs.stats)."""
+    ws = _bn_workspace(C, device)
+    return _lib.lib().jpb_bn_stats_accumulator(ptr(ws))
 
 
 def batchnorm_eval(x, res, gamma, beta, running_mean, running_var, eps, relu):

@@ -30,19 +30,22 @@ def _load_pretrained(module, path, num_input_images=1):
 
 def resnet18_forward(net: ResNet18P, x, training):
     """x: normalised channels-last input.  Returns the five feature levels."""
-    x = ops.conv2d(x, net.conv1.weight, stride=2, pad=3)
+    # bn_next: the convolution's epilogue accumulates the BatchNorm statistics of its output, so every conv -> BN pair must be
+    # adjacent (the shortcut branch of a down-sampling block is therefore evaluated first; the result is the same)
+    x = ops.conv2d(x, net.conv1.weight, stride=2, pad=3, bn_next=training)
     x = ops.batchnorm(x, net.bn1, training, relu=True)
     feats = [x]
     x = ops.maxpool(x, 3, 2, 1)
     for li in range(1, 5):
         for blk in getattr(net, "layer%d" % li):
-            y = ops.conv2d(x, blk.conv1.weight, stride=blk.stride, pad=1)
-            y = ops.batchnorm(y, blk.bn1, training, relu=True)
-            y = ops.conv2d(y, blk.conv2.weight, pad=1)
+            res = x
             if blk.downsample is not None:
-                sc = ops.conv2d(x, blk.downsample[0].weight, stride=blk.stride)
-                x = ops.batchnorm(sc, blk.downsample[1], training)
-            x = ops.batchnorm(y, blk.bn2, training, relu=True, residual=x)
+                sc = ops.conv2d(x, blk.downsample[0].weight, stride=blk.stride, bn_next=training)
+                res = ops.batchnorm(sc, blk.downsample[1], training)
+            y = ops.conv2d(x, blk.conv1.weight, stride=blk.stride, pad=1, bn_next=training)
+            y = ops.batchnorm(y, blk.bn1, training, relu=True)
+            y = ops.conv2d(y, blk.conv2.weight, pad=1, bn_next=training)
+            x = ops.batchnorm(y, blk.bn2, training, relu=True, residual=res)
         feats.append(x)
     return feats
 
@@ -203,9 +206,9 @@ class Decoder(nn.Module):
         d = self.decoder
         for lvl in range(5):
             k = 5 * lvl
-            x = ops.conv2d(x, d[k].weight, d[k].bias, pad=1)
+            x = ops.conv2d(x, d[k].weight, d[k].bias, pad=1, bn_next=self.training)
             x = ops.batchnorm(x, d[k + 1], self.training, relu=True)
-            x = ops.conv2d([(x, True)], d[k + 3].weight, d[k + 3].bias, pad=1)
+            x = ops.conv2d([(x, True)], d[k + 3].weight, d[k + 3].bias, pad=1, bn_next=self.training)
             x = ops.batchnorm(x, d[k + 4], self.training)
         x = ops.conv2d(x, d[25].conv.weight, d[25].conv.bias, pad=1, reflect=True)
         return x if is_training else torch.softmax(x, 1)

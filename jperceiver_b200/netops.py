@@ -45,7 +45,10 @@ def _act(y, act):
     raise ValueError(act)
 
 
-def conv2d(inputs, weight, bias=None, *, stride=1, pad=0, reflect=False, act="none", residual=None):
+FUSE_BN_STATS = True   # accumulate BatchNorm statistics in the epilogue of the convolution that feeds a training-mode BatchNorm
+
+
+def conv2d(inputs, weight, bias=None, *, stride=1, pad=0, reflect=False, act="none", residual=None, bn_next=False):
     """Implicit-GEMM convolution with fused gather/epilogue.
 
     ``inputs``: a tensor, or a list of ``(tensor, up2x)`` pairs that are (nearest-2x up-sampled and)
@@ -58,7 +61,11 @@ def conv2d(inputs, weight, bias=None, *, stride=1, pad=0, reflect=False, act="no
     _need_cuda(inputs[0][0])
     xs, ups = [t for t, _ in inputs], [u for _, u in inputs]
     if inputs[0][0].is_cuda and BACKEND["conv2d"] == "jpb":
-        return _conv.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual)
+        y = _conv.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual,
+                            bn_stats=bool(bn_next and FUSE_BN_STATS and BACKEND["batchnorm"] == "jpb"))
+        if bn_next and _conv.STATS_FUSED[0]:
+            y._jpb_bn_stats = True      # consumed (and cleared) by the batchnorm() call that follows
+        return y
     return _conv._torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual)   # host emulation (tests) / library mode
 
 
@@ -74,8 +81,11 @@ def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1
             if not (torch.is_tensor(nbt) and nbt.is_cuda and nbt.dtype == torch.int64):
                 bn.num_batches_tracked += k
                 nbt = None
+            ready = bool(getattr(x, "_jpb_bn_stats", False))
+            if ready:
+                x._jpb_bn_stats = False
             return JF.batchnorm_train(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                      1.0 - (1.0 - momentum) ** k, eps, relu, nbt, k)
+                                      1.0 - (1.0 - momentum) ** k, eps, relu, nbt, k, stats_ready=ready)
         return JF.batchnorm_eval(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, eps, relu)
     if training:
         # ``stat_updates`` = 2 on the road-head BNs reproduces the reference's duplicated forward pass

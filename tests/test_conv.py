@@ -143,3 +143,43 @@ def test_conv_backward_matches_fp32_library(case):
     if not stem:
         for i, (a, b) in enumerate(zip(xm, xr)):
             close(a.grad, b.grad, "input%d" % i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,Cout,H,W,stride,bias", [(64, 64, 40, 64, 1, False), (64, 128, 40, 64, 2, False), (128, 16, 16, 16, 1, True),
+                                                     (4, 64, 64, 96, 2, False)])
+def test_bn_statistics_fused_into_conv_epilogue(C, Cout, H, W, stride, bias):
+    """conv -> training BatchNorm with the statistics accumulated by the convolution epilogue (one BN launch) must equal the
+    two-pass BatchNorm on the same convolution output: y, running statistics, num_batches_tracked, and all gradients."""
+    from jperceiver_b200 import netops as ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4, C, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    k = 7 if C == 4 else 3
+    w = (torch.randn(Cout, C if C != 4 else 3, k, k, generator=g) * 0.1).to(dev).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(Cout, generator=g).to(dev) if bias else None
+    res = {}
+    for fuse in (False, True):
+        ops.FUSE_BN_STATS = fuse
+        bn = torch.nn.BatchNorm2d(Cout).to(dev).train()
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(Cout, generator=torch.Generator().manual_seed(1)) + 0.5)
+            bn.bias.copy_(torch.randn(Cout, generator=torch.Generator().manual_seed(2)))
+        xx, ww = x.clone().requires_grad_(C != 4), w.clone().requires_grad_(True)
+        y = ops.conv2d(xx, ww, b, stride=stride, pad=k // 2, bn_next=True)
+        fused = bool(getattr(y, "_jpb_bn_stats", False))
+        assert not fused or fuse            # never fused when switched off
+        if fuse and stride == 1:            # (small stride-2 cases run split-K, whose partial tiles cannot carry statistics)
+            assert fused
+        z = ops.batchnorm(y, bn, True, relu=True)
+        gz = torch.randn(z.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        grads = torch.autograd.grad(z, [ww, bn.weight, bn.bias] + ([xx] if C != 4 else []), gz)
+        res[fuse] = [z.detach(), bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone().float()] + list(grads)
+    ops.FUSE_BN_STATS = True
+    for a_, b_ in zip(res[False], res[True]):
+        assert (a_ - b_).abs().max().item() <= 1e-4 * max(a_.abs().max().item(), 1.0)   # fp32 partial sums in a different order
+    # the shared accumulators are left clean: a plain two-pass BatchNorm right after gives the library result
+    bn2 = torch.nn.BatchNorm2d(Cout).to(dev).train()
+    t = torch.randn(2, Cout, 8, 8, device=dev).contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.functional.batch_norm(t, None, None, bn2.weight, bn2.bias, True)
+    assert (ops.batchnorm(t, bn2, True) - ref).abs().max().item() < 1e-5
