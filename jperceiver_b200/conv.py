@@ -171,15 +171,21 @@ def _torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual):
     return y
 
 
+KSPLIT_SLOTS = int(_os.environ.get("JPB_KSPLIT_SLOTS", "296"))
+
+
 def _ksplit(M, N, nkb):
-    """Split-K factor for tiles that cannot fill the 148 SMs (deep, small-extent layers: layer3/4, pose and layout tails)."""
+    """Split-K factor for tiles that cannot fill the machine (deep, small-extent layers: layer3/4, pose and layout tails).
+    Target: two shallow CTAs per SM (the wide-tile kernel then runs its 2-CTA/SM configuration), >= 4 K blocks per CTA."""
     nt = 16
     while nt < N and nt < 256:
         nt *= 2
     tiles = ((M + 127) // 128) * ((N + nt - 1) // nt)
     if tiles >= 74 or nkb < 16:
         return 1
-    return max(1, min(148 // tiles, nkb // 8, 16))
+    if KSPLIT_SLOTS <= 148:
+        return max(1, min(148 // tiles, nkb // 8, 16))
+    return max(1, min(KSPLIT_SLOTS // tiles, nkb // 4, 32))
 
 
 def _fill_sources(a, xs, ups):

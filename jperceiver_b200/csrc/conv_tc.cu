@@ -186,7 +186,7 @@ __device__ __forceinline__ void bn_stats_to_smem(uint32_t dst, int NT, int lane,
     v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
     v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
   }
-  if (lane < 8) {
+  if (lane < 8 && lane * 4 < NT) {   // a 16-column tile has only four column groups: the others would spill into the next region
     sts128(dst + (uint32_t)lane * 16u, make_float4(v[0], v[1], v[2], v[3]));
     sts128(dst + (uint32_t)(NT + lane * 4) * 4u, make_float4(v[4], v[5], v[6], v[7]));
   }
