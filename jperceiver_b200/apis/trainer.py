@@ -187,21 +187,26 @@ class TrainEngine:
         if self.world > 1:
             dist.all_reduce(self.flat.grad)
 
-    def step(self, data, need_log=True):
-        """data: dict of device tensors (see ``change_input_variable``).  Returns the stacked loss tensor
-        ``[entries..., total]`` on the device (names in ``self.last_names``)."""
+    def forward_backward(self, data):
+        """Forward + ``compute_losses`` + backward into the flat gradient buffer.  Returns (names, values, total)."""
         from .. import functional as JF, conv as JC
         self.flat.zero_grad()
         JC.WT.enabled = True
         JC.WT.refresh()            # one launch: flipped/transposed weights of every convolution for this step's data gradients
-        _, losses = self.model(data)
-        names, vals, total = loss_scalars(losses)
-        JF.DIRECT_GRAD = True      # backward kernels add parameter gradients straight into the flat gradient buffer
         try:
+            _, losses = self.model(data)
+            names, vals, total = loss_scalars(losses)
+            JF.DIRECT_GRAD = True  # backward kernels add parameter gradients straight into the flat gradient buffer
             total.backward()
         finally:
             JF.DIRECT_GRAD = False
             JC.WT.enabled = JC.WT.fresh = False
+        return names, vals, total
+
+    def step(self, data, need_log=True):
+        """data: dict of device tensors (see ``change_input_variable``).  Returns the stacked loss tensor
+        ``[entries..., total]`` on the device (names in ``self.last_names``)."""
+        names, vals, total = self.forward_backward(data)
         self.exchange_gradients()
         self.optimizer.step(self.world)
         self.last_names = names + ["loss"]
