@@ -141,43 +141,50 @@ def test_data_parallel_gradient_exchange_gloo_world2():
 
 
 @pytest.mark.gpu
-def test_engine_gradients_match_plain_autograd_gpu():
-    """TrainEngine.forward_backward (parameter gradients added straight into the flat buffer by the backward kernels, batched
-    weight re-layout for the data gradients) must produce the same
-    flat gradient as plain autograd (per-parameter gradient tensors accumulated by AccumulateGrad) over the same kernels — on the first call and on the second (cached re-layout buffers)."""
+def test_direct_gradient_accumulation_matches_plain_autograd_gpu():
+    """The training-step backward adds parameter gradients straight into ``param.grad`` (views of the flat gradient buffer) and
+    hands autograd None.  Per operator, on identical inputs, that must equal the plain path (gradient tensors returned to
+    autograd) — and a second backward must accumulate (2x), as parameters shared between calls (the pose encoder runs once per
+    source frame) require.  Whole-network comparisons cannot check this: under TF32 operand rounding the network amplifies
+    fp32 atomic-order noise to 1e-4..1e-3 per activation, so two identical runs already differ by a few percent in gradient
+    norm (tools/diag_noise.py)."""
     import torch
-    from oracle import port as O
-    from jperceiver_b200 import _lib, netops
-    from jperceiver_b200.apis import TrainEngine
-    from jperceiver_b200.model import MONO
+    from jperceiver_b200 import _lib, functional as JF, netops as ops
     _lib._handle, _lib._emulated = None, False
     _lib.lib()
     dev = torch.device("cuda:0")
-    opt = dict(name="Baseline", depth_num_layers=18, pose_num_layers=18, frame_ids=[0, -1, 1], imgs_per_gpu=2, height=128, width=384,
-               scales=[0, 1, 2, 3], min_depth=0.1, max_depth=100.0, depth_pretrained_path=None, pose_pretrained_path=None,
-               automask=True, disp_norm=True, smoothness_weight=1e-3, scale_weight=0.1, dynamic_weight=15.0, static_weight=5.0,
-               occ_map_size=64, num_class=2, loss_type="iou", loss_weight=20, loss2_type="boundary", loss2_weight=20,
-               type="static", loss_sum=3, split="odometry", automask_noise=0.0)
-    model = MONO.module_dict["Baseline"](opt)
-    model.load_state_dict(O.synth_params(model.state_dict(), seed=5))
-    model.to(dev).train()
-    model.DepthDecoder.drop_p = 0.0
-    inp = O.synth_inputs(opt, 2, seed=2, hw_full=(120, 400))
-    oK = inp[("odometry_K", 0, 0)]
-    oK[:, 0, 0] *= 0.3; oK[:, 1, 1] *= 0.3; oK[:, 0, 2] = 200.0; oK[:, 1, 2] = 40.0
-    data = {k: v.to(dev) for k, v in inp.items()}
-    engine = TrainEngine(model)
-    # plain autograd over the same forward kernels
-    engine.flat.zero_grad()
-    _, losses = model(data)
-    sum(losses.values()).backward()
-    ref = engine.flat.grad.clone()
-    scale = ref.abs().max().item()
-    assert scale > 0
-    for call in range(2):
-        engine.forward_backward(data)
-        got = engine.flat.grad
-        err = (got - ref).abs().max().item()
-        # TF32 products are identical in both paths; differences are fp32 accumulation order (atomic adds)
-        assert err <= 2e-3 * scale, (call, err, scale)
-        assert ((got - ref).abs() > 1e-4 * scale).float().mean().item() < 1e-3
+    CL = torch.channels_last
+    g = torch.Generator().manual_seed(21)
+
+    def check(build, params):
+        """build() -> scalar loss using ``params`` (leaf tensors requiring grad)."""
+        plain = torch.autograd.grad(build(), params)
+        for p in params:
+            p.grad = torch.zeros_like(p)          # same strides as the parameter (channels-last weights stay channels-last)
+        for rep in (1, 2):
+            JF.DIRECT_GRAD = True
+            try:
+                build().backward()
+            finally:
+                JF.DIRECT_GRAD = False
+            for p, ref in zip(params, plain):
+                err = (p.grad - rep * ref).abs().max().item()
+                assert err <= 2e-5 * rep * max(ref.abs().max().item(), 1e-6), (rep, tuple(p.shape), err)
+
+    # convolution: weight gradient + bias gradient, 3x3 with activation and 1x1 without
+    for cin, cout, k, act in ((64, 128, 3, "leaky"), (128, 256, 1, "none"), (256, 16, 3, "relu")):
+        x = torch.randn(2, cin, 24, 40, generator=g).to(dev).contiguous(memory_format=CL)
+        w = (torch.randn(cout, cin, k, k, generator=g) * 0.05).to(dev).contiguous(memory_format=CL).requires_grad_(True)
+        b = torch.randn(cout, generator=g).to(dev).requires_grad_(True)
+        G = torch.randn(2, cout, 24, 40, generator=g).to(dev)
+        check(lambda: (ops.conv2d(x, w, b, pad=k // 2, act=act) * G).sum(), [w, b])
+    # BatchNorm affine parameters
+    bn = torch.nn.BatchNorm2d(64).to(dev).train()
+    xb = torch.randn(2, 64, 24, 40, generator=g).to(dev).contiguous(memory_format=CL)
+    Gb = torch.randn(2, 64, 24, 40, generator=g).to(dev)
+    check(lambda: (ops.batchnorm(xb, bn, True, relu=True) * Gb).sum(), [bn.weight, bn.bias])
+    # CVP transform module
+    fc0, fc2 = torch.nn.Linear(16, 16).to(dev), torch.nn.Linear(16, 16).to(dev)
+    xc = torch.randn(2, 32, 4, 4, generator=g).to(dev).contiguous(memory_format=CL)
+    Gc = torch.randn(2, 32, 4, 4, generator=g).to(dev)
+    check(lambda: (ops.cvp_mlp(xc, fc0, fc2) * Gc).sum(), [fc0.weight, fc0.bias, fc2.weight, fc2.bias])
