@@ -218,6 +218,9 @@ int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const float* dz, floa
 /* ---- backward of the convolution epilogue: dz = dy * act'(y) (act as in JpbConvArgs, from the OUTPUT y) and
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */
 int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int C, int act, float* dbias, void* stream);
+/* finishing pass of a split-K convolution whose partial tiles were summed without the epilogue: z = act(z + bias + residual)
+ * in place; z, residual: [rows][C] NHWC, C % 4 == 0; bias / residual may be NULL.                                  */
+int jpb_bias_act(float* z, const float* bias, const float* residual, long long rows, int C, int act, void* stream);
 
 /* ---- BatchNorm2d (training: per-GPU batch statistics) fused with the residual add and ReLU that follow it
  * (resnet.py:28-45, layout_model.py:146-158).  x, res, y, dy, dx, dres: [rows][C] NHWC, C % 4 == 0.

@@ -155,6 +155,7 @@ class _Signatures:
     jpb_conv2d_fwd = [C.POINTER(ConvArgs), V]
     jpb_conv2d_wgrad = [C.POINTER(ConvWgradArgs), V]
     jpb_act_bwd = [P, P, P, C.c_longlong, I, I, P, V]
+    jpb_bias_act = [P, P, P, C.c_longlong, I, I, V]
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]

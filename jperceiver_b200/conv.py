@@ -171,6 +171,7 @@ def _torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual):
     return y
 
 
+SPLIT_EPILOGUE = int(_os.environ.get('JPB_SPLIT_EPILOGUE', '1'))   # split-K also for convolutions with bias / activation (finishing pass)
 KSPLIT_SLOTS = int(_os.environ.get("JPB_KSPLIT_SLOTS", "296"))
 
 
@@ -181,7 +182,7 @@ def _ksplit(M, N, nkb):
     while nt < N and nt < 256:
         nt *= 2
     tiles = ((M + 127) // 128) * ((N + nt - 1) // nt)
-    if tiles >= 74 or nkb < 16:
+    if tiles >= 74 or nkb < 16 or KSPLIT_SLOTS <= 0:
         return 1
     if KSPLIT_SLOTS <= 148:
         return max(1, min(148 // tiles, nkb // 8, 16))
@@ -403,7 +404,12 @@ class _ConvTC(torch.autograd.Function):
         table, kcol = ordered_table(src_C, kh, kw, dev)
         wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
         nkb = table.shape[0] // 8
-        ks = _ksplit(B * Ho * Wo, N, nkb) if (bias is None and residual is None and act == "none") else 1
+        ks = _ksplit(B * Ho * Wo, N, nkb)
+        has_epi = bias is not None or residual is not None or act != "none"
+        if ks > 1 and has_epi and (N % 4 or not SPLIT_EPILOGUE):
+            ks = 1
+        # split-K layers with an epilogue: the partial tiles are summed without it and one small pass finishes in place
+        finish = ks > 1 and has_epi
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=dev, memory_format=CL)
         if ks > 1:
             out.zero_()
@@ -416,11 +422,12 @@ class _ConvTC(torch.autograd.Function):
         a.table, a.nkb = ptr(table), table.shape[0] // 8
         a.ntaps, a.kw = kh * kw, kw
         a.kcol, a.l1_gather = (ptr(kcol) if kcol is not None else None), int(L1_GATHER and kcol is not None)
-        a.bias = ptr(bias.detach()) if bias is not None else None
         if residual is not None:
             residual = residual if residual.is_contiguous(memory_format=CL) else residual.contiguous(memory_format=CL)
-            a.residual = ptr(residual)
-        a.act = ACT[act]
+        if not finish:
+            a.bias = ptr(bias.detach()) if bias is not None else None
+            a.residual = ptr(residual) if residual is not None else None
+            a.act = ACT[act]
         a.out = ptr(out)
         STATS_FUSED[0] = False
         if cfg.get("bn_stats") and ks == 1 and N % 4 == 0 and N <= 2048:
@@ -432,6 +439,10 @@ class _ConvTC(torch.autograd.Function):
         a.dbg_skip = DBG_SKIP
         tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
         check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd")
+        if finish:
+            check(_launch("conv_bias_act", out, lambda: _lib.lib().jpb_bias_act(
+                ptr(out), ptr(bias.detach()) if bias is not None else None, ptr(residual) if residual is not None else None,
+                B * Ho * Wo, N, ACT[act], stream_of(out))), "jpb_bias_act")
         ctx.cfg = cfg
         ctx.has = (bias is not None, residual is not None)
         ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)

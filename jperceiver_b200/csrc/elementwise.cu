@@ -59,7 +59,37 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* dy, const flo
   }
 }
 
+
+// epilogue of a split-K convolution: the partial tiles were summed into `z` without bias / residual / activation (partial
+// sums cannot run the epilogue); finish in place: z = act(z + bias[c] + residual)
+__global__ void __launch_bounds__(256) bias_act_kernel(float* z, const float* bias, const float* residual, long long n4, int C, int act) {
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n4; i += (long long)gridDim.x * JPB_NT) {
+    const int c = (int)((i * 4) % C);
+    float4 v = *reinterpret_cast<float4*>(z + i * 4);
+    if (bias) { v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3]; }
+    if (residual) { const float4 r = *reinterpret_cast<const float4*>(residual + i * 4); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    float o[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < 4; ++k) {
+      float t = o[k];
+      if (act == 1) t = t > 0.f ? t : 0.f;
+      else if (act == 2) t = t > 0.f ? t : 0.01f * t;
+      else if (act == 3) t = 1.f / (1.f + __expf(-t));
+      o[k] = t;
+    }
+    *reinterpret_cast<float4*>(z + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
+
+extern "C" int jpb_bias_act(float* z, const float* bias, const float* residual, long long rows, int C, int act, void* stream) {
+  if (!z || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;
+  const long long n4 = rows * C / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  JPB_LAUNCH(bias_act_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, z, bias, residual, n4, C, act);
+  return jpb_status();
+}
 
 extern "C" int jpb_act_bwd(const float* dy, const float* y, float* dz, long long rows, int C, int act, float* dbias, void* stream) {
   if (!dy || rows < 1 || C < 1 || (act != 0 && !y) || (!dz && !dbias)) return JPB_ERR_ARG;
