@@ -204,12 +204,26 @@ def run_ours(args):
         v["ms_per_step"] = v["ms_total"] / prof_steps
         v["launches_per_step"] = v["launches"] // prof_steps
 
+    pipelined = [False]
     if args.graph:
         engine.capture(resident, warmup=2)
         step_resident = lambda: engine.replay()
 
+        pipelined[0] = not args.no_prefetch
+
         def step_e2e():
-            out = engine.replay(host)                          # H2D of this step's inputs from pinned memory, then the step
+            # every step: one H2D of a whole batch from pinned memory + the step + a blocking D2H of the loss scalars.  With
+            # prefetch (default) the H2D of the NEXT batch overlaps the step on a side stream (double-buffered staging), as a
+            # prefetching loader would; --no-prefetch copies this step's batch first, then steps.
+            if pipelined[0]:
+                try:
+                    out = engine.replay_pipelined(host)
+                except Exception as e:                         # never lose the e2e number to the optional overlap
+                    sys.stderr.write("bench: input prefetch disabled (%r)\n" % (e,))
+                    pipelined[0] = False
+                    out = engine.replay(host)
+            else:
+                out = engine.replay(host)
             d2h[:out.numel()].copy_(out, non_blocking=False)   # D2H of the step's result (blocks: the loss is read)
     else:
         step_resident = lambda: engine.step(resident, need_log=False)
@@ -253,7 +267,9 @@ def run_ours(args):
                    "frames_per_s": value * (1 + F_src), "operator_backends": dict(netops.BACKEND),
                    "execution": "one CUDA graph per step (captured from the eager step)" if args.graph else "eager"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": synthetic.batch_bytes(host),
-                "d2h_bytes_per_step": 4 * (len(engine.last_names))},
+                "d2h_bytes_per_step": 4 * (len(engine.last_names)),
+                "input_pipeline": ("H2D of the next batch overlapped with the step (double-buffered staging, side stream)"
+                                   if pipelined[0] else "H2D of the step's batch, then the step")},
         "gpu_launches": launches, "clocks": clocks,
         # dominant kernels of the step: the tcgen05 implicit-GEMM convolutions (forward, data gradient, weight gradient)
         "roofline": {"kernel": "conv_tc_fwd / conv_tc_fwd2 / conv_tc_wgrad (tcgen05 kind::tf32, all %d launches of a step)"
@@ -301,6 +317,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-prefetch", action="store_true", help="e2e: copy each step's batch before the step instead of overlapping the next batch's H2D")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
