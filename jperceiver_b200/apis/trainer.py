@@ -284,20 +284,17 @@ class TrainEngine:
 
 
 def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=False, validate=False, logger=None):
-    """Training loop over an iterable of batch dicts (the reference drives mmcv's Runner here; the runner,
-    checkpoint and eval hooks are SURVEY.md §8(f) 'next').  ``dataset_train`` must yield collated batch dicts."""
-    import logging
-    logger = logger or logging.getLogger()
+    """``mono.apis.train_mono`` (trainer.py:58-73, 146-199): build the runner, register the config's hooks, resume / load,
+    run ``cfg.total_epochs``.  ``dataset_train`` must yield collated batch dicts (the datasets and loaders themselves are
+    outside this path's scope); validation hooks are SURVEY.md §8(f)-4."""
+    from .runner import Runner
     dev = torch.device("cuda", torch.cuda.current_device())
     model.to(dev).train()
-    engine = TrainEngine(model, cfg.optimizer, cfg.get("optimizer_config", {}).get("grad_clip"))
-    interval = cfg.get("log_config", {}).get("interval", 50)
-    it = 0
-    for epoch in range(cfg.get("total_epochs", 1)):
-        for batch in dataset_train:
-            out = engine.step(change_input_variable(batch, dev), need_log=(it % interval == 0))
-            if it % interval == 0:
-                vals = out.tolist()
-                logger.info("epoch %d iter %d %s", epoch, it, ", ".join("%s: %.5f" % kv for kv in zip(engine.last_names, vals)))
-            it += 1
-    return engine
+    runner = Runner(model, cfg.optimizer, cfg.get("optimizer_config", {}), cfg.get("work_dir"), cfg.get("log_level", "INFO"), logger)
+    runner.register_training_hooks(cfg.get("lr_config"), cfg.get("optimizer_config"), cfg.get("checkpoint_config"), cfg.get("log_config"))
+    if cfg.get("resume_from"):
+        runner.resume(cfg.resume_from)
+    elif cfg.get("load_from"):
+        runner.load_checkpoint(cfg.load_from)
+    runner.run([dataset_train], cfg.get("workflow", [("train", 1)]), cfg.get("total_epochs", 1))
+    return runner.engine
