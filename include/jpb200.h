@@ -119,7 +119,9 @@ int jpb_scale_loss_bwd(const JpbScaleLossArgs* args, void* stream);
  * all-zero for an empty mask.  Exact (integer squared distances).  work: 2*B*n*n ints.              */
 int jpb_signed_distance(const float* label, int B, int n, int* work, float* sdf, void* stream);
 
-/* ---- BEV head loss: loss_weight*IoU + CE(weight=[1,w_fg]) + loss2_weight*BD (net.py:554-617) ------ */
+/* ---- BEV head loss (net.py:554-617): loss_weight*region + [loss_sum>=2] loss2_weight*BD + [loss_sum==3] CE(weight=[1,w_fg])
+ * region: 0 soft IoU (dice_loss.py:293-331), 1 soft Dice (:255-291), 2 Tversky alpha=.3 beta=.7 (:333-372),
+ *         3 focal alpha=.25 gamma=2 smooth=1e-5 (focal_loss.py:7-92)                                             */
 typedef struct JpbBevArgs {
   const float* logits;      /* element (b,c,y,x) at logits[b*stride_b + (y*occ+x)*stride_p + c*stride_c] */
   long long stride_b, stride_c, stride_p;
@@ -127,7 +129,9 @@ typedef struct JpbBevArgs {
   const float* sdf;         /* [B,occ,occ] */
   int B, occ;
   float w_fg, loss_weight, loss2_weight;
-  double* acc;              /* [4*B + 3], zero-filled by the caller, kept for backward */
+  double* acc;              /* [4*B + 4], zero-filled by the caller, kept for backward */
+  int region;               /* 0 iou, 1 dice, 2 tversky, 3 focal */
+  int loss_sum;             /* 1: region only, 2: + boundary, 3: + boundary + cross entropy (opt.loss_sum) */
 } JpbBevArgs;
 int jpb_bev_loss_fwd(const JpbBevArgs* args, float* out, void* stream);
 int jpb_bev_loss_bwd(const JpbBevArgs* args, const float* grad_out, float* grad_logits, void* stream);

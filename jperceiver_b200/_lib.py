@@ -67,7 +67,7 @@ class BevArgs(C.Structure):
     _fields_ = [
         ("logits", C.c_void_p), ("stride_b", C.c_longlong), ("stride_c", C.c_longlong), ("stride_p", C.c_longlong),
         ("label", C.c_void_p), ("sdf", C.c_void_p), ("B", C.c_int), ("occ", C.c_int), ("w_fg", C.c_float),
-        ("loss_weight", C.c_float), ("loss2_weight", C.c_float), ("acc", C.c_void_p),
+        ("loss_weight", C.c_float), ("loss2_weight", C.c_float), ("acc", C.c_void_p), ("region", C.c_int), ("loss_sum", C.c_int),
     ]
 
 

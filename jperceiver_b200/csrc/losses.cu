@@ -369,7 +369,23 @@ __global__ void __launch_bounds__(256) sdf_rows_kernel(const float* label, int n
 // (boundary_loss.py:137 `if posmask.any()`): gbg == INF everywhere handles it above.
 
 // =============================================================================== BEV head loss
-// acc layout: [b*4 + {A,Bq,Cq,Dq}] per-sample soft confusion sums, then [4B + {ce_num, ce_den, bd}]
+// out = loss_weight * region + [loss_sum >= 2] loss2_weight * BD + [loss_sum == 3] CE     (net.py:554-617)
+// region (a.region): 0 soft IoU, 1 soft Dice, 2 Tversky(alpha=.3, beta=.7) — all of the form
+//   -mean_{b,c} (k*TP + 1) / (k*TP + al*FP + be*FN + 1)   (dice_loss.py:255-372; k = 2 for Dice) —
+// or 3 focal: mean over pixels of -alpha_y (1-pt)^2 log(pt), pt = (1-s) p_y + s p_other + s, s = 1e-5, alpha = (.25, .75)
+// (focal_loss.py:7-92).
+// acc layout: [b*4 + {A,Bq,Cq,Dq}] per-sample soft confusion sums (A = sum p0[y=0], Bq = sum p0[y=1], Cq = sum p1[y=0],
+// Dq = sum p1[y=1]), then [4B + {ce_num, ce_den, bd, focal}]
+struct RegionCoef { double k, al, be; };
+__device__ __forceinline__ RegionCoef region_coef(int region) {
+  RegionCoef r;
+  r.k = region == 1 ? 2.0 : 1.0;
+  r.al = region == 2 ? 0.3 : 1.0;
+  r.be = region == 2 ? 0.7 : 1.0;
+  return r;
+}
+constexpr float FOCAL_S = 1e-5f;
+
 __global__ void __launch_bounds__(256) bev_fwd_kernel(JpbBevArgs a) {
   __shared__ double red[32];
   const int b = blockIdx.y, n2 = a.occ * a.occ;
@@ -377,7 +393,7 @@ __global__ void __launch_bounds__(256) bev_fwd_kernel(JpbBevArgs a) {
   const float* lab = a.label + (size_t)b * n2;
   const float* phi = a.sdf + (size_t)b * n2;
   float A = 0.f, Bq = 0.f, Cq = 0.f, Dq = 0.f;
-  double cen = 0.0, ced = 0.0, bd = 0.0;
+  double cen = 0.0, ced = 0.0, bd = 0.0, foc = 0.0;
   for (int e = blockIdx.x * JPB_NT + JPB_TID; e < n2; e += gridDim.x * JPB_NT) {
     const float u = l0[(size_t)e * a.stride_p], v = l0[(size_t)e * a.stride_p + a.stride_c];
     const float m = fmaxf(u, v);
@@ -391,25 +407,37 @@ __global__ void __launch_bounds__(256) bev_fwd_kernel(JpbBevArgs a) {
     cen += (double)(wy * nll);
     ced += (double)wy;
     bd += (double)(p1 * phi[e]);
+    if (a.region == 3) {
+      const float pt = (1.f - FOCAL_S) * (fg ? p1 : p0) + FOCAL_S * (fg ? p0 : p1) + FOCAL_S;
+      const float om = 1.f - pt;
+      foc += (double)(-(fg ? 0.75f : 0.25f) * om * om * logf(pt));
+    }
   }
-  const double vals[7] = {(double)A, (double)Bq, (double)Cq, (double)Dq, cen, ced, bd};
-  for (int k = 0; k < 7; ++k) {
+  const double vals[8] = {(double)A, (double)Bq, (double)Cq, (double)Dq, cen, ced, bd, foc};
+  for (int k = 0; k < 8; ++k) {
     const double t = jpb_block_sum<double>(vals[k], red);
     if (JPB_TID == 0) atomicAdd(k < 4 ? &a.acc[b * 4 + k] : &a.acc[4 * a.B + (k - 4)], t);
   }
 }
 
-__global__ void bev_finalize_kernel(const double* acc, int B, int occ, float lw, float l2w, float* out) {
+__global__ void bev_finalize_kernel(const double* acc, int B, int occ, float lw, float l2w, int region, int loss_sum, float* out) {
   if (blockIdx.x != 0 || JPB_TID != 0) return;
-  double iou = 0.0;
-  for (int b = 0; b < B; ++b) {
-    const double A = acc[b * 4], Bq = acc[b * 4 + 1], Cq = acc[b * 4 + 2], Dq = acc[b * 4 + 3];
-    iou += (A + 1.0) / (A + Bq + Cq + 1.0) + (Dq + 1.0) / (Dq + Cq + Bq + 1.0);
+  double reg = 0.0;
+  if (region == 3) {
+    reg = acc[4 * B + 3] / ((double)B * occ * occ);
+  } else {
+    const RegionCoef rc = region_coef(region);
+    for (int b = 0; b < B; ++b) {
+      const double A = acc[b * 4], Bq = acc[b * 4 + 1], Cq = acc[b * 4 + 2], Dq = acc[b * 4 + 3];
+      // class 0: TP = A, FP = Bq, FN = Cq;  class 1: TP = Dq, FP = Cq, FN = Bq
+      reg += (rc.k * A + 1.0) / (rc.k * A + rc.al * Bq + rc.be * Cq + 1.0) + (rc.k * Dq + 1.0) / (rc.k * Dq + rc.al * Cq + rc.be * Bq + 1.0);
+    }
+    reg = -reg / (2.0 * B);
   }
-  iou = -iou / (2.0 * B);
-  const double ce = acc[4 * B] / acc[4 * B + 1];
-  const double bd = acc[4 * B + 2] / ((double)B * occ * occ);
-  out[0] = (float)((double)lw * iou + ce + (double)l2w * bd);
+  double v = (double)lw * reg;
+  if (loss_sum >= 2) v += (double)l2w * acc[4 * B + 2] / ((double)B * occ * occ);
+  if (loss_sum == 3) v += acc[4 * B] / acc[4 * B + 1];
+  out[0] = (float)v;
 }
 
 __global__ void __launch_bounds__(256) bev_bwd_kernel(JpbBevArgs a, const float* gout, float* glogits) {
@@ -418,15 +446,23 @@ __global__ void __launch_bounds__(256) bev_bwd_kernel(JpbBevArgs a, const float*
   float* gl = glogits + (size_t)b * a.stride_b;
   const float* lab = a.label + (size_t)b * n2;
   const float* phi = a.sdf + (size_t)b * n2;
-  const double A = a.acc[b * 4], Bq = a.acc[b * 4 + 1], Cq = a.acc[b * 4 + 2], Dq = a.acc[b * 4 + 3];
-  const double U0 = A + Bq + Cq + 1.0, U1 = Dq + Cq + Bq + 1.0;
   const float g = gout[0];
-  const double k = -(double)a.loss_weight / (2.0 * a.B) * g;
-  const float cA = (float)(k * (Bq + Cq) / (U0 * U0));
-  const float cBC = (float)(k * (-(A + 1.0) / (U0 * U0) - (Dq + 1.0) / (U1 * U1)));
-  const float cD = (float)(k * (Cq + Bq) / (U1 * U1));
-  const float cew = g / (float)a.acc[4 * a.B + 1];
-  const float bdk = g * a.loss2_weight / ((float)a.B * (float)n2);
+  // d loss / d{A, Bq, Cq, Dq} of the ratio-type region terms
+  float cA = 0.f, cB = 0.f, cC = 0.f, cD = 0.f;
+  if (a.region != 3) {
+    const RegionCoef rc = region_coef(a.region);
+    const double A = a.acc[b * 4], Bq = a.acc[b * 4 + 1], Cq = a.acc[b * 4 + 2], Dq = a.acc[b * 4 + 3];
+    const double U0 = rc.k * A + rc.al * Bq + rc.be * Cq + 1.0, U1 = rc.k * Dq + rc.al * Cq + rc.be * Bq + 1.0;
+    const double N0 = rc.k * A + 1.0, N1 = rc.k * Dq + 1.0;
+    const double k = -(double)a.loss_weight / (2.0 * a.B) * g;
+    cA = (float)(k * rc.k * (rc.al * Bq + rc.be * Cq) / (U0 * U0));
+    cD = (float)(k * rc.k * (rc.al * Cq + rc.be * Bq) / (U1 * U1));
+    cB = (float)(k * (-rc.al * N0 / (U0 * U0) - rc.be * N1 / (U1 * U1)));
+    cC = (float)(k * (-rc.be * N0 / (U0 * U0) - rc.al * N1 / (U1 * U1)));
+  }
+  const float cew = a.loss_sum == 3 ? g / (float)a.acc[4 * a.B + 1] : 0.f;
+  const float bdk = a.loss_sum >= 2 ? g * a.loss2_weight / ((float)a.B * (float)n2) : 0.f;
+  const float fok = g * a.loss_weight / ((float)a.B * (float)n2);
   for (int e = blockIdx.x * JPB_NT + JPB_TID; e < n2; e += gridDim.x * JPB_NT) {
     const float u = l0[(size_t)e * a.stride_p], v = l0[(size_t)e * a.stride_p + a.stride_c];
     const float m = fmaxf(u, v);
@@ -435,8 +471,16 @@ __global__ void __launch_bounds__(256) bev_bwd_kernel(JpbBevArgs a, const float*
     const float p0 = eu / den, p1 = ev / den;
     const bool fg = lab[e] > 0.5f;
     // d loss / d p_c
-    const float g0 = fg ? cBC : cA;
-    const float g1 = (fg ? cD : cBC) + bdk * phi[e];
+    float g0 = fg ? cB : cA;
+    float g1 = (fg ? cD : cC) + bdk * phi[e];
+    if (a.region == 3) {
+      const float pt = (1.f - FOCAL_S) * (fg ? p1 : p0) + FOCAL_S * (fg ? p0 : p1) + FOCAL_S;
+      const float om = 1.f - pt;
+      // d/dpt [-al (1-pt)^2 log pt] = al (2 (1-pt) log pt - (1-pt)^2 / pt)
+      const float dpt = fok * (fg ? 0.75f : 0.25f) * (2.f * om * logf(pt) - om * om / pt);
+      g0 += dpt * (fg ? FOCAL_S : 1.f - FOCAL_S);
+      g1 += dpt * (fg ? 1.f - FOCAL_S : FOCAL_S);
+    }
     const float dot = g0 * p0 + g1 * p1;
     const float wy = fg ? a.w_fg : 1.f;
     gl[(size_t)e * a.stride_p] = p0 * (g0 - dot) + cew * wy * (p0 - (fg ? 0.f : 1.f));
@@ -527,7 +571,7 @@ extern "C" int jpb_bev_loss_fwd(const JpbBevArgs* a, float* out, void* stream) {
   if (!a || !a->logits || !a->label || !a->sdf || !a->acc || !out) return JPB_ERR_ARG;
   dim3 grid(grid_for((long long)a->occ * a->occ, 256, 64), a->B);
   JPB_LAUNCH(bev_fwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *a);
-  JPB_LAUNCH(bev_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, a->acc, a->B, a->occ, a->loss_weight, a->loss2_weight, out);
+  JPB_LAUNCH(bev_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, a->acc, a->B, a->occ, a->loss_weight, a->loss2_weight, a->region, a->loss_sum, out);
   return jpb_status();
 }
 

@@ -272,23 +272,23 @@ def signed_distance(label):
 
 class _BevLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, label, sdf, w_fg, lw, l2w):
+    def forward(ctx, logits, label, sdf, w_fg, lw, l2w, region=0, loss_sum=3):
         if logits.dtype != torch.float32:
             logits = logits.float()
         if not (logits.is_contiguous() or logits.is_contiguous(memory_format=torch.channels_last)):
             logits = logits.contiguous()
         label = _f32c(label)
         B, _, occ, _ = logits.shape
-        acc = torch.zeros(4 * B + 3, dtype=torch.float64, device=logits.device)
+        acc = torch.zeros(4 * B + 4, dtype=torch.float64, device=logits.device)
         out = torch.empty((), dtype=torch.float32, device=logits.device)
-        a = _BevLoss._args(logits, label, sdf, acc, w_fg, lw, l2w)
+        a = _BevLoss._args(logits, label, sdf, acc, w_fg, lw, l2w, region, loss_sum)
         check(_lib.lib().jpb_bev_loss_fwd(C.byref(a), ptr(out), stream_of(logits)), "jpb_bev_loss_fwd")
         ctx.save_for_backward(logits, label, sdf, acc)
-        ctx.args = (w_fg, lw, l2w)
+        ctx.args = (w_fg, lw, l2w, region, loss_sum)
         return out
 
     @staticmethod
-    def _args(logits, label, sdf, acc, w_fg, lw, l2w):
+    def _args(logits, label, sdf, acc, w_fg, lw, l2w, region=0, loss_sum=3):
         a = _lib.BevArgs()
         sb, sc, sy, sx = logits.stride()
         assert sy == logits.shape[3] * sx, "logits rows must be dense"
@@ -296,6 +296,7 @@ class _BevLoss(torch.autograd.Function):
         a.label, a.sdf, a.acc = ptr(label), ptr(sdf), ptr(acc)
         a.B, a.occ = logits.shape[0], logits.shape[2]
         a.w_fg, a.loss_weight, a.loss2_weight = float(w_fg), float(lw), float(l2w)
+        a.region, a.loss_sum = int(region), int(loss_sum)
         return a
 
     @staticmethod
@@ -304,12 +305,20 @@ class _BevLoss(torch.autograd.Function):
         a = _BevLoss._args(logits, label, sdf, acc, *ctx.args)
         gl = torch.empty_like(logits)  # preserves the (dense) strides
         check(_lib.lib().jpb_bev_loss_bwd(C.byref(a), ptr(_f32c(g).reshape(1)), ptr(gl), stream_of(logits)), "jpb_bev_loss_bwd")
-        return gl, None, None, None, None, None
+        return gl, None, None, None, None, None, None, None
 
 
-def bev_head_loss(logits, label, sdf, w_fg, loss_weight=20.0, loss2_weight=20.0):
-    """``compute_topview_loss`` for loss_type='iou', loss2_type='boundary', loss_sum=3."""
-    return _BevLoss.apply(logits, label, sdf, w_fg, loss_weight, loss2_weight)
+BEV_REGION = {"iou": 0, "dice": 1, "tversky": 2, "focal": 3}
+
+
+def bev_head_loss(logits, label, sdf, w_fg, loss_weight=20.0, loss2_weight=20.0, loss_type="iou", loss_sum=3):
+    """``compute_topview_loss`` (net.py:554-617): ``loss_type`` in {iou, dice, tversky, focal}; ``loss_sum`` 1 = region term
+    only, 2 = + boundary loss, 3 = + boundary loss + weighted cross entropy (``loss2_type`` is 'boundary' in every config)."""
+    if loss_type not in BEV_REGION:
+        raise NotImplementedError("loss_type %r (the reference defines iou, dice, focal, tversky)" % (loss_type,))
+    if loss_sum not in (1, 2, 3):
+        raise NotImplementedError("loss_sum %r (the reference defines 1, 2, 3)" % (loss_sum,))
+    return _BevLoss.apply(logits, label, sdf, w_fg, loss_weight, loss2_weight, BEV_REGION[loss_type], loss_sum)
 
 
 class _L1Mean(torch.autograd.Function):

@@ -205,23 +205,21 @@ class Baseline(nn.Module):
         L = {}
         lw, l2w = o.loss_weight, o.loss2_weight
         lwS, l2wS = o.get("loss_weightS", lw), o.get("loss2_weightS", l2w)
-        if o.get("loss_type", "iou") != "iou" or o.get("loss2_type", "boundary") != "boundary" or o.get("loss_sum", 3) != 3:
-            if typ != "static_eigen":
-                raise NotImplementedError("BEV loss variant (%s, %s, loss_sum=%s) is not implemented yet; the B200 path covers "
-                                          "iou + CE + boundary (loss_sum=3), which all five target configs use"
-                                          % (o.get("loss_type"), o.get("loss2_type"), o.get("loss_sum")))
+        if o.get("loss2_type", "boundary") != "boundary" and typ != "static_eigen":
+            raise NotImplementedError("loss2_type %r: the reference only defines 'boundary' (net.py:574-575)" % (o.get("loss2_type"),))
+        bev = dict(loss_type=o.get("loss_type", "iou"), loss_sum=o.get("loss_sum", 3))
         if typ in ROAD_TYPES:
             y = inputs[("bothS", 0, 0)]
             sdf = JF.signed_distance(y.reshape(y.shape[0], y.shape[-2], y.shape[-1]))
-            L["topview_loss"] = JF.bev_head_loss(outputs["topview"], y, sdf, o.static_weight, lwS, l2wS)
-            L["transform_topview_loss"] = JF.bev_head_loss(outputs["transform_topview"], y, sdf, o.static_weight, lwS, l2wS)
+            L["topview_loss"] = JF.bev_head_loss(outputs["topview"], y, sdf, o.static_weight, lwS, l2wS, **bev)
+            L["transform_topview_loss"] = JF.bev_head_loss(outputs["transform_topview"], y, sdf, o.static_weight, lwS, l2wS, **bev)
             L["transform_loss"] = JF.l1_mean(outputs["features"], outputs["retransform_features"])
             L["layout_loss"] = L["topview_loss"] + 0.001 * L["transform_loss"] + L["transform_topview_loss"]
         if typ in CAR_TYPES:
             y = inputs[("bothD", 0, 0)]
             sdf = JF.signed_distance(y.reshape(y.shape[0], y.shape[-2], y.shape[-1]))
-            L["topview_lossB"] = JF.bev_head_loss(outputs["topviewB"], y, sdf, o.dynamic_weight, lw, l2w)
-            L["transform_topview_lossB"] = JF.bev_head_loss(outputs["transform_topviewB"], y, sdf, o.dynamic_weight, lw, l2w)
+            L["topview_lossB"] = JF.bev_head_loss(outputs["topviewB"], y, sdf, o.dynamic_weight, lw, l2w, **bev)
+            L["transform_topview_lossB"] = JF.bev_head_loss(outputs["transform_topviewB"], y, sdf, o.dynamic_weight, lw, l2w, **bev)
             L["transform_lossB"] = JF.l1_mean(outputs["featuresB"], outputs["retransform_featuresB"])
             L["layout_lossB"] = L["topview_lossB"] + 0.001 * L["transform_lossB"] + L["transform_topview_lossB"]
         label = None

@@ -465,20 +465,40 @@ def signed_distance(mask_np):
     return sdf
 
 
-def bev_head_loss(logits, label, w_fg, loss_weight=20.0, loss2_weight=20.0):
-    """loss_type='iou', loss2_type='boundary', loss_sum=3: ``lw·IoU + CE + l2w·BD``."""
+def bev_head_loss(logits, label, w_fg, loss_weight=20.0, loss2_weight=20.0, loss_type="iou", loss_sum=3):
+    """``compute_topview_loss`` (M/net.py:554-617): region term selected by ``loss_type`` — soft IoU (M/dice_loss.py:293-331),
+    soft Dice (:255-291), Tversky alpha=.3 beta=.7 (:333-372), focal alpha=.25 gamma=2 smooth=1e-5 (M/focal_loss.py:7-92) —
+    times ``loss_weight``; ``loss_sum`` 2 adds ``loss2_weight`` x boundary loss, 3 adds the weighted cross entropy as well."""
     B = logits.shape[0]
     y = label.reshape(B, logits.shape[2], logits.shape[3]).long()
     p = F.softmax(logits, 1)
     oh = F.one_hot(y, 2).permute(0, 3, 1, 2).to(p.dtype)
-    tp = (p * oh).sum((2, 3))
-    fp = (p * (1 - oh)).sum((2, 3))
-    fn = ((1 - p) * oh).sum((2, 3))
-    iou = -((tp + 1) / (tp + fp + fn + 1)).mean()
-    ce = F.cross_entropy(logits, y, weight=torch.tensor([1.0, float(w_fg)]))
+    if loss_type == "focal":
+        s = 1e-5
+        key = torch.clamp(oh, s / (2 - 1), 1.0 - s)
+        pt = (key * p).sum(1) + s
+        alpha = torch.where(y == 0, torch.tensor(0.25), torch.tensor(0.75)).to(p.dtype)
+        region = (-alpha * (1 - pt) ** 2 * pt.log()).mean()
+    else:
+        tp = (p * oh).sum((2, 3))
+        fp = (p * (1 - oh)).sum((2, 3))
+        fn = ((1 - p) * oh).sum((2, 3))
+        if loss_type == "iou":
+            region = -((tp + 1) / (tp + fp + fn + 1)).mean()
+        elif loss_type == "dice":
+            region = -((2 * tp + 1) / (2 * tp + fp + fn + 1)).mean()
+        elif loss_type == "tversky":
+            region = -((tp + 1) / (tp + 0.3 * fp + 0.7 * fn + 1)).mean()
+        else:
+            raise ValueError(loss_type)
+    if loss_sum == 1:
+        return loss_weight * region
     phi = torch.from_numpy(np.stack([signed_distance(m) for m in y.numpy()])).to(torch.float32)
     bd = (p[:, 1] * phi).mean()
-    return loss_weight * iou + ce + loss2_weight * bd
+    if loss_sum == 2:
+        return loss_weight * region + loss2_weight * bd
+    ce = F.cross_entropy(logits, y, weight=torch.tensor([1.0, float(w_fg)]))
+    return loss_weight * region + ce + loss2_weight * bd      # the reference's order of the three terms (net.py:583-585)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -494,16 +514,17 @@ def compute_losses(opt, inputs, outputs, noise=None, warp_align_corners=True):
     L = {}
     lw, l2w = opt["loss_weight"], opt["loss2_weight"]
     lwS, l2wS = _get(opt, "loss_weightS", lw), _get(opt, "loss2_weightS", l2w)
+    bev_kw = dict(loss_type=_get(opt, "loss_type", "iou"), loss_sum=_get(opt, "loss_sum", 3))
     if typ in ROAD_TYPES:
         y = inputs[("bothS", 0, 0)]
-        L["topview_loss"] = bev_head_loss(outputs["topview"], y, opt["static_weight"], lwS, l2wS)
-        L["transform_topview_loss"] = bev_head_loss(outputs["transform_topview"], y, opt["static_weight"], lwS, l2wS)
+        L["topview_loss"] = bev_head_loss(outputs["topview"], y, opt["static_weight"], lwS, l2wS, **bev_kw)
+        L["transform_topview_loss"] = bev_head_loss(outputs["transform_topview"], y, opt["static_weight"], lwS, l2wS, **bev_kw)
         L["transform_loss"] = (outputs["features"] - outputs["retransform_features"]).abs().mean()
         L["layout_loss"] = L["topview_loss"] + 0.001 * L["transform_loss"] + L["transform_topview_loss"]
     if typ in CAR_TYPES:
         y = inputs[("bothD", 0, 0)]
-        L["topview_lossB"] = bev_head_loss(outputs["topviewB"], y, opt["dynamic_weight"], lw, l2w)
-        L["transform_topview_lossB"] = bev_head_loss(outputs["transform_topviewB"], y, opt["dynamic_weight"], lw, l2w)
+        L["topview_lossB"] = bev_head_loss(outputs["topviewB"], y, opt["dynamic_weight"], lw, l2w, **bev_kw)
+        L["transform_topview_lossB"] = bev_head_loss(outputs["transform_topviewB"], y, opt["dynamic_weight"], lw, l2w, **bev_kw)
         L["transform_lossB"] = (outputs["featuresB"] - outputs["retransform_featuresB"]).abs().mean()
         L["layout_lossB"] = L["topview_lossB"] + 0.001 * L["transform_lossB"] + L["transform_topview_lossB"]
     label = None

@@ -346,3 +346,27 @@ def test_batchnorm_train_forward_backward_vs_torch(dev, C, H, W, relu, has_res):
     rev = rev + res if has_res else rev
     rev = torch.relu(rev) if relu else rev
     assert (ev.cpu() - rev).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("loss_type", ["iou", "dice", "tversky", "focal"])
+@pytest.mark.parametrize("loss_sum", [1, 2, 3])
+def test_bev_loss_variants_vs_oracle_and_reference(dev, loss_type, loss_sum):
+    """the region-loss variants of compute_topview_loss.  Values against the vectors produced by the
+    reference's own code (tests/golden/kat_bev_variants.npz), gradients against the oracle's autograd."""
+    gold = np.load(os.path.join(GOLDEN, "kat_bev_variants.npz"))
+    big = torch.cat([4 * pat((2, 1, 256, 256), 9) - 2, 4 * pat((2, 1, 256, 256), 10) - 2], 1)
+    lab = torch.zeros(2, 1, 256, 256)
+    lab[:, :, 64:176, 48:144] = 1
+    lab[1, :, 200:240, 10:250] = 1
+    sdf = JF.signed_distance(D(lab.reshape(2, 256, 256), dev))
+    for w in (5, 15):
+        key = "%s_s%d_w%d" % (loss_type, loss_sum, w)
+        x0 = big.clone().requires_grad_(True)
+        ref = O.bev_head_loss(x0, lab, float(w), 20.0, 20.0, loss_type=loss_type, loss_sum=loss_sum)
+        (g0,) = torch.autograd.grad(ref, x0)
+        x1 = D(big, dev).requires_grad_(True)
+        got = JF.bev_head_loss(x1, D(lab, dev), sdf, float(w), 20.0, 20.0, loss_type=loss_type, loss_sum=loss_sum)
+        assert abs(got.item() - float(gold[key])) <= 3e-6 * max(abs(float(gold[key])), 1.0), key
+        (g1,) = torch.autograd.grad(got, x1)
+        assert (g1.cpu() - g0).abs().max().item() <= 2e-5 * g0.abs().max().item() + 1e-10, key
+        assert abs(g1.abs().sum().item() - float(gold[key + "_gsum"])) <= 1e-4 * float(gold[key + "_gsum"]), key

@@ -98,3 +98,22 @@ def test_kat8_transform_loss(kat):
 
 def test_empty_foreground_sdf_is_zero():
     assert not O.signed_distance(np.zeros((8, 8), dtype=np.uint8)).any()
+
+
+@pytest.mark.parametrize("loss_type", ["iou", "dice", "tversky", "focal"])
+@pytest.mark.parametrize("loss_sum", [1, 2, 3])
+def test_bev_loss_variants_match_reference(loss_type, loss_sum):
+    """every region-loss variant x loss_sum of compute_topview_loss against values produced by the
+    reference's own code (oracle/make_golden_bev.py), value and input-gradient checksum."""
+    gold = np.load(os.path.join(GOLDEN, "kat_bev_variants.npz"))
+    big = torch.cat([4 * pat((2, 1, 256, 256), 9) - 2, 4 * pat((2, 1, 256, 256), 10) - 2], 1)
+    lab = torch.zeros(2, 1, 256, 256)
+    lab[:, :, 64:176, 48:144] = 1
+    lab[1, :, 200:240, 10:250] = 1
+    for w in (5, 15):
+        x = big.clone().requires_grad_(True)
+        v = O.bev_head_loss(x, lab, float(w), 20.0, 20.0, loss_type=loss_type, loss_sum=loss_sum)
+        (g,) = torch.autograd.grad(v, x)
+        key = "%s_s%d_w%d" % (loss_type, loss_sum, w)
+        assert abs(v.item() - float(gold[key])) <= 2e-6 * max(abs(float(gold[key])), 1.0), key
+        assert abs(g.abs().sum().item() - float(gold[key + "_gsum"])) <= 1e-4 * float(gold[key + "_gsum"]), key
