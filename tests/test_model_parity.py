@@ -173,3 +173,33 @@ def test_full_size_gpu(typ):
         run_case(torch.device("cuda:0"), typ, 320, 1024, 256, 2, hw, rel=1e-3)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, netops.BACKEND["conv2d"] = old
+
+
+def test_eval_mode_outputs_match_oracle(dev):
+    """Inference path (SURVEY.md §8(f)-4, ``model.eval()``): BatchNorm running statistics, no dropout, no pose / loss branch;
+    ``Baseline.forward`` returns the outputs dict only (net.py:77-82).  Host emulation (fp32 library convolutions): tight."""
+    if dev.type == "cuda":
+        pytest.skip("training-mode parity covers the GPU kernels at full size; the eval-only kernel (BatchNorm with running "
+                    "statistics) is checked under emulation")
+    torch.set_num_threads(os.cpu_count() or 1)
+    opt = default_options(type="Argo_both", split="argo", height=256, width=256, occ_map_size=64, frame_ids=[0, -1, 1], imgs_per_gpu=2)
+    model = MONO.module_dict["Baseline"](opt)
+    P = O.synth_params(model.state_dict(), seed=6)
+    model.load_state_dict(P)
+    model.to(dev).eval()
+    inp = O.synth_inputs(opt, 2, seed=4, hw_full=(120, 400))
+    with torch.no_grad():
+        ref = O.forward({k: v.clone() for k, v in P.items()}, opt, {k: v.clone() for k, v in inp.items()}, training=False)
+        got = model({k: v.to(dev) for k, v in inp.items()})
+    assert isinstance(got, dict)
+    for k in ref:
+        if not torch.is_tensor(ref[k]):
+            continue
+        a, b = got[k].detach().cpu(), ref[k].detach()
+        assert a.shape == b.shape, k
+        assert (a - b).abs().max().item() <= 1e-3 * max(b.abs().max().item(), 1e-6), k
+    assert ("cam_T_cam", 0, -1) not in got
+    sd = model.state_dict()
+    for k in sd:                                   # evaluation must not touch the running statistics
+        if "running" in k or "tracked" in k:
+            assert torch.equal(sd[k].cpu(), P[k]), k
