@@ -60,6 +60,9 @@ typedef struct JpbPhotoGrad {
 } JpbPhotoGrad;
 
 int jpb_photometric_fwd(const JpbPhotoArgs* args, void* stream);
+/* Forward schedule: 2 = one value per instruction (default, the measured one); 3 = the two source frames of a snippet packed
+ * into FADD2/FMUL2/FFMA2 pairs (same results within fp32 rounding).  Process-wide; not thread-safe against running launches. */
+int jpb_photometric_set_variant(int fwd_variant);
 int jpb_photometric_bwd(const JpbPhotoArgs* args, const JpbPhotoGrad* grad, void* stream);
 
 /* ---- area-downsampled target pyramid -----------------------------------------------------------

@@ -128,6 +128,7 @@ class _Signatures:
     P, I, F, V = C.c_void_p, C.c_int, C.c_float, C.c_void_p
     jpb_photometric_fwd = [C.POINTER(PhotoArgs), V]
     jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
+    jpb_photometric_set_variant = [I]
     jpb_finalize = [P, P, F, P, I, V]
     jpb_weight_flipT = [P, I, I, V]
     jpb_cct_select_fwd = [P] * 10 + [I, I, I, I, V]
@@ -179,6 +180,9 @@ def lib():
                            "jperceiver_b200 has no CPU fallback" % LIB_PATH)
         _handle = C.CDLL(LIB_PATH)
         _declare(_handle)
+        v = os.environ.get("JPB_PHOTO_FWD")      # opt-in forward schedule of the photometric kernel (2 default, 3 packed)
+        if v:
+            check(_handle.jpb_photometric_set_variant(int(v)), "jpb_photometric_set_variant(JPB_PHOTO_FWD=%s)" % v)
     return _handle
 
 

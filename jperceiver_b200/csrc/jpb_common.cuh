@@ -24,6 +24,8 @@ static jpb_dim3 threadIdx(0, 0, 0), blockIdx(0, 0, 0), blockDim(1, 1, 1), gridDi
 typedef void* cudaStream_t;
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 v = {x, y}; return v; }
 #define __global__
 #define __device__
 #define __host__
@@ -111,6 +113,21 @@ __device__ __forceinline__ int jpb_reflect(int i, int n) {  // ReflectionPad ind
   return i;
 }
 __device__ __forceinline__ int jpb_clampi(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
+
+// ------------------------------------------------------------------ packed fp32 pairs
+// sm_100 issues two fp32 operations per lane with one FADD2 / FMUL2 / FFMA2 instruction (operands in aligned 64-bit
+// register pairs).  Kernels that are bound by the FMA pipe process two independent values (the two source frames of a
+// snippet) per instruction through these wrappers; the host emulation evaluates the two lanes one after the other.
+#ifdef JPB_HOST_EMU
+static inline float2 jpb_add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 jpb_mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 jpb_fma2(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#else
+__device__ __forceinline__ float2 jpb_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 jpb_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 jpb_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+__device__ __forceinline__ float2 jpb_dup2(float v) { return make_float2(v, v); }
 
 // ------------------------------------------------------------------ Philox4x32-10 counter RNG
 struct JpbPhilox {

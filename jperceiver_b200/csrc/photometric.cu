@@ -425,6 +425,256 @@ __global__ void __launch_bounds__(256, 3) photometric_fwd_kernel(JpbPhotoArgs a)
 }
 #undef JPB_STRIP_CANDIDATE
 
+// ------------------------------------------------------------------------------------ forward, packed variant (F <= 2)
+// Same tile (32x32 + 1-pixel apron) and the same two phases as photometric_fwd_kernel, re-organised around what the ncu
+// capture of that kernel showed (profiles/README.md: 1800 thread instructions per pixel, FMA pipe and gather latency bound):
+//  * phase 1 issues every load of a staged pixel unconditionally (taps clamped instead of predicated: a clamped tap always
+//    carries weight 0 because the sampling coordinate was clipped first), uses 32-bit offsets, one MUFU.RCP for the
+//    perspective divide and a folded pixel->grid->pixel scale (ix = u*W/(W-1) - 0.5), and stages the identity sources too;
+//  * shared memory holds the two source frames of a candidate kind interleaved as float2 (f0, f1), and phase 2 evaluates both
+//    frames with one packed FADD2 / FMUL2 / FFMA2 per operation (jpb_*2 wrappers): half the FMA-pipe issue slots;
+//  * phase 2 streams down the strip once per channel with all window sums in registers (no local arrays).
+namespace v3 {
+constexpr int TW = 32, TH = 32, SR = 4;                 // tile and strip height
+constexpr int AW = TW + 2, AH = TH + 2, AN = AW * AH;   // tile + apron
+
+// MUFU.RCP / MUFU.SQRT without the denormal pre-scaling of div.approx / sqrt.approx (arguments here are >= 1e-8)
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef JPB_HOST_EMU
+  return 1.f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+__device__ __forceinline__ float fast_sqrt_ftz(float x) {
+#ifdef JPB_HOST_EMU
+  return sqrtf(x);
+#else
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+// keep a per-sample base pointer in a 64-bit register pair so that every access is one IMAD.WIDE + load
+#ifdef JPB_HOST_EMU
+#define JPB_PIN_PTR(p) ((void)0)
+#else
+#define JPB_PIN_PTR(p) asm volatile("" : "+l"(p))
+#endif
+
+// warped sample of one staged pixel for one source frame: Project (layers.py:73-82) + grid_sample(bilinear, border);
+// c0/c1/c2 are the three colour planes of the source frame
+__device__ __forceinline__ void warp3(const SrcGeom& g, float X0, float X1, float X2, const float* c0, const float* c1, const float* c2,
+                                      int H, int W, float cw, float ch, float v[3]) {
+  const float p0 = g.P[0] * X0 + g.P[1] * X1 + g.P[2] * X2 + g.P[3];
+  const float p1 = g.P[4] * X0 + g.P[5] * X1 + g.P[6] * X2 + g.P[7];
+  const float p2 = g.P[8] * X0 + g.P[9] * X1 + g.P[10] * X2 + g.P[11];
+  const float inv = fast_rcp(p2 + 1e-7f);
+  float ix = (p0 * inv) * cw - 0.5f, iy = (p1 * inv) * ch - 0.5f;
+  // clip_coordinates, NaN-safe order as ATen (min(max(x, 0), size-1))
+  if (!(ix > 0.f)) ix = 0.f;
+  if (ix > (float)(W - 1)) ix = (float)(W - 1);
+  if (!(iy > 0.f)) iy = 0.f;
+  if (iy > (float)(H - 1)) iy = (float)(H - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int xa = (int)fx0, ya = (int)fy0;
+  const float tx = ix - fx0, ty = iy - fy0;
+  const int xb = min(xa + 1, W - 1), yb = min(ya + 1, H - 1);   // clamped taps have tx (ty) == 0
+  const int o00 = ya * W + xa, o01 = ya * W + xb, o10 = yb * W + xa, o11 = yb * W + xb;
+  const float wnw = (1.f - tx) * (1.f - ty), wne = tx * (1.f - ty), wsw = (1.f - tx) * ty, wse = tx * ty;
+  const float a0 = __ldg(c0 + o00), a1 = __ldg(c0 + o01), a2 = __ldg(c0 + o10), a3 = __ldg(c0 + o11);
+  const float b0 = __ldg(c1 + o00), b1 = __ldg(c1 + o01), b2 = __ldg(c1 + o10), b3 = __ldg(c1 + o11);
+  const float d0 = __ldg(c2 + o00), d1 = __ldg(c2 + o01), d2 = __ldg(c2 + o10), d3 = __ldg(c2 + o11);
+  v[0] = ((a0 * wnw + a1 * wne) + a2 * wsw) + a3 * wse;
+  v[1] = ((b0 * wnw + b1 * wne) + b2 * wsw) + b3 * wse;
+  v[2] = ((d0 * wnw + d1 * wne) + d2 * wsw) + d3 * wse;
+}
+
+struct PairState {   // horizontal 3-sums of the previous two rows (x, x^2, x*y) and the previous centre value, two frames each
+  float2 h1a, h1b, h2a, h2b, h3a, h3b, xbp;
+};
+struct TargetOut {   // per output row, broadcast to both lanes
+  float2 MY, TWO_MY, CY1, CY2, YBP;
+};
+
+__device__ __forceinline__ void pair_row(PairState& S, const float2 xa, const float2 xb, const float2 xc, const float2 Ya, const float2 Yb,
+                                         const float2 Yc, const bool emit, const TargetOut& t, float2& err) {
+  const float2 h1 = jpb_add2(jpb_add2(xa, xb), xc);
+  const float2 h2 = jpb_fma2(xc, xc, jpb_fma2(xb, xb, jpb_mul2(xa, xa)));
+  const float2 h3 = jpb_fma2(xc, Yc, jpb_fma2(xb, Yb, jpb_mul2(xa, Ya)));
+  if (emit) {
+    const float2 NINTH = jpb_dup2(1.f / 9.f), NNINTH = jpb_dup2(-1.f / 9.f);
+    const float2 s1 = jpb_add2(jpb_add2(S.h1a, S.h1b), h1);
+    const float2 s2 = jpb_add2(jpb_add2(S.h2a, S.h2b), h2);
+    const float2 s3 = jpb_add2(jpb_add2(S.h3a, S.h3b), h3);
+    const float2 mx = jpb_mul2(s1, NINTH), nmx = jpb_mul2(s1, NNINTH);
+    const float2 d1 = jpb_fma2(mx, mx, t.CY1);                                   // mu_x^2 + mu_y^2 + C1
+    const float2 d2 = jpb_fma2(nmx, mx, jpb_fma2(s2, NINTH, t.CY2));             // sigma_x + sigma_y + C2
+    const float2 vxy = jpb_fma2(nmx, t.MY, jpb_mul2(s3, NINTH));                 // sigma_xy
+    const float2 n1 = jpb_fma2(mx, t.TWO_MY, jpb_dup2(SSIM_C1));
+    const float2 n2 = jpb_fma2(vxy, jpb_dup2(2.f), jpb_dup2(SSIM_C2));
+    const float2 n = jpb_mul2(n1, n2), d = jpb_mul2(d1, d2);
+    const float2 ssim = make_float2(__saturatef(0.5f - 0.5f * (n.x * fast_rcp(d.x))), __saturatef(0.5f - 0.5f * (n.y * fast_rcp(d.y))));
+    const float2 df = jpb_fma2(S.xbp, jpb_dup2(-1.f), t.YBP);
+    const float2 e2 = jpb_fma2(df, df, jpb_dup2(1e-6f));
+    const float2 l1 = make_float2(fast_sqrt_ftz(e2.x), fast_sqrt_ftz(e2.y));
+    err = jpb_fma2(ssim, jpb_dup2(0.85f / 3.f), err);
+    err = jpb_fma2(l1, jpb_dup2(0.15f / 3.f), err);
+  }
+  S.h1a = S.h1b; S.h1b = h1; S.h2a = S.h2b; S.h2b = h2; S.h3a = S.h3b; S.h3b = h3; S.xbp = xb;
+}
+
+__global__ void __launch_bounds__(256, 2) photometric_fwd_kernel(JpbPhotoArgs a) {
+  JPB_DYN_SMEM(float, sm);
+  __shared__ SrcGeom geom[2];
+  __shared__ double red[32];
+  const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int F = a.F, H = a.H, W = a.W;
+  const bool ident = a.automask != 0;
+  const int pl = H * W;
+  float* s_tgt = sm;                                                  // [3][AN]
+  float2* s_wp = reinterpret_cast<float2*>(sm + 3 * AN);              // [3][AN] warped (f0, f1)
+  float2* s_id = s_wp + 3 * AN;                                       // [3][AN] identity (f0, f1), automask only
+  const float* tb0 = a.target + (size_t)b * 3 * pl;
+  const float* sa0 = a.src[0] + (size_t)b * 3 * pl;
+  const float* sb0 = a.src[F > 1 ? 1 : 0] + (size_t)b * 3 * pl;
+  const float *tb1 = tb0 + pl, *tb2 = tb1 + pl, *sa1 = sa0 + pl, *sa2 = sa1 + pl, *sb1 = sb0 + pl, *sb2 = sb1 + pl;
+
+  for (int f = JPB_TID; f < F; f += JPB_NT) make_geom(a.K + b * 16, a.T[f] + b * 16, geom[f]);
+  __syncthreads();
+
+  // ---- phase 1: stage target, identity and warped pixels of the tile + apron (reflect-indexed at the border)
+  const float* disp = a.disp + (size_t)b * a.hs * a.ws;
+  const int hs = a.hs, ws = a.ws;
+  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const float cw = (float)W / (float)(W - 1), ch = (float)H / (float)(H - 1);
+  const float drange = a.max_disp - a.min_disp, dmin = a.min_disp;
+  float ik[9];
+  {
+    const float* iK = a.invK + b * 16;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ik[3 * i] = __ldg(iK + 4 * i); ik[3 * i + 1] = __ldg(iK + 4 * i + 1); ik[3 * i + 2] = __ldg(iK + 4 * i + 2); }
+  }
+  float* wo0 = a.warped[0] ? a.warped[0] + (size_t)b * 3 * pl : nullptr;
+  float* wo1 = (F > 1 && a.warped[1]) ? a.warped[1] + (size_t)b * 3 * pl : nullptr;
+  // one register pair per colour plane: every access below is one IMAD.WIDE + LDG
+  JPB_PIN_PTR(tb0); JPB_PIN_PTR(tb1); JPB_PIN_PTR(tb2); JPB_PIN_PTR(sa0); JPB_PIN_PTR(sa1); JPB_PIN_PTR(sa2);
+  JPB_PIN_PTR(sb0); JPB_PIN_PTR(sb1); JPB_PIN_PTR(sb2); JPB_PIN_PTR(disp);
+#pragma unroll 2
+  for (int e = JPB_TID; e < AN; e += JPB_NT) {
+    const int hy = e / AW, hx = e - hy * AW;
+    const int y = jpb_reflect(min(y0 + hy - 1, H), H), x = jpb_reflect(min(x0 + hx - 1, W), W);
+    const int o = y * W + x;
+    const float t0 = __ldg(tb0 + o), t1 = __ldg(tb1 + o), t2 = __ldg(tb2 + o);
+    float2 i0, i1, i2;
+    if (ident) {
+      i0.x = __ldg(sa0 + o); i1.x = __ldg(sa1 + o); i2.x = __ldg(sa2 + o);
+      i0.y = __ldg(sb0 + o); i1.y = __ldg(sb1 + o); i2.y = __ldg(sb2 + o);
+    }
+    // bilinear up-sampling of disp_s (align_corners=False), disp_to_depth (layers.py:33-38)
+    int uy0, uy1, ux0, ux1;
+    float uly, ulx;
+    up_axis(y, sy, hs, uy0, uy1, uly);
+    up_axis(x, sx, ws, ux0, ux1, ulx);
+    const int ur0 = uy0 * ws, ur1 = uy1 * ws;
+    const float da = __ldg(disp + (ur0 + ux0)), db = __ldg(disp + (ur0 + ux1));
+    const float dc = __ldg(disp + (ur1 + ux0)), de = __ldg(disp + (ur1 + ux1));
+    const float D = (1.f - uly) * ((1.f - ulx) * da + ulx * db) + uly * ((1.f - ulx) * dc + ulx * de);
+    const float z = fast_rcp(dmin + drange * D);
+    const float fx = (float)x, fy = (float)y;
+    const float X0 = z * (ik[0] * fx + ik[1] * fy + ik[2]);   // Backproject (layers.py:57-61)
+    const float X1 = z * (ik[3] * fx + ik[4] * fy + ik[5]);
+    const float X2 = z * (ik[6] * fx + ik[7] * fy + ik[8]);
+    float v0[3], v1[3];
+    warp3(geom[0], X0, X1, X2, sa0, sa1, sa2, H, W, cw, ch, v0);
+    if (F > 1) warp3(geom[1], X0, X1, X2, sb0, sb1, sb2, H, W, cw, ch, v1);
+    else { v1[0] = v0[0]; v1[1] = v0[1]; v1[2] = v0[2]; }
+    s_tgt[e] = t0; s_tgt[AN + e] = t1; s_tgt[2 * AN + e] = t2;
+    s_wp[e] = make_float2(v0[0], v1[0]); s_wp[AN + e] = make_float2(v0[1], v1[1]); s_wp[2 * AN + e] = make_float2(v0[2], v1[2]);
+    if (ident) { s_id[e] = i0; s_id[AN + e] = i1; s_id[2 * AN + e] = i2; }
+    const bool interior = hy >= 1 && hy <= TH && hx >= 1 && hx <= TW && (y0 + hy - 1) < H && (x0 + hx - 1) < W;
+    if (interior) {
+      if (wo0) { wo0[o] = v0[0]; wo0[pl + o] = v0[1]; wo0[2 * pl + o] = v0[2]; }
+      if (wo1) { wo1[o] = v1[0]; wo1[pl + o] = v1[1]; wo1[2 * pl + o] = v1[2]; }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: one (column, SR-row strip) per thread, both frames of a candidate kind per packed instruction
+  float local = 0.f;
+  for (int e = JPB_TID; e < TW * (TH / SR); e += JPB_NT) {
+    const int tx = e % TW, ry0 = (e / TW) * SR;
+    const int x = x0 + tx;
+    if (x >= W || y0 + ry0 >= H) continue;
+    float2 errI[SR], errW[SR];
+#pragma unroll
+    for (int r = 0; r < SR; ++r) { errI[r] = jpb_dup2(0.f); errW[r] = jpb_dup2(0.f); }
+    const int base = ry0 * AW + tx + 1;   // apron index of the strip's first window row (row above the strip), centre column
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      const float* yp = s_tgt + c * AN + base;
+      const float2* wp = s_wp + c * AN + base;
+      const float2* ip = s_id + c * AN + base;
+      float t1a = 0.f, t1b = 0.f, t2a = 0.f, t2b = 0.f, ybp = 0.f;
+      PairState SI, SW;
+      SI.h1a = SI.h1b = SI.h2a = SI.h2b = SI.h3a = SI.h3b = SI.xbp = jpb_dup2(0.f);
+      SW = SI;
+#pragma unroll
+      for (int r = 0; r < SR + 2; ++r) {
+        const float ya = yp[r * AW - 1], yb = yp[r * AW], yc = yp[r * AW + 1];
+        const float t1 = (ya + yb) + yc, t2 = yc * yc + (yb * yb + ya * ya);
+        TargetOut t;
+        if (r >= 2) {
+          const float m = ((t1a + t1b) + t1) * (1.f / 9.f);
+          const float mm = m * m;
+          t.MY = jpb_dup2(m); t.TWO_MY = jpb_dup2(2.f * m);
+          t.CY1 = jpb_dup2(mm + SSIM_C1);
+          t.CY2 = jpb_dup2((((t2a + t2b) + t2) * (1.f / 9.f) - mm) + SSIM_C2);
+          t.YBP = jpb_dup2(ybp);
+        }
+        const float2 Ya = jpb_dup2(ya), Yb = jpb_dup2(yb), Yc = jpb_dup2(yc);
+        if (ident) pair_row(SI, ip[r * AW - 1], ip[r * AW], ip[r * AW + 1], Ya, Yb, Yc, r >= 2, t, errI[r >= 2 ? r - 2 : 0]);
+        pair_row(SW, wp[r * AW - 1], wp[r * AW], wp[r * AW + 1], Ya, Yb, Yc, r >= 2, t, errW[r >= 2 ? r - 2 : 0]);
+        t1a = t1b; t1b = t1; t2a = t2b; t2b = t2; ybp = yb;
+      }
+    }
+    // ---- candidates -> min / argmin (identity terms first, with their tie-breaking noise)
+#pragma unroll
+    for (int r = 0; r < SR; ++r) {
+      const int y = y0 + ry0 + r;
+      if (y >= H) continue;
+      const size_t po = (size_t)b * pl + (size_t)y * W + x;
+      float best = 3.0e38f;
+      int besti = 0;
+      int nid = 0;
+      if (ident) {
+        nid = F;
+        float nz0 = 0.f, nz1 = 0.f;
+        if (!a.noise[0] && a.noise_scale != 0.f) {
+          randn2(a.seed, a.stream + (a.step ? 64ull * (uint64_t)a.step[0] : 0ull), (uint64_t)po, nz0, nz1);
+          nz0 *= a.noise_scale; nz1 *= a.noise_scale;
+        }
+        const float v0 = errI[r].x + (a.noise[0] ? a.noise[0][po] : nz0);
+        if (v0 < best) { best = v0; besti = 0; }
+        if (F > 1) {
+          const float v1 = errI[r].y + (a.noise[1] ? a.noise[1][po] : nz1);
+          if (v1 < best) { best = v1; besti = 1; }
+        }
+      }
+      if (errW[r].x < best) { best = errW[r].x; besti = nid; }
+      if (F > 1 && errW[r].y < best) { best = errW[r].y; besti = nid + 1; }
+      if (a.min_index) a.min_index[po] = (long long)besti;
+      if (a.winner) a.winner[po] = (unsigned char)besti;
+      local += best;
+    }
+  }
+  const double tot = jpb_block_sum<double>((double)local, red);
+  if (JPB_TID == 0) atomicAdd(a.loss_sum, tot);
+}
+}  // namespace v3
+
 // ------------------------------------------------------------------------------------ backward
 // d(loss_s)/d(disp_s) and d(loss_s)/d(T_f).  Gradient reaches a warped candidate only where it is the
 // arg-min; each warped pixel feeds the (up to) 9 SSIM windows around it, with multiplicity 2 where the
@@ -634,9 +884,30 @@ __global__ void __launch_bounds__(256) photometric_bwd_kernel(JpbPhotoArgs a, Jp
 
 }  // namespace
 
+static int g_fwd_variant = 2;   // 2: photometric_fwd_kernel (measured, default); 3: v3::photometric_fwd_kernel (packed fp32)
+
+extern "C" int jpb_photometric_set_variant(int fwd_variant) {
+  if (fwd_variant != 2 && fwd_variant != 3) return JPB_ERR_ARG;
+  g_fwd_variant = fwd_variant;
+  return JPB_OK;
+}
+
 extern "C" int jpb_photometric_fwd(const JpbPhotoArgs* a, void* stream) {
   if (!a || a->F < 1 || a->F > JPB_MAX_SRC || a->H < 3 || a->W < 3 || !a->loss_sum) return JPB_ERR_ARG;
   const int nid = a->automask ? a->F : 0;
+  if (a->F <= 2 && g_fwd_variant == 3 && (long long)a->H * a->W * 3 < (1ll << 31)) {   // packed variant (opt-in until measured)
+    const size_t smem = (size_t)(3 + 6 + (nid ? 6 : 0)) * v3::AN * sizeof(float);
+    dim3 grid((a->W + v3::TW - 1) / v3::TW, (a->H + v3::TH - 1) / v3::TH, a->B);
+#ifndef JPB_HOST_EMU
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      if (cudaFuncSetAttribute(v3::photometric_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+      configured = smem;
+    }
+#endif
+    JPB_LAUNCH(v3::photometric_fwd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+    return jpb_status();
+  }
   if (a->F <= 2) {   // fast path: 32x32 tiles, separable window sums (every reference configuration: F <= 2)
     const size_t smem = (size_t)(3 + 3 * a->F) * Q1_N * sizeof(float);
     dim3 grid((a->W + QT_W - 1) / QT_W, (a->H + QT_H - 1) / QT_H, a->B);

@@ -57,7 +57,18 @@ def _photo_case(B=2, H=24, W=40, s=0, F=2, seed=0):
     return target, sources, disp, K, invK, Ts
 
 
-def test_photometric_kat5(dev):
+@pytest.fixture(params=[2, 3], ids=["fwd2", "fwd3"])
+def photo_variant(request, dev):
+    """Both forward schedules of the fused photometric kernel (include/jpb200.h: jpb_photometric_set_variant).  The packed
+    one is opt-in until it has been measured; its GPU parity cases live in tests/test_zz_photometric_packed.py (sorted last)."""
+    if request.param == 3 and dev.type == "cuda":
+        pytest.skip("packed schedule on the GPU: tests/test_zz_photometric_packed.py")
+    _lib.check(_lib.lib().jpb_photometric_set_variant(request.param), "jpb_photometric_set_variant")
+    yield request.param
+    _lib.check(_lib.lib().jpb_photometric_set_variant(2), "jpb_photometric_set_variant")
+
+
+def test_photometric_kat5(dev, photo_variant):
     kat = np.load(os.path.join(GOLDEN, "kat.npz"))
     H, W = 8, 12
     K = torch.tensor([[.58 * W, 0, .5 * W, 0], [0, 1.92 * H, .5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]]).unsqueeze(0)
@@ -72,7 +83,7 @@ def test_photometric_kat5(dev):
 
 
 @pytest.mark.parametrize("s,H,W,automask", [(0, 24, 40, True), (1, 36, 72, True), (2, 32, 64, False), (0, 17, 33, True)])
-def test_photometric_forward_backward_vs_oracle(dev, s, H, W, automask):
+def test_photometric_forward_backward_vs_oracle(dev, photo_variant, s, H, W, automask):
     target, sources, disp, K, invK, Ts = _photo_case(H=H, W=W, s=s)
     B = target.shape[0]
     g = torch.Generator().manual_seed(5)
@@ -97,6 +108,42 @@ def test_photometric_forward_backward_vs_oracle(dev, s, H, W, automask):
     assert (gd0 - gd1).abs().max().item() <= 2e-3 * gd0.abs().max().item() + 1e-9
     for a, b in zip(T0, T1):
         assert (a.grad - b.grad.cpu()).abs().max().item() <= 2e-3 * a.grad.abs().max().item() + 1e-9
+
+
+def test_photometric_single_source_and_inkernel_noise(dev, photo_variant):
+    """frame_ids [0, -1] (configs 1 and 4: one source frame) and the in-kernel Philox draw of the automask noise."""
+    target, sources, disp, K, invK, Ts = _photo_case(H=40, W=72, s=0, F=1, seed=3)
+    m, idx, warped = O.photometric_scale(disp, target, sources, Ts, K, invK, automask=True, noise=None)
+    args = (D(disp, dev), D(target, dev), D(sources, dev), D(Ts, dev), D(K, dev), D(invK, dev))
+    loss, winner, idx1, warped1 = JF.photometric_loss(*args, num_scales=4, noise_scale=0.0, debug_outputs=True)
+    assert abs(loss.item() - m.item() / 4) <= 1e-5 * abs(m.item() / 4)
+    assert (idx1.cpu() != idx).float().mean().item() < 2e-3 and int(idx1.max()) <= 1
+    assert (warped[0] - warped1[0].cpu()).abs().max().item() < 5e-4
+    la = JF.photometric_loss(*args, num_scales=4, seed=7, stream=1)[0].item()
+    lb = JF.photometric_loss(*args, num_scales=4, seed=7, stream=1)[0].item()
+    lc = JF.photometric_loss(*args, num_scales=4, seed=8, stream=1)[0].item()
+    assert la == lb and la != lc
+    assert abs(la - loss.item()) < 1e-4 * abs(loss.item()) + 1e-6 and abs(lc - loss.item()) < 1e-4 * abs(loss.item()) + 1e-6
+
+
+def test_photometric_variants_agree(dev):
+    """The packed forward schedule reproduces the default one: same arg-min except at fp32 ties, same loss to 1e-6 relative."""
+    if dev.type == "cuda":
+        pytest.skip("packed schedule on the GPU: tests/test_zz_photometric_packed.py")
+    target, sources, disp, K, invK, Ts = _photo_case(B=2, H=64, W=96, s=1, seed=11)
+    args = (D(disp, dev), D(target, dev), D(sources, dev), D(Ts, dev), D(K, dev), D(invK, dev))
+    out = {}
+    try:
+        for v in (2, 3):
+            _lib.check(_lib.lib().jpb_photometric_set_variant(v), "jpb_photometric_set_variant")
+            out[v] = JF.photometric_loss(*args, num_scales=4, noise_scale=0.0, debug_outputs=True)
+    finally:
+        _lib.check(_lib.lib().jpb_photometric_set_variant(2), "jpb_photometric_set_variant")
+    assert abs(out[2][0].item() - out[3][0].item()) <= 2e-6 * abs(out[2][0].item())
+    assert (out[2][2] != out[3][2]).float().mean().item() < 2e-3
+    for w2, w3 in zip(out[2][3], out[3][3]):
+        assert (w2 - w3).abs().max().item() < 5e-4
+    assert _lib.lib().jpb_photometric_set_variant(7) != 0        # unknown schedule: argument error, nothing changes
 
 
 def test_area_pyramid_and_smoothness_kat4(dev):

@@ -34,8 +34,10 @@ def make_case(B, H, W, F, dev, seed=0):
     return target, sources, disps, K.to(dev), invK.to(dev), Ts
 
 
-def run(B=4, H=320, W=1024, F=2, iters=20, warmup=3):
+def run(B=4, H=320, W=1024, F=2, iters=20, warmup=3, variant=None):
     dev = torch.device("cuda:0")
+    if variant is not None:
+        _lib.check(_lib.lib().jpb_photometric_set_variant(variant), "jpb_photometric_set_variant")
     target, sources, disps, K, invK, Ts = make_case(B, H, W, F, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     disps = [d.requires_grad_(True) for d in disps]
@@ -71,7 +73,7 @@ def run(B=4, H=320, W=1024, F=2, iters=20, warmup=3):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm = peaks.get("hbm_gbs", 6650.0)
-    return {"metric": "fused photometric-loss ms/batch (4 scales)", "B": B, "H": H, "W": W, "F": F,
+    return {"metric": "fused photometric-loss ms/batch (4 scales)", "fwd_variant": variant or int(os.environ.get("JPB_PHOTO_FWD", 2)), "B": B, "H": H, "W": W, "F": F,
             "fwd_ms": fwd, "bwd_ms": bwd, "fwd_alg_bytes": bytes_fwd, "bwd_alg_bytes": bytes_bwd,
             "fwd_gbs": bytes_fwd / fwd / 1e6, "bwd_gbs": bytes_bwd / bwd / 1e6, "hbm_peak_gbs": hbm,
             "fwd_frac": bytes_fwd / fwd / 1e6 / hbm, "bwd_frac": bytes_bwd / bwd / 1e6 / hbm,
@@ -83,5 +85,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=4)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--variant", type=int, default=None, help="forward schedule: 2 (default) or 3 (packed fp32 pairs)")
     a = ap.parse_args()
-    print(json.dumps(run(B=a.B, iters=a.iters)))
+    print(json.dumps(run(B=a.B, iters=a.iters, variant=a.variant)))
