@@ -322,6 +322,28 @@ int jpb_weight_flipT(const JpbWeightT* entries_dev, int nent, int nblocks, void*
  * (the `.mean()` / weight scalings of net.py:175-190, done on device so no loss term syncs the host) */
 int jpb_finalize(const double* acc, const double* den, float scale, float* out, int n, void* stream);
 
+/* ---- evaluation metrics on the device (validation hook) ------------------------------------------
+ * depth : eval_hooks.py:149-197 (disp_to_depth, cv2.resize to the ground-truth frame, 1/x, validity + crop mask, median
+ *         scaling or the fixed stereo scale, clamp) + pixel_error.py:27-40 (compute_errors), one sample per batch entry.
+ * BEV   : eval_hooks.py:185-197 + pixel_error.py:62-118 (mean_IU, mean_precision): the three counts both are built from. */
+typedef struct JpbDepthEvalArgs {
+  const float* disp;          /* [B,h,w]   outputs[("disp",0,0)] (sigmoid output, not yet scaled)                 */
+  const float* gt;            /* [B,gh,gw] data['gt_depth']; values outside (min_depth, max_depth) are ignored     */
+  int B, h, w, gh, gw;
+  float min_disp, max_disp;   /* disp_to_depth: 1/max_depth', 1/min_depth' of the NETWORK range (0.01, 10)         */
+  float min_depth, max_depth; /* MIN_DEPTH = 1e-3, MAX_DEPTH = 80 (eval_hooks.py:14-15)                            */
+  int crop[4];                /* rows [crop0,crop1) x cols [crop2,crop3) (eval_hooks.py:168-172)                   */
+  float fixed_scale;          /* > 0: cfg.data['stereo_scale'] (x36); 0: median scaling                            */
+  float* work;                /* [B,2,gh*gw] scratch: compacted (gt, prediction) pairs                             */
+  int* count;                 /* [B] valid pixels per sample; caller zero-fills                                    */
+  double* out;                /* [B,8] abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, ratio (NaN when count == 0)    */
+} JpbDepthEvalArgs;
+int jpb_depth_eval(const JpbDepthEvalArgs* args, void* stream);
+/* counts[b] = {#(pred==1 & gt==1), #(pred==1), #(gt==1)} with pred = argmax over the two logits; += (caller zero-fills);
+ * logits addressed as base + b*stride_b + c*stride_c + pixel*stride_p (elements); label [B,occ*occ] float {0,1}. */
+int jpb_bev_confusion(const float* logits, long long stride_b, long long stride_c, long long stride_p, const float* label,
+                      int B, int occ, long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

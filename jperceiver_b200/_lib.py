@@ -99,6 +99,12 @@ class WeightT(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("Cin", C.c_int), ("taps", C.c_int), ("block_start", C.c_int)]
 
 
+class DepthEvalArgs(C.Structure):
+    _fields_ = [("disp", C.c_void_p), ("gt", C.c_void_p), ("B", C.c_int), ("h", C.c_int), ("w", C.c_int), ("gh", C.c_int),
+                ("gw", C.c_int), ("min_disp", C.c_float), ("max_disp", C.c_float), ("min_depth", C.c_float), ("max_depth", C.c_float),
+                ("crop", C.c_int * 4), ("fixed_scale", C.c_float), ("work", C.c_void_p), ("count", C.c_void_p), ("out", C.c_void_p)]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("grad_scale", C.c_float), ("max_norm", C.c_float), ("normsq", C.c_void_p), ("step", C.c_void_p)]
@@ -165,6 +171,8 @@ class _Signatures:
     jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, I, P, C.c_longlong, I, V]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
+    jpb_depth_eval = [C.POINTER(DepthEvalArgs), V]
+    jpb_bev_confusion = [P, C.c_longlong, C.c_longlong, C.c_longlong, P, I, I, P, V]
 
 
 def exported_symbols():

@@ -127,6 +127,18 @@ def load_checkpoint(engine, path, strict=True, map_location="cpu"):
 
 
 # ------------------------------------------------------------------------------------------------ runner
+class LogBuffer:
+    """The two members of ``mmcv.runner.LogBuffer`` the evaluation hooks write (eval_hooks.py:311-327)."""
+
+    def __init__(self):
+        self.output = OrderedDict()
+        self.ready = False
+
+    def clear_output(self):
+        self.output.clear()
+        self.ready = False
+
+
 class Runner:
     def __init__(self, model, optimizer_cfg=None, optimizer_config=None, work_dir=None, log_level="INFO", logger=None, engine=None):
         grad_clip = (optimizer_config or {}).get("grad_clip")
@@ -143,6 +155,8 @@ class Runner:
         self.log_interval = None
         self.json_log = None
         self._buffer = []          # device loss vectors of the iterations since the last log line
+        self.log_buffer = LogBuffer()
+        self._hooks = []           # extra hooks (``register_hook``): objects with ``after_train_epoch(runner)``
         self._t_iter = self._t_data = 0.0
         self.timestamp = time.strftime("%Y%m%d_%H%M%S", time.localtime())
 
@@ -160,6 +174,35 @@ class Runner:
                 raise NotImplementedError("logger hooks %r (the reference configs use TextLoggerHook)" % (unknown,))
             if self.work_dir and "TextLoggerHook" in kinds:
                 self.json_log = os.path.join(self.work_dir, "%s.log.json" % self.timestamp)
+
+    def register_hook(self, hook, priority="NORMAL"):
+        """``mmcv.Runner.register_hook`` for epoch-level hooks (the reference registers its ``DistEvalMonoHook`` this way,
+        trainer.py:186-190)."""
+        if not hasattr(hook, "after_train_epoch"):
+            raise TypeError("hook must define after_train_epoch(runner)")
+        self._hooks.append(hook)
+
+    @property
+    def rank(self):
+        return self.engine.rank
+
+    @property
+    def world_size(self):
+        return self.engine.world
+
+    def _after_train_epoch(self):
+        for hook in self._hooks:
+            hook.after_train_epoch(self)
+        if self.log_buffer.ready:
+            rec = OrderedDict(mode="val", epoch=self.epoch + 1, iter=self.inner_iter + 1, lr=self.current_lr()[0])
+            rec.update((k, float(v)) for k, v in self.log_buffer.output.items())
+            self.logger.info("Epoch(val) [%d][%d]\t%s", rec["epoch"], rec["iter"],
+                             ", ".join("%s: %.4f" % (k, float(v)) for k, v in self.log_buffer.output.items()))
+            if self.json_log and self.engine.rank == 0:
+                with open(self.json_log, "a") as f:
+                    f.write(json.dumps(rec) + "\n")
+            self.last_val = rec
+            self.log_buffer.clear_output()
 
     def current_lr(self):
         return [self.engine.optimizer.lr]
@@ -246,6 +289,7 @@ class Runner:
         self._buffer = []
         if self.checkpoint_interval and (self.epoch + 1) % self.checkpoint_interval == 0 and self.work_dir:
             self.save_checkpoint(self.work_dir)
+        self._after_train_epoch()
         self.epoch += 1
 
     def run(self, data_loaders, workflow=(("train", 1),), max_epochs=1):

@@ -286,11 +286,15 @@ class TrainEngine:
 def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=False, validate=False, logger=None):
     """``mono.apis.train_mono`` (trainer.py:58-73, 146-199): build the runner, register the config's hooks, resume / load,
     run ``cfg.total_epochs``.  ``dataset_train`` must yield collated batch dicts (the datasets and loaders themselves are
-    outside this path's scope); validation hooks are SURVEY.md §8(f)-4."""
+    outside this path's scope).  ``validate=True`` registers the device-side ``DistEvalMonoHook`` over ``dataset_val`` every
+    ``cfg.validate_interval`` epochs (trainer.py:186-190)."""
     from .runner import Runner
     dev = torch.device("cuda", torch.cuda.current_device())
     model.to(dev).train()
     runner = Runner(model, cfg.optimizer, cfg.get("optimizer_config", {}), cfg.get("work_dir"), cfg.get("log_level", "INFO"), logger)
+    if validate:
+        from ..core.evaluation import DistEvalMonoHook
+        runner.register_hook(DistEvalMonoHook(dataset_val, cfg.get("validate_interval", 1), cfg))
     runner.register_training_hooks(cfg.get("lr_config"), cfg.get("optimizer_config"), cfg.get("checkpoint_config"), cfg.get("log_config"))
     if cfg.get("resume_from"):
         runner.resume(cfg.resume_from)
