@@ -344,6 +344,44 @@ int jpb_depth_eval(const JpbDepthEvalArgs* args, void* stream);
 int jpb_bev_confusion(const float* logits, long long stride_b, long long stride_c, long long stride_p, const float* label,
                       int B, int occ, long long* counts, void* stream);
 
+/* ---- batched image preprocessing (training input pipeline) -------------------------------------------
+ * mono_dataset.py:126-171 (preprocess: Resize(ANTIALIAS) twice, ColorJitter, ToTensor), :202-203 (flip / jitter draws),
+ * :417-431 (label resize + binarisation).  Bit-exact with Pillow's Resample.c / Blend.c / Convert.c on the same bytes.
+ * Frames are uint8 HWC; float outputs are NCHW in [0,1] (ToTensor).  Coefficient / position tables come from the host
+ * (built in double precision exactly as Pillow's precompute_coeffs + normalize_coeffs_8bpc do).                        */
+typedef struct JpbResizeArgs {
+  const unsigned char* src;   /* [B,Hin,Win,3]                                                                     */
+  unsigned char* tmp;         /* [B,Hin,Wout,3] scratch: result of the horizontal pass                             */
+  unsigned char* dst;         /* [B,Hout,Wout,3] or NULL                                                           */
+  float* dst_f;               /* [B,3,Hout,Wout] = ToTensor(dst) or NULL                                           */
+  int B, Hin, Win, Hout, Wout;
+  const int* kx;              /* [Wout,ksx] 22-bit fixed-point coefficients of the horizontal pass                 */
+  const int* bx;              /* [Wout,2]   first source column, tap count                                         */
+  int ksx;                    /* 0: Win == Wout (Pillow skips the pass)                                            */
+  const int* ky;              /* [Hout,ksy] */
+  const int* by;              /* [Hout,2]   */
+  int ksy;
+  const unsigned char* flip;  /* [B] 1: Image.transpose(FLIP_LEFT_RIGHT) before resizing; NULL: none              */
+} JpbResizeArgs;
+int jpb_resize_lanczos_u8(const JpbResizeArgs* args, void* stream);
+
+typedef struct JpbJitterArgs {
+  const unsigned char* src;   /* [B,H,W,3]                                                                         */
+  unsigned char* dst;         /* [B,H,W,3] or NULL                                                                 */
+  float* dst_f;               /* [B,3,H,W] = ToTensor(dst) or NULL                                                 */
+  int B, H, W;
+  const int* order;           /* [B,4] ColorJitter's fn_idx permutation: 0 brightness, 1 contrast, 2 saturation, 3 hue */
+  const float* factor;        /* [B,4] brightness, contrast, saturation factors as C floats ([3] unused)           */
+  const int* hue_shift;       /* [B]   uint8(int32(hue_factor * 255)) (torchvision _functional_pil.adjust_hue)     */
+  const unsigned char* enable;/* [B] do_color_aug per sample (0: pass-through) or NULL (all on)                    */
+  unsigned long long* lsum;   /* [B] scratch for the contrast operator's mean; caller zero-fills                   */
+} JpbJitterArgs;
+int jpb_color_jitter_u8(const JpbJitterArgs* args, void* stream);
+/* label[b] = (nearest-resized src == 255) as float; src [B,Hin,Win] uint8, dst [B,size,size]; xtab/ytab [size] source
+ * positions (Geometry.c ImagingScaleAffine, accumulated in double on the host).                                       */
+int jpb_bev_label_u8(const unsigned char* src, float* dst, int B, int Hin, int Win, int size, const int* xtab, const int* ytab,
+                     const unsigned char* flip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,17 @@ class DepthEvalArgs(C.Structure):
                 ("crop", C.c_int * 4), ("fixed_scale", C.c_float), ("work", C.c_void_p), ("count", C.c_void_p), ("out", C.c_void_p)]
 
 
+class ResizeArgs(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("tmp", C.c_void_p), ("dst", C.c_void_p), ("dst_f", C.c_void_p), ("B", C.c_int), ("Hin", C.c_int),
+                ("Win", C.c_int), ("Hout", C.c_int), ("Wout", C.c_int), ("kx", C.c_void_p), ("bx", C.c_void_p), ("ksx", C.c_int),
+                ("ky", C.c_void_p), ("by", C.c_void_p), ("ksy", C.c_int), ("flip", C.c_void_p)]
+
+
+class JitterArgs(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_f", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("order", C.c_void_p), ("factor", C.c_void_p), ("hue_shift", C.c_void_p), ("enable", C.c_void_p), ("lsum", C.c_void_p)]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("grad_scale", C.c_float), ("max_norm", C.c_float), ("normsq", C.c_void_p), ("step", C.c_void_p)]
@@ -172,6 +183,9 @@ class _Signatures:
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
     jpb_depth_eval = [C.POINTER(DepthEvalArgs), V]
+    jpb_resize_lanczos_u8 = [C.POINTER(ResizeArgs), V]
+    jpb_color_jitter_u8 = [C.POINTER(JitterArgs), V]
+    jpb_bev_label_u8 = [P, P, I, I, I, I, P, P, P, V]
     jpb_bev_confusion = [P, C.c_longlong, C.c_longlong, C.c_longlong, P, I, I, P, V]
 
 
