@@ -82,21 +82,23 @@ int jpb_smooth_fwd(const float* disp, const float* J, int B, int h, int w, int d
 int jpb_smooth_bwd(const float* disp, const float* J, int B, int h, int w, int disp_norm, float weight,
                    const double* acc, const float* grad_out, float* grad_disp /* += */, void* stream);
 
-/* ---- CGT scale label (net.py:212-310 static, 403-476 both; layers.py:214-252) -------------------
+/* ---- CGT scale label (net.py:212-310 static, 311-402 dynamic, 403-476 both; layers.py:214-252) ----
  * out[b] = warp(z_map) * warp(label)              (mode 0, "Argo_both")
- *        = warp(z_map) * [warp(label)==1] * quad  (mode 1, "static"/"static_raw"; quad = the cv2-filled
- *          rectangle projection of net.py:292-306, rasterised by the host from sample 0's calibration) */
+ *        = warp(z_map) * [warp(label)==1] * quad  (mode 1, "static"/"static_raw"/"Argo_static"; quad = the cv2-filled
+ *          rectangle projection of net.py:292-306, rasterised by the host from sample 0's calibration)
+ *        = warp(z_map) * quad                     (mode 2, "dynamic"/"Argo_dynamic": net.py:390-401 masks the z-map
+ *          by the quad alone; label may be NULL; z_offset is 0 for KITTI, net.py:325-326) */
 typedef struct JpbScaleLabelArgs {
-  const float* label;       /* [B,occ,occ] inputs[("both_dynamic"|"bothS",0,0)] in {0,1}           */
+  const float* label;       /* [B,occ,occ] inputs[("both_dynamic"|"bothS",0,0)] in {0,1}; unused in mode 2 */
   const float* K3;          /* inputs[("odometry_K",0,0)]: element (i,j) of sample b at K3[b*k_stride+i*k_row+j] */
   int k_stride, k_row;
   const float* Tr;          /* [B,4,4] inputs[("Tr_cam2_velo",0,0)]                                */
-  const unsigned char* quad;/* [Hf,Wf] (mode 1) or NULL                                            */
+  const unsigned char* quad;/* [Hf,Wf] (modes 1, 2) or NULL (mode 0)                                   */
   float* out;               /* [B,Hf,Wf]                                                           */
   int B, occ, Hf, Wf;
-  int mode;                 /* 0 both, 1 static                                                    */
+  int mode;                 /* 0 both, 1 static, 2 dynamic                                         */
   int align_corners;        /* torchgeometry 0.1.2 leaves it to torch's default: un-pinned, see DESIGN.md */
-  float z_offset;           /* 0.27 KITTI, 1.9 Argoverse (net.py:229-233)                          */
+  float z_offset;           /* 0.27 KITTI (0 in mode 2), 1.9 Argoverse (net.py:229-233, 323-326)   */
   float cam_height;         /* 1.73 KITTI, 0.33 Argoverse (net.py:257-260)                         */
 } JpbScaleLabelArgs;
 int jpb_scale_label(const JpbScaleLabelArgs* args, void* stream);

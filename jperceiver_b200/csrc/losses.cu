@@ -233,9 +233,13 @@ __global__ void __launch_bounds__(256) scale_label_kernel(JpbScaleLabelArgs a) {
     if (ix > -1.f && ix < (float)occ && iy > -1.f && iy < (float)occ) {
       // rot90(k=3): map_rot[i][j] = map[occ-1-j][i];  z_rot[i][j] = (j+1)*40/occ - delta
       const float wz = sample_zeros([&](int i, int j) { return (float)(j + 1) * zs - a.z_offset; }, occ, ix, iy);
-      const float wl = sample_zeros([&](int i, int j) { return L[(occ - 1 - j) * occ + i]; }, occ, ix, iy);
-      if (a.mode == 0) out = wz * wl;                                       // Argo_both: product of the two warps
-      else out = (wl >= 0.99999905f && a.quad[e] != 0) ? wz : 0.f;          // static: exact-1 mask AND cv2 quad
+      if (a.mode == 2) {
+        out = a.quad[e] != 0 ? wz : 0.f;                                    // dynamic: cv2 quad only, the label is never warped
+      } else {
+        const float wl = sample_zeros([&](int i, int j) { return L[(occ - 1 - j) * occ + i]; }, occ, ix, iy);
+        if (a.mode == 0) out = wz * wl;                                     // Argo_both: product of the two warps
+        else out = (wl >= 0.99999905f && a.quad[e] != 0) ? wz : 0.f;        // static: exact-1 mask AND cv2 quad
+      }
     }
     a.out[(size_t)b * Hf * Wf + e] = out;
   }
@@ -538,7 +542,8 @@ extern "C" int jpb_smooth_bwd(const float* disp, const float* J, int B, int h, i
 }
 
 extern "C" int jpb_scale_label(const JpbScaleLabelArgs* a, void* stream) {
-  if (!a || !a->label || !a->K3 || !a->Tr || !a->out || (a->mode == 1 && !a->quad)) return JPB_ERR_ARG;
+  if (!a || !a->K3 || !a->Tr || !a->out || a->mode < 0 || a->mode > 2) return JPB_ERR_ARG;
+  if ((a->mode != 2 && !a->label) || (a->mode != 0 && !a->quad)) return JPB_ERR_ARG;
   dim3 grid(grid_for((long long)a->Hf * a->Wf, 256, 148 * 4), a->B);
   JPB_LAUNCH(scale_label_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *a);
   return jpb_status();

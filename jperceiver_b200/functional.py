@@ -202,21 +202,28 @@ def smooth_loss(disp, J, weight, disp_norm=True):
 # --------------------------------------------------------------------------------------------------
 # CGT scale label / loss
 # --------------------------------------------------------------------------------------------------
-def scale_label(label, odometry_K, Tr, out_hw, *, split, mode, quad=None, align_corners=True):
-    label, Kc, Tr = _f32c(label), _f32c(odometry_K), _f32c(Tr)
-    B, occ = label.shape[0], label.shape[-1]
+def scale_label(label, odometry_K, Tr, out_hw, *, split, mode, quad=None, align_corners=True, occ=None):
+    """CGT scale label.  ``mode``: 'both' (net.py:403-476), 'static' (:212-310) or 'dynamic' (:311-402; the reference
+    reads the BEV label there only for its shape, so ``label`` may be None when ``occ`` is given)."""
+    Kc, Tr = _f32c(odometry_K), _f32c(Tr)
+    if mode != "dynamic" or label is not None:
+        label = _f32c(label)
+        occ = label.shape[-1]
+        if label.shape[-2] != occ:
+            raise ValueError("The shape of both label is not %d" % occ)   # net.py:222-223
+    B = Kc.shape[0]
     Hf, Wf = out_hw
-    out = torch.empty(B, 1, Hf, Wf, dtype=torch.float32, device=label.device)
+    out = torch.empty(B, 1, Hf, Wf, dtype=torch.float32, device=Kc.device)
     a = _lib.ScaleLabelArgs()
-    a.label, a.K3, a.Tr, a.out = ptr(label), ptr(Kc), ptr(Tr), ptr(out)
+    a.label, a.K3, a.Tr, a.out = (ptr(label) if label is not None else None), ptr(Kc), ptr(Tr), ptr(out)
     a.k_stride, a.k_row = Kc.shape[-2] * Kc.shape[-1], Kc.shape[-1]
     a.quad = ptr(quad) if quad is not None else None
     a.B, a.occ, a.Hf, a.Wf = B, occ, Hf, Wf
-    a.mode = {"both": 0, "static": 1}[mode]
+    a.mode = {"both": 0, "static": 1, "dynamic": 2}[mode]
     a.align_corners = int(align_corners)
-    a.z_offset = 1.9 if split == "argo" else 0.27
+    a.z_offset = 1.9 if split == "argo" else (0.0 if mode == "dynamic" else 0.27)
     a.cam_height = 0.33 if split == "argo" else 1.73
-    check(_lib.lib().jpb_scale_label(C.byref(a), stream_of(label)), "jpb_scale_label")
+    check(_lib.lib().jpb_scale_label(C.byref(a), stream_of(Kc)), "jpb_scale_label")
     return out
 
 

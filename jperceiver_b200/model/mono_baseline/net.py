@@ -33,7 +33,7 @@ from .params import BNP
 
 ROAD_TYPES = ("static", "static_raw", "Argo_static", "Argo_both")
 CAR_TYPES = ("dynamic", "Argo_dynamic", "Argo_both")
-LABEL_TYPES = ("static", "static_raw", "Argo_static", "Argo_both")
+LABEL_TYPES = ("static", "static_raw", "Argo_static", "Argo_both", "dynamic", "Argo_dynamic")   # /net.py:119-124
 
 
 class _Opt(dict):
@@ -195,6 +195,13 @@ class Baseline(nn.Module):
         if o["type"] == "Argo_both":
             return JF.scale_label(inputs[("both_dynamic", 0, 0)], inputs[("odometry_K", 0, 0)], inputs[("Tr_cam2_velo", 0, 0)],
                                   (height, width), split=o.split, mode="both", align_corners=self.warp_align_corners)
+        if o["type"] in ("dynamic", "Argo_dynamic"):
+            # get_scale_label_dynamic (net.py:311-402) reads inputs[("bothS",0,0)] only for its shape although the dynamic
+            # dataset branch emits bothD alone (mono_dataset.py:277): the label is optional here, the z-map is masked by
+            # the quad only
+            return JF.scale_label(inputs.get(("bothS", 0, 0)), inputs[("odometry_K", 0, 0)], inputs[("Tr_cam2_velo", 0, 0)],
+                                  (height, width), split=o.split, mode="dynamic", quad=self._quad_mask(inputs, height, width),
+                                  align_corners=self.warp_align_corners, occ=o.occ_map_size)
         return JF.scale_label(inputs[("bothS", 0, 0)], inputs[("odometry_K", 0, 0)], inputs[("Tr_cam2_velo", 0, 0)],
                               (height, width), split=o.split, mode="static", quad=self._quad_mask(inputs, height, width),
                               align_corners=self.warp_align_corners)

@@ -142,8 +142,9 @@ def make_e2e(typ):
     torch.manual_seed(0)
     model = R.build_baseline(opt)
     shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
-    with open(os.path.join(GOLD, "state_dict_shapes.json"), "w") as f:
-        json.dump(shapes, f, indent=0)
+    if typ == "Argo_both":
+        with open(os.path.join(GOLD, "state_dict_shapes.json"), "w") as f:
+            json.dump(shapes, f, indent=0)
     P = O.synth_params(model.state_dict(), seed=3)
     model.load_state_dict(P)
     model.train()
@@ -195,6 +196,8 @@ def make_e2e(typ):
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
-    make_kats()
-    for typ in ("Argo_both", "static", "static_raw"):
+    only = sys.argv[1:]
+    if not only:
+        make_kats()
+    for typ in only or ("Argo_both", "static", "static_raw", "dynamic"):
         make_e2e(typ)

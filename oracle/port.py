@@ -419,9 +419,12 @@ def static_quad_mask(Minv0, occ, height, width):
 def scale_label(opt, inputs, warp_align_corners=True):
     typ, split, occ = opt["type"], opt["split"], opt["occ_map_size"]
     height, width = inputs[("color", 0, -1)].shape[2:4]
+    dyn = typ in ("dynamic", "Argo_dynamic")
     lab = inputs[("both_dynamic", 0, 0)] if typ == "Argo_both" else inputs[("bothS", 0, 0)]
     B = lab.shape[0]
-    delta = 1.9 if split == "argo" else 0.27
+    # get_scale_label_dynamic (M/net.py:311-402) drops the 0.27 m offset for KITTI (:325-326) and never warps the label:
+    # it reads bothS only for its shape (:316-320), the z-map is masked by the cv2 quad alone (:390-401)
+    delta = 1.9 if split == "argo" else (0.0 if dyn else 0.27)
     z = (torch.arange(occ, 0, -1, dtype=torch.float32) * (40.0 / occ) - delta).view(1, 1, occ, 1).repeat(B, 1, 1, occ)
     lab = torch.rot90(lab.float(), 3, (2, 3))  # fliplr on dim 1 (size 1) is a no-op; rotate(270) == rot90(k=3)
     z = torch.rot90(z, 3, (2, 3))
@@ -432,6 +435,8 @@ def scale_label(opt, inputs, warp_align_corners=True):
     if typ == "Argo_both":
         return wz * wl
     quad = static_quad_mask(Minv[0], occ, height, width)
+    if dyn:
+        return wz * quad.view(1, 1, height, width)
     return wz * ((wl >= ONE_TOL).float() * quad.view(1, 1, height, width))
 
 
@@ -506,6 +511,7 @@ def bev_head_loss(logits, label, w_fg, loss_weight=20.0, loss2_weight=20.0, loss
 # ----------------------------------------------------------------------------------------------
 ROAD_TYPES = ("static", "static_raw", "Argo_static", "Argo_both")
 CAR_TYPES = ("dynamic", "Argo_dynamic", "Argo_both")
+LABEL_TYPES = ROAD_TYPES + ("dynamic", "Argo_dynamic")   # every type of /net.py:119-124 builds a CGT label
 
 
 def compute_losses(opt, inputs, outputs, noise=None, warp_align_corners=True):
@@ -528,7 +534,7 @@ def compute_losses(opt, inputs, outputs, noise=None, warp_align_corners=True):
         L["transform_lossB"] = (outputs["featuresB"] - outputs["retransform_featuresB"]).abs().mean()
         L["layout_lossB"] = L["topview_lossB"] + 0.001 * L["transform_lossB"] + L["transform_topview_lossB"]
     label = None
-    if typ in ("static", "static_raw", "Argo_static", "Argo_both"):
+    if typ in LABEL_TYPES:
         label = scale_label(opt, inputs, warp_align_corners)
         outputs["scale_label"] = label
     fids = list(opt["frame_ids"])

@@ -140,6 +140,13 @@ def test_static_nonsquare_small(dev):
     run_case(dev, "static", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
 
 
+def test_dynamic_small(dev):
+    """``type='dynamic'`` (/net.py:119-159): vehicle heads only + the dynamic CGT label (net.py:311-402)."""
+    if dev.type == "cuda":
+        pytest.skip("the dynamic label kernel is covered on the GPU by tests/test_losses.py::test_scale_label_dynamic_vs_oracle")
+    run_case(dev, "dynamic", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
+
+
 @pytest.mark.gpu
 def test_full_size_gpu_tf32():
     """The product configuration: tcgen05 TF32 convolutions.  A TF32 rounding can flip one of the network's hard

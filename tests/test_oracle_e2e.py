@@ -31,7 +31,7 @@ def _run(typ):
     return P, outs, losses, total
 
 
-@pytest.mark.parametrize("typ", ["Argo_both", "static", "static_raw"])
+@pytest.mark.parametrize("typ", ["Argo_both", "static", "static_raw", "dynamic"])
 def test_port_matches_reference_run(typ):
     torch.set_num_threads(os.cpu_count() or 1)
     gold = np.load(os.path.join(GOLDEN, f"e2e_{typ}_1024.npz"))
