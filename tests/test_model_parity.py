@@ -143,7 +143,7 @@ def test_static_nonsquare_small(dev):
 def test_dynamic_small(dev):
     """``type='dynamic'`` (/net.py:119-159): vehicle heads only + the dynamic CGT label (net.py:311-402)."""
     if dev.type == "cuda":
-        pytest.skip("the dynamic label kernel is covered on the GPU by tests/test_losses.py::test_scale_label_dynamic_vs_oracle")
+        pytest.skip("the dynamic label kernel is covered on the GPU by tests/test_zz_dynamic_label.py")
     run_case(dev, "dynamic", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
 
 
