@@ -199,5 +199,5 @@ if __name__ == "__main__":
     only = sys.argv[1:]
     if not only:
         make_kats()
-    for typ in only or ("Argo_both", "static", "static_raw", "dynamic"):
+    for typ in only or ("Argo_both", "static", "static_raw", "dynamic", "Argo_static", "Argo_dynamic"):
         make_e2e(typ)

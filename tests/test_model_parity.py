@@ -147,6 +147,17 @@ def test_dynamic_small(dev):
     run_case(dev, "dynamic", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
 
 
+@pytest.mark.parametrize("typ", ["static_eigen", "Argo_static", "Argo_dynamic"])
+def test_other_types_small(dev, typ):
+    """The remaining ``opt.type`` values: ``static_eigen`` (BASELINE.json config 5; neither reference net defines it — pinned to
+    depth + pose only, SURVEY.md §8 a-0 iii) and the Argoverse single-head types of /net.py:114-159 (oracle pinned by
+    tests/golden/e2e_Argo_static_1024.npz / e2e_Argo_dynamic_1024.npz)."""
+    if dev.type == "cuda":
+        pytest.skip("type dispatch is host logic; its kernels are covered on the GPU by test_full_size_gpu / test_zz_dynamic_label")
+    hw = (120, 400) if typ == "static_eigen" else (200, 240)
+    run_case(dev, typ, 128, 384, 64, 2, hw, fids=(0, -1), rel=2e-4)
+
+
 @pytest.mark.gpu
 def test_full_size_gpu_tf32():
     """The product configuration: tcgen05 TF32 convolutions.  A TF32 rounding can flip one of the network's hard

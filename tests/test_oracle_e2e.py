@@ -31,7 +31,7 @@ def _run(typ):
     return P, outs, losses, total
 
 
-@pytest.mark.parametrize("typ", ["Argo_both", "static", "static_raw", "dynamic"])
+@pytest.mark.parametrize("typ", ["Argo_both", "static", "static_raw", "dynamic", "Argo_static", "Argo_dynamic"])
 def test_port_matches_reference_run(typ):
     torch.set_num_threads(os.cpu_count() or 1)
     gold = np.load(os.path.join(GOLDEN, f"e2e_{typ}_1024.npz"))
@@ -53,6 +53,8 @@ def test_port_matches_reference_run(typ):
             got = sample(outs[name])
             assert np.max(np.abs(got - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref))), key
     gtol = 2e-4 if typ == "Argo_both" else 2e-3  # static*: the pinned ">= 1-2^-20" mask test moves scale_loss by ~1e-5
+    if typ == "Argo_static":   # Argoverse geometry puts more of the mask edge inside the frame: scale_loss (the only term that
+        gtol = 5e-3            # differs) moves by 7e-4 of its value at s=2, the depth-decoder gradients by 2.7e-3
     for k in GRAD_KEYS:
         g = P[k].grad
         ref = gold["grad/" + k]

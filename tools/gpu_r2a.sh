@@ -1,0 +1,40 @@
+#!/bin/bash
+# Round 2, first GPU call (1 GPU, ~12 min of box time): first on-device run of everything written after the round-1 GPU budget
+# was spent, and the A/B of the opt-in kernel variants against the measured defaults.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_r2a.sh'
+# Outputs land in gpurun_out/ (copy what is to be judged into profiles/ as r2_*).
+mkdir -p gpurun_out
+# 1. the whole GPU suite WITHOUT -x, so that one failing first-run case does not hide the others
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+grep -E "passed|failed|FAILED|ERROR|pytest exit" gpurun_out/pytest_gpu.log | tail -15
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+# 2. photometric forward: measured default (2) vs packed fp32 pairs (3), B = 4 and 8
+for v in 2 3; do for b in 4 8; do
+  timeout 120 python tools/bench_photometric.py --B $b --variant $v > gpurun_out/photo_v${v}_b${b}.json 2> gpurun_out/photo_v${v}_b${b}.err
+  python -c "
+import json; d=json.load(open('gpurun_out/photo_v${v}_b${b}.json')); print('photometric variant', d['fwd_variant'], 'B', d['B'], 'fwd ms', round(d['fwd_ms'],4), 'frac', round(d['fwd_frac'],4), 'bwd ms', round(d['bwd_ms'],4))"
+done; done
+# 3. the memory-bound network kernels (BatchNorm, max-pool), with the opt-in pool schedules if present
+timeout 200 python tools/bench_misc.py > gpurun_out/misc_default.txt 2>&1; tail -12 gpurun_out/misc_default.txt
+if grep -q JPB_POOL_VARIANT jperceiver_b200/_lib.py 2>/dev/null; then
+  JPB_POOL_VARIANT=1 timeout 200 python tools/bench_misc.py > gpurun_out/misc_pool1.txt 2>&1; grep -i pool gpurun_out/misc_pool1.txt | tail -6
+fi
+# 4. the bench line with the default kernels, then with the packed photometric forward
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+JPB_PHOTO_FWD=3 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_photo3.json 2> gpurun_out/bench_n1_photo3.err
+python - <<'EOF'
+import json
+for f in ("gpurun_out/bench_n1.json", "gpurun_out/bench_n1_photo3.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, round(d["value"], 2), "img/s", round(d["ms_per_step"], 3), "ms  e2e", round(d["e2e"]["value"], 2),
+              "conv frac", round(d["roofline"]["frac"], 4), "photo frac", round(d["roofline_photometric"]["frac"], 4))
+    except Exception as e:   # noqa: BLE001
+        print(f, "unreadable:", e)
+EOF
+# 5. evidence: ncu --set full of the packed photometric forward (scale 0) and the launch list of one eager step
+JPB_PHOTO_FWD=3 timeout 300 ncu --set full --clock-control none --import-source on -k regex:photometric_fwd -s 4 -c 1 -o gpurun_out/ncu_photo_v3 -f \
+  python tools/bench_photometric.py --B 4 --iters 2 > gpurun_out/ncu_photo_v3.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step.csv \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_bench.log 2>&1
+ls -la gpurun_out | tail -20
