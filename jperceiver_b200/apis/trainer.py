@@ -285,8 +285,10 @@ class TrainEngine:
 
 def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=False, validate=False, logger=None):
     """``mono.apis.train_mono`` (trainer.py:58-73, 146-199): build the runner, register the config's hooks, resume / load,
-    run ``cfg.total_epochs``.  ``dataset_train`` must yield collated batch dicts (the datasets and loaders themselves are
-    outside this path's scope).  ``validate=True`` registers the device-side ``DistEvalMonoHook`` over ``dataset_val`` every
+    run ``cfg.total_epochs``.  ``dataset_train`` is a map-style dataset with a ``flag`` array (what ``get_dataset`` returns): it
+    is wrapped by ``build_dataloader(dataset, cfg.imgs_per_gpu, cfg.workers_per_gpu, dist=distributed)`` exactly as
+    ``_dist_train`` / ``_non_dist_train`` do (trainer.py:148-151, 202-208) — epoch-seeded, group-pure, one contiguous slice of
+    the plan per rank; an iterable of already collated batch dicts is used as it is.  ``validate=True`` registers the device-side ``DistEvalMonoHook`` over ``dataset_val`` every
     ``cfg.validate_interval`` epochs (trainer.py:186-190)."""
     from .runner import Runner
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -300,5 +302,12 @@ def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=Fa
         runner.resume(cfg.resume_from)
     elif cfg.get("load_from"):
         runner.load_checkpoint(cfg.load_from)
-    runner.run([dataset_train], cfg.get("workflow", [("train", 1)]), cfg.get("total_epochs", 1))
+    loader = dataset_train
+    if hasattr(dataset_train, "__getitem__") and hasattr(dataset_train, "flag"):
+        from ..datasets.loader import build_dataloader
+        gpus = cfg.get("gpus", [0])
+        loader = build_dataloader(dataset_train, cfg.imgs_per_gpu, cfg.get("workers_per_gpu", 0),
+                                  num_gpus=1 if distributed else max(len(gpus) if hasattr(gpus, "__len__") else int(gpus), 1),
+                                  dist=distributed)
+    runner.run([loader], cfg.get("workflow", [("train", 1)]), cfg.get("total_epochs", 1))
     return runner.engine

@@ -112,3 +112,39 @@ def _view_of(r, name):
     names = [n for n, p in r.model.named_parameters() if p.requires_grad]
     i = names.index(name)
     return r.engine.flat.views[i][0], r.engine.flat.params[i]
+
+
+class TinySnippets(torch.utils.data.Dataset):
+    """A map-style dataset with the ``flag`` array the group samplers need (mono_dataset.py sets it to zeros)."""
+
+    def __init__(self, n):
+        import numpy as np
+        self.flag = np.zeros(n, dtype=np.int64)
+        g = torch.Generator().manual_seed(3)
+        self.x = torch.randn(n, 3, 8, 8, generator=g)
+
+    def __len__(self):
+        return len(self.flag)
+
+    def __getitem__(self, i):
+        return {"x": self.x[int(i)], "idx": int(i)}
+
+
+def test_runner_epochs_follow_the_sampler_plan(tmp_path):
+    """``build_dataloader`` + ``Runner.train_epoch``: the epoch is handed to the sampler (DistSamplerSeedHook), each epoch visits
+    the plan of ``DistributedGroupSampler`` for that epoch."""
+    from jperceiver_b200.datasets import build_dataloader
+    ds = TinySnippets(9)
+    loader = build_dataloader(ds, 2, 0, dist=True)          # no process group: rank 0 of 1
+    seen = []
+    model = Tiny()
+    fwd = model.forward
+    model.forward = lambda inputs: (seen.append(inputs["idx"].tolist()), fwd(inputs))[1]
+    runner = Runner(model, dict(type="Adam", lr=1e-3, weight_decay=0), None, str(tmp_path))
+    runner.register_training_hooks(dict(policy="step", step=[50]), None, None, None)
+    runner.run([loader], [("train", 1)], 2)
+    assert runner.iter == 10 and len(seen) == 10            # 9 -> 10 padded snippets, 5 steps per epoch
+    for epoch in (0, 1):
+        plan = loader.sampler.plan(epoch)[0].reshape(-1, 2).tolist()
+        assert seen[5 * epoch:5 * epoch + 5] == plan
+    assert seen[:5] != seen[5:]
