@@ -200,6 +200,22 @@ def run_ours(args):
         if name in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
             conv_flops += 2.0 * tag[0] * tag[1] * tag[2] * len(evs) / prof_steps
             conv_ms += sum(a.elapsed_time(b) for a, b in evs) / prof_steps
+    # the same launches against the tighter of their two rooflines: per launch max(FLOPs / tensor peak,
+    # minimum bytes / HBM peak) with minimum bytes = output + weights + input read once (input taken as M*K/kh^2 elements: a lower
+    # bound for strided / concatenated layers, so the fraction below is not flattered)
+    conv_bound_ms = None
+    try:
+        pk0, _ = peaks()
+        tot = 0.0
+        for (name, tag), evs in JF.PROFILE_DETAIL.items():
+            if name in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
+                M_, N_, K_, kh_ = float(tag[0]), float(tag[1]), float(tag[2]), float(max(int(tag[3]), 1))
+                t_tensor = 2.0 * M_ * N_ * K_ / (pk0["bf16_tflops"] / 2.0 * 1e12)
+                t_hbm = 4.0 * (M_ * N_ + N_ * K_ + M_ * K_ / (kh_ * kh_)) / (pk0["hbm_gbs"] * 1e9)
+                tot += max(t_tensor, t_hbm) * 1e3 * len(evs) / prof_steps
+        conv_bound_ms = tot
+    except Exception as e:   # noqa: BLE001  (an extra figure must never cost the bench line)
+        sys.stderr.write("bench: per-kernel conv bound not computed (%r)\n" % (e,))
     for v in kern.values():
         v["ms_per_step"] = v["ms_total"] / prof_steps
         v["launches_per_step"] = v["launches"] // prof_steps
@@ -279,6 +295,8 @@ def run_ours(args):
                      "frac": (conv_flops / (conv_ms * 1e-3) / 1e12) / (pk["bf16_tflops"] / 2.0) if conv_ms else None,
                      "traffic": None, "peak_source": pk_src + " bf16 dense peak / 2 (kind::tf32 issues at half the bf16 rate)",
                      "algorithmic_flops_per_step": conv_flops, "ms_per_step": conv_ms,
+                     "per_kernel_bound_ms_per_step": conv_bound_ms,
+                     "frac_of_per_kernel_bound": (conv_bound_ms / conv_ms) if (conv_bound_ms and conv_ms) else None,
                      "share_of_step": conv_ms / ms_step if conv_ms else None},
         # the kernel BASELINE.json names: fused photometric loss, forward, one launch per scale
         "roofline_photometric": {"kernel": "photometric_fwd_kernel (mean over the 4 scale launches)", "bound": "hbm", "achieved": achieved,
