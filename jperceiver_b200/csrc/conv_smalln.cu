@@ -38,7 +38,7 @@ __device__ __forceinline__ float small_act(float v, int act) {
   return v;
 }
 
-#ifdef JPB_HOST_EMU
+#if defined(JPB_HOST_EMU) && !defined(JPB_HOST_EMU_MT)
 #define SM_LANES 1
 #define SM_LANE 0
 #define SM_WARPS 1
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) smalln_project_kernel(const float* x, con
         acc[j] += v.x * wj[0] + v.y * wj[1] + v.z * wj[2] + v.w * wj[3];
       }
     }
-#ifndef JPB_HOST_EMU
+#if !defined(JPB_HOST_EMU) || defined(JPB_HOST_EMU_MT)
     for (int j = 0; j < NT; ++j)
       for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
 #endif

@@ -7,6 +7,10 @@
 // logic in the GPU-less container.  The emulation build is test infrastructure only: the product
 // library (libjpb200.so) is never built with JPB_HOST_EMU and the Python package never loads the
 // emulation library.  tcgen05/TMA kernels are excluded from the emulation build.
+// With -DJPB_HOST_EMU_MT on top (tests/emu, C++20) a block runs with its REAL thread count: one OS thread per CUDA
+// thread, __syncthreads / __syncwarp are barriers, warp shuffles exchange through a per-warp buffer, atomics are
+// serialised — so block-level synchronisation, shuffle reductions and shared-memory indexing are exercised too
+// (blocks still run one after the other).  Slow: small cases only.
 #pragma once
 
 #include <stdint.h>
@@ -20,7 +24,25 @@
 #include <vector>
 struct jpb_dim3 { unsigned x, y, z; jpb_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 typedef jpb_dim3 dim3;
-static jpb_dim3 threadIdx(0, 0, 0), blockIdx(0, 0, 0), blockDim(1, 1, 1), gridDim(1, 1, 1);
+#ifdef JPB_HOST_EMU_MT
+#include <barrier>
+#include <memory>
+#include <mutex>
+#include <thread>
+// inline variables: ONE instance for all translation units of the emulation library (the inline helpers below are merged
+// across translation units by the linker and must all see the same state)
+inline thread_local jpb_dim3 threadIdx(0, 0, 0);
+inline jpb_dim3 blockIdx(0, 0, 0), blockDim(1, 1, 1), gridDim(1, 1, 1);
+struct JpbEmuBlock {   // synchronisation state of the block that is running
+  std::unique_ptr<std::barrier<>> block;
+  std::vector<std::unique_ptr<std::barrier<>>> warp;
+  std::vector<unsigned long long> xchg;   // [warp][32] shuffle exchange slots
+  std::mutex atomics;
+};
+inline JpbEmuBlock jpb_emu_blk;
+#else
+inline jpb_dim3 threadIdx(0, 0, 0), blockIdx(0, 0, 0), blockDim(1, 1, 1), gridDim(1, 1, 1);
+#endif
 typedef void* cudaStream_t;
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
@@ -33,15 +55,42 @@ static inline float2 make_float2(float x, float y) { float2 v = {x, y}; return v
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)
+#ifdef JPB_HOST_EMU_MT
+#define __syncthreads() jpb_emu_blk.block->arrive_and_wait()
+#define __syncwarp() jpb_emu_blk.warp[threadIdx.x >> 5]->arrive_and_wait()
+template <typename T>
+static inline T jpb_emu_shfl(T v, int src_lane) {   // every live lane of the warp calls it (full-mask shuffles only)
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* slot = &jpb_emu_blk.xchg[(size_t)w * 32];
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  slot[lane] = bits;
+  jpb_emu_blk.warp[w]->arrive_and_wait();
+  T r = v;
+  if (src_lane >= 0 && src_lane < 32 && w * 32 + src_lane < (int)blockDim.x) memcpy(&r, &slot[src_lane], sizeof(T));
+  jpb_emu_blk.warp[w]->arrive_and_wait();
+  return r;
+}
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int o) { const int l = (threadIdx.x & 31) + o; return jpb_emu_shfl(v, l < 32 ? l : -1); }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return jpb_emu_shfl(v, (int)((threadIdx.x & 31) ^ m)); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int l) { return jpb_emu_shfl(v, l & 31); }
+#else
 #define __syncthreads() ((void)0)
 #define __syncwarp() ((void)0)
+#endif
 #define __threadfence() ((void)0)
 #define __ldg(p) (*(p))
-static std::vector<unsigned char> jpb_emu_dynsmem;
+inline std::vector<unsigned char> jpb_emu_dynsmem;
 #define JPB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(jpb_emu_dynsmem.data())
-template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = o + (T)v; return o; }
-static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
-static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+#ifdef JPB_HOST_EMU_MT
+#define JPB_EMU_ATOMIC_GUARD std::lock_guard<std::mutex> jpb_emu_guard_(jpb_emu_blk.atomics)
+#else
+#define JPB_EMU_ATOMIC_GUARD ((void)0)
+#endif
+template <typename T, typename U> static inline T atomicAdd(T* p, U v) { JPB_EMU_ATOMIC_GUARD; T o = *p; *p = o + (T)v; return o; }
+static inline int atomicMax(int* p, int v) { JPB_EMU_ATOMIC_GUARD; int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int* p, int v) { JPB_EMU_ATOMIC_GUARD; int o = *p; if (v < o) *p = v; return o; }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define __expf expf
@@ -54,6 +103,40 @@ static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); re
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 using std::max;
 using std::min;
+#ifdef JPB_HOST_EMU_MT
+// one OS thread per CUDA thread of the block; a thread that returns from the kernel leaves the barriers (as an exited
+// CUDA thread no longer takes part in bar.sync)
+template <typename Body>
+static inline void jpb_emu_run_block(unsigned nthreads, Body body) {
+  const unsigned nwarps = (nthreads + 31) / 32;
+  jpb_emu_blk.block.reset(new std::barrier<>(nthreads));
+  jpb_emu_blk.warp.clear();
+  for (unsigned w = 0; w < nwarps; ++w) jpb_emu_blk.warp.emplace_back(new std::barrier<>(std::min(32u, nthreads - 32 * w)));
+  jpb_emu_blk.xchg.assign((size_t)nwarps * 32, 0ull);
+  std::vector<std::thread> pool;
+  pool.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    pool.emplace_back([t, &body]() {
+      threadIdx = jpb_dim3(t, 0, 0);
+      body();
+      jpb_emu_blk.warp[t >> 5]->arrive_and_drop();
+      jpb_emu_blk.block->arrive_and_drop();
+    });
+  for (auto& th : pool) th.join();
+}
+#define JPB_LAUNCH(kernel, grid, block, smem, stream, ...)                                         \
+  do {                                                                                             \
+    jpb_dim3 g_ = (grid), b_ = (block);                                                            \
+    if (jpb_emu_dynsmem.size() < (size_t)(smem) + 16) jpb_emu_dynsmem.resize((size_t)(smem) + 16); \
+    gridDim = g_; blockDim = jpb_dim3(b_.x * b_.y * b_.z, 1, 1);                                   \
+    for (unsigned bz_ = 0; bz_ < g_.z; ++bz_)                                                      \
+      for (unsigned by_ = 0; by_ < g_.y; ++by_)                                                    \
+        for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) {                                                \
+          blockIdx = jpb_dim3(bx_, by_, bz_);                                                      \
+          jpb_emu_run_block(blockDim.x, [&]() { kernel(__VA_ARGS__); });                           \
+        }                                                                                          \
+  } while (0)
+#else
 #define JPB_LAUNCH(kernel, grid, block, smem, stream, ...)                                         \
   do {                                                                                             \
     jpb_dim3 g_ = (grid);                                                                          \
@@ -66,6 +149,7 @@ using std::min;
           kernel(__VA_ARGS__);                                                                     \
         }                                                                                          \
   } while (0)
+#endif
 #define JPB_LAST_ERROR() 0
 #else
 // ------------------------------------------------------------------ CUDA build
@@ -91,7 +175,7 @@ static inline int jpb_status() { int e = JPB_LAST_ERROR(); return e == 0 ? JPB_O
 // gets the total (other threads get a partial they must not use).
 template <typename T>
 __device__ __forceinline__ T jpb_block_sum(T v, T* scratch) {
-#ifdef JPB_HOST_EMU
+#if defined(JPB_HOST_EMU) && !defined(JPB_HOST_EMU_MT)
   (void)scratch;
   return v;
 #else

@@ -20,18 +20,26 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build")
 EXCLUDE = ("conv_tc.cu", "tma_util.cu")
 
 
-def build_emulation() -> str:
+def build_emulation(mt: bool | None = None) -> str:
+    """``mt=False``: one "thread" per block (fast; kernel arithmetic and indexing).  ``mt=True``: ``-DJPB_HOST_EMU_MT`` — every
+    block runs with its real thread count on OS threads with real barriers / shuffles (slow; synchronisation and reductions)."""
+    if mt is None:   # JPB_EMU_MT=1 python -m pytest tests/<file> -m "not gpu": any emulation suite with real block threads
+        mt = os.environ.get("JPB_EMU_MT", "0") not in ("", "0")
     os.makedirs(OUT, exist_ok=True)
     srcs = [s for s in sorted(glob.glob(os.path.join(CSRC, "*.cu"))) if os.path.basename(s) not in EXCLUDE]
     h = hashlib.sha256()
     for p in srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "jpb200.h")]:
         h.update(open(p, "rb").read())
-    lib = os.path.join(OUT, "libjpb200_emu_%s.so" % h.hexdigest()[:12])
+    stem = "libjpb200_emt_" if mt else "libjpb200_emu_"
+    lib = os.path.join(OUT, stem + "%s.so" % h.hexdigest()[:12])
     if os.path.exists(lib):
         return lib
-    for old in glob.glob(os.path.join(OUT, "libjpb200_emu_*.so")):
+    for old in glob.glob(os.path.join(OUT, stem + "*.so")):
         os.remove(old)
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DJPB_HOST_EMU", "-Wno-unused-variable", "-Wno-unused-function", "-o", lib]
+    if mt:
+        cmd[2] = "-std=c++20"
+        cmd += ["-DJPB_HOST_EMU_MT", "-pthread"]
     for s in srcs:
         cmd += ["-x", "c++", s]
     r = subprocess.run(cmd, capture_output=True, text=True)
