@@ -30,13 +30,17 @@ def build_emulation(mt: bool | None = None) -> str:
     h = hashlib.sha256()
     for p in srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "jpb200.h")]:
         h.update(open(p, "rb").read())
+    h.update(b"flags-v2")
     stem = "libjpb200_emt_" if mt else "libjpb200_emu_"
     lib = os.path.join(OUT, stem + "%s.so" % h.hexdigest()[:12])
     if os.path.exists(lib):
         return lib
     for old in glob.glob(os.path.join(OUT, stem + "*.so")):
         os.remove(old)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DJPB_HOST_EMU", "-Wno-unused-variable", "-Wno-unused-function", "-o", lib]
+    # -fno-gnu-unique / -Bsymbolic: the two emulation libraries define the same inline state (jpb_common.cuh) and may be loaded into
+    # one process; each must bind to its own copy
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fno-gnu-unique", "-Wl,-Bsymbolic", "-DJPB_HOST_EMU", "-Wno-unused-variable",
+           "-Wno-unused-function", "-o", lib]
     if mt:
         cmd[2] = "-std=c++20"
         cmd += ["-DJPB_HOST_EMU_MT", "-pthread"]
