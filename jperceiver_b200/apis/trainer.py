@@ -291,7 +291,12 @@ def train_mono(model, dataset_train, dataset_val, cfg, args=None, distributed=Fa
     the plan per rank; an iterable of already collated batch dicts is used as it is.  ``validate=True`` registers the device-side ``DistEvalMonoHook`` over ``dataset_val`` every
     ``cfg.validate_interval`` epochs (trainer.py:186-190)."""
     from .runner import Runner
-    dev = torch.device("cuda", torch.cuda.current_device())
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", torch.cuda.current_device())
+    elif _lib.is_emulated():                  # tests only: the kernels' host emulation was installed explicitly
+        dev = torch.device("cpu")
+    else:
+        raise _lib.JpbError("train_mono needs a CUDA device (there is no CPU fallback)")
     model.to(dev).train()
     runner = Runner(model, cfg.optimizer, cfg.get("optimizer_config", {}), cfg.get("work_dir"), cfg.get("log_level", "INFO"), logger)
     if validate:
