@@ -30,7 +30,7 @@ def emu():
     _lib._handle, _lib._emulated = None, False
 
 
-def _small_config(tmp_path):
+def _small_config(tmp_path, extra=""):
     """The reference's odometry config, executed as it is, with the shapes reduced and the authors' file paths removed."""
     text = open(REF_CFG).read()
     text += '''
@@ -41,7 +41,7 @@ model.update(height=HEIGHT, width=WIDTH, imgs_per_gpu=IMGS_PER_GPU, occ_map_size
              depth_pretrained_path=None, pose_pretrained_path=None)
 imgs_per_gpu, workers_per_gpu, total_epochs, validate = IMGS_PER_GPU, 0, 1, False
 log_config = dict(interval=1, hooks=[dict(type='TextLoggerHook')])
-'''
+''' + extra
     path = tmp_path / "cfg_small.py"
     path.write_text(text)
     return str(path)
@@ -73,3 +73,26 @@ def test_reference_train_py_runs_unchanged(emu, tmp_path, monkeypatch):
         assert key in lines[0] and lines[0][key] == lines[0][key], key     # present and not NaN
     keys = list(ck["state_dict"])
     assert len(keys) == 766 and keys[0].startswith("DepthEncoder.")
+
+
+def test_reference_train_py_two_ranks_gloo(tmp_path):
+    """``--launcher pytorch`` under torchrun, 2 processes (gloo instead of nccl in ``dist_params``, no GPU here): init_dist, the
+    DistributedGroupSampler plan (8 snippets -> 4 per rank -> 2 steps), the gradient all-reduce, rank-0 checkpoint and log."""
+    import socket
+    import subprocess
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    cfg = _small_config(tmp_path, "data.update(num_samples=8)\ndist_params = dict(backend='gloo')\n")
+    work = str(tmp_path / "work2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "_run_ref_train.py"), TRAIN_PY, "--config", cfg, "--work_dir", work,
+           "--launcher", "pytorch"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    ck = torch.load(os.path.join(work, "epoch_1.pth"), weights_only=False)
+    assert ck["meta"]["epoch"] == 1 and ck["meta"]["iter"] == 2
+    logs = [f for f in os.listdir(work) if f.endswith(".log.json")]
+    assert len(logs) == 1                                     # rank 0 only
+    lines = [json.loads(l) for l in open(os.path.join(work, logs[0]))]
+    assert len(lines) == 2 and all(l["loss"] == l["loss"] for l in lines)
