@@ -20,6 +20,7 @@ class SyntheticSnippets(torch.utils.data.Dataset):
     def __init__(self, cfg, training=True):
         self.opt = dict(height=int(cfg["height"]), width=int(cfg["width"]), frame_ids=list(cfg["frame_ids"]) if training else [0],
                         occ_map_size=int(cfg.get("occ_map_size", 256)), split=cfg.get("split", "odometry"))
+        self.training = bool(training)
         self.n = int(cfg.get("num_samples", 64))
         self.seed0 = int(cfg.get("seed", 1024)) + (0 if training else 1 << 20)
         self.flag = np.zeros(self.n, dtype=np.int64)
@@ -29,7 +30,13 @@ class SyntheticSnippets(torch.utils.data.Dataset):
 
     def __getitem__(self, i):
         b = synthetic.make_batch(self.opt, 1, seed=self.seed0 + int(i))
-        return {k: v[0] for k, v in b.items()}
+        d = {k: v[0] for k, v in b.items()}
+        if not self.training:      # validation items carry a ground-truth depth frame (0 = no LiDAR return), kitti_dataset.py:66-77
+            g = torch.Generator().manual_seed(self.seed0 + int(i))
+            h, w = d[("color", 0, -1)].shape[-2:]
+            depth = 2.0 + 60.0 * torch.rand(h, w, generator=g)
+            d["gt_depth"] = torch.where(torch.rand(h, w, generator=g) < 0.2, depth, torch.zeros(()))
+        return d
 
 
 def get_dataset(cfg, training=True):

@@ -39,7 +39,7 @@ HEIGHT, WIDTH, IMGS_PER_GPU = 128, 384, 2
 data.update(name='synthetic', height=HEIGHT, width=WIDTH, num_samples=4, occ_map_size=64, frame_ids=[0, -1])
 model.update(height=HEIGHT, width=WIDTH, imgs_per_gpu=IMGS_PER_GPU, occ_map_size=64, frame_ids=[0, -1],
              depth_pretrained_path=None, pose_pretrained_path=None)
-imgs_per_gpu, workers_per_gpu, total_epochs, validate = IMGS_PER_GPU, 0, 1, False
+imgs_per_gpu, workers_per_gpu, total_epochs = IMGS_PER_GPU, 0, 1          # validate = True stays, as in the reference's file
 log_config = dict(interval=1, hooks=[dict(type='TextLoggerHook')])
 ''' + extra
     path = tmp_path / "cfg_small.py"
@@ -67,7 +67,12 @@ def test_reference_train_py_runs_unchanged(emu, tmp_path, monkeypatch):
     assert os.path.exists(os.path.join(work, "latest.pth"))
     logs = [f for f in os.listdir(work) if f.endswith(".log.json")]
     lines = [json.loads(l) for l in open(os.path.join(work, logs[0]))]
-    assert len(lines) == 2 and lines[0]["lr"] == 1e-4
+    train = [l for l in lines if l["mode"] == "train"]
+    assert len(train) == 2 and train[0]["lr"] == 1e-4
+    # cfg.validate = True (the reference's setting): DistEvalMonoHook ran over the validation split after the epoch
+    val = [l for l in lines if l["mode"] == "val"]
+    assert len(val) == 1 and all(k in val[0] for k in ("abs_rel", "a1", "scale mean", "iou_road", "mAP_road")), lines
+    assert 0.0 <= val[0]["a1"] <= 1.0 and val[0]["abs_rel"] > 0.0
     for key in ("topview_loss", "transform_topview_loss", "transform_loss", "layout_loss", "loss",
                 "('min_reconstruct_loss', 0)", "('scale_loss', 3)", "('smooth_loss', 2)"):
         assert key in lines[0] and lines[0][key] == lines[0][key], key     # present and not NaN
@@ -95,4 +100,6 @@ def test_reference_train_py_two_ranks_gloo(tmp_path):
     logs = [f for f in os.listdir(work) if f.endswith(".log.json")]
     assert len(logs) == 1                                     # rank 0 only
     lines = [json.loads(l) for l in open(os.path.join(work, logs[0]))]
-    assert len(lines) == 2 and all(l["loss"] == l["loss"] for l in lines)
+    train = [l for l in lines if l["mode"] == "train"]
+    assert len(train) == 2 and all(l["loss"] == l["loss"] for l in train)
+    assert sum(l["mode"] == "val" for l in lines) == 1       # validation: sample idx on rank idx % 2, one all-reduce of the rows
