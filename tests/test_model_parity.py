@@ -221,3 +221,32 @@ def test_eval_mode_outputs_match_oracle(dev):
     for k in sd:                                   # evaluation must not touch the running statistics
         if "running" in k or "tracked" in k:
             assert torch.equal(sd[k].cpu(), P[k]), k
+
+
+def test_standalone_pose_modules_copy_weights_by_name(dev):
+    """``scripts/draw_odometry.py:49-69``: ``PoseEncoder(18, None, 2)`` / ``PoseDecoder(num_ch_enc)`` built on their own, weights
+    copied from a training checkpoint by ``'PoseEncoder.' + name`` / ``'PoseDecoder.' + name``, eval-mode forward of a
+    concatenated frame pair -> (axisangle, translation).  The state_dict key names are part of the API."""
+    if dev.type == "cuda":
+        pytest.skip("module surface is host logic; the pose kernels are covered by tests/test_heads.py and test_full_size_gpu")
+    from jperceiver_b200.model.mono_baseline.networks import PoseDecoder, PoseEncoder
+    opt = default_options(type="static", split="odometry", height=128, width=384, occ_map_size=64, frame_ids=[0, -1], imgs_per_gpu=1)
+    full = MONO.module_dict["Baseline"](opt)
+    checkpoint = {"state_dict": O.synth_params(full.state_dict(), seed=8)}
+    pose_encoder = PoseEncoder(18, None, 2)
+    pose_decoder = PoseDecoder(pose_encoder.num_ch_enc)
+    for name, param in pose_encoder.state_dict().items():
+        pose_encoder.state_dict()[name].copy_(checkpoint["state_dict"]["PoseEncoder." + name])
+    for name, param in pose_decoder.state_dict().items():
+        pose_decoder.state_dict()[name].copy_(checkpoint["state_dict"]["PoseDecoder." + name])
+    pose_encoder.to(dev).eval()
+    pose_decoder.to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    pair = torch.rand(2, 6, 192, 640, generator=g)
+    with torch.no_grad():
+        axisangle, translation = pose_decoder(pose_encoder(pair.to(dev)))
+        feats = O.resnet18_features(checkpoint["state_dict"], "PoseEncoder.encoder", pair, False)
+        aa, t = O.pose_decoder(checkpoint["state_dict"], "PoseDecoder", feats[-1])
+    assert axisangle.shape[0] == 2 and axisangle.reshape(2, -1).shape[1] == 3 and translation.reshape(2, -1).shape[1] == 3
+    assert (axisangle.reshape(2, 3).cpu() - aa).abs().max().item() <= 1e-3 * max(aa.abs().max().item(), 1e-6)
+    assert (translation.reshape(2, 3).cpu() - t).abs().max().item() <= 1e-3 * max(t.abs().max().item(), 1e-6)
