@@ -48,7 +48,8 @@ typedef struct JpbPhotoArgs {
   double* loss_sum;                /* [1] += sum over b,y,x of min over candidates                 */
   long long* min_index;            /* [B,H,W] int64 argmin (outputs[("min_index",s)]) or NULL      */
   unsigned char* winner;           /* [B,H,W] same argmin as a byte (kept for backward) or NULL    */
-  float* warped[JPB_MAX_SRC];      /* [B,3,H,W] outputs[("color",f,s)] or NULL                     */
+  float* warped[JPB_MAX_SRC];      /* [B,3,H,W] outputs[("color",f,s)] or NULL.  Forward: written.  Backward: when non-NULL, the
+                                      frames the forward of this scale wrote are staged instead of being re-projected          */
 } JpbPhotoArgs;
 
 typedef struct JpbPhotoGrad {

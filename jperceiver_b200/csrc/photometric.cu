@@ -718,10 +718,15 @@ __global__ void __launch_bounds__(256) photometric_bwd_kernel(JpbPhotoArgs a, Jp
     float rc[3];
     pixel_ray(a.invK + b * 16, x, y, rc);
     for (int f = 0; f < F; ++f) {
-      Sample s;
-      project(geom[f], z, rc, W, H, s);
       float v[3];
-      gather3(a.src[f] + (size_t)b * 3 * plane, H, W, s, v);
+      if (a.warped[f]) {   // the forward launch of this scale kept its warped frame (outputs[("color",f,s)]): stage it as it is
+        const float* wv = a.warped[f] + (size_t)b * 3 * plane + o;
+        v[0] = wv[0]; v[1] = wv[plane]; v[2] = wv[2 * plane];
+      } else {
+        Sample s;
+        project(geom[f], z, rc, W, H, s);
+        gather3(a.src[f] + (size_t)b * 3 * plane, H, W, s, v);
+      }
       float* d = s_wp + f * 3 * P2_N + e;
       d[0] = v[0]; d[P2_N] = v[1]; d[2 * P2_N] = v[2];
     }

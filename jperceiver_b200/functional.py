@@ -4,6 +4,7 @@ happens in ``libjpb200.so``."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -96,6 +97,8 @@ class _Photometric(torch.autograd.Function):
         if cfg["debug_outputs"]:
             min_index = torch.empty(B, H, W, dtype=torch.int64, device=dev)
             a.min_index = ptr(min_index)
+        keep = bool(cfg.get("keep_warped", False)) and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[5 + F:5 + 2 * F]))
+        if cfg["debug_outputs"] or keep:
             for i in range(F):
                 w = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
                 warped.append(w)
@@ -105,7 +108,8 @@ class _Photometric(torch.autograd.Function):
         loss = finalize(acc, 1.0 / (B * H * W * cfg["num_scales"])).reshape(())
         ctx.cfg = cfg
         ctx.noises = noises
-        ctx.save_for_backward(disp_c, K, invK, target, winner, *sources, *Ts)
+        ctx.kept = len(warped) if keep else 0
+        ctx.save_for_backward(disp_c, K, invK, target, winner, *sources, *Ts, *(warped if keep else []))
         ctx.mark_non_differentiable(winner)
         outs = [loss, winner]
         if cfg["debug_outputs"]:
@@ -122,6 +126,8 @@ class _Photometric(torch.autograd.Function):
         B, _, H, W = target.shape
         a = _photo_args(disp, target, sources, Ts, ctx.noises, K, invK, cfg["automask"], cfg["min_depth"],
                         cfg["max_depth"], cfg["noise_scale"], cfg["seed"], cfg["stream"])
+        for i, w in enumerate(ctx.saved_tensors[5 + 2 * F:5 + 2 * F + ctx.kept]):
+            a.warped[i] = ptr(w)          # phase A of the backward stages these instead of re-projecting the apron
         g = PhotoGrad()
         gl = _f32c(gloss).reshape(1)
         gdisp = torch.zeros_like(disp)
@@ -135,15 +141,20 @@ class _Photometric(torch.autograd.Function):
         return (gdisp, None, None, None, None) + (None,) * F + tuple(gT) + (None,) * n_extra
 
 
+KEEP_WARPED = os.environ.get("JPB_PHOTO_KEEP_WARPED", "0") not in ("", "0")   # opt-in until timed on a B200 (tools/gpu_r2a.sh)
+
+
 def photometric_loss(disp, target, sources, Ts, K, invK, *, num_scales=4, automask=True, min_depth=0.1,
-                     max_depth=100.0, noise=None, noise_scale=1e-5, seed=0, stream=0, step=None, debug_outputs=False):
+                     max_depth=100.0, noise=None, noise_scale=1e-5, seed=0, stream=0, step=None, debug_outputs=False,
+                     keep_warped=None):
     """``loss_dict[("min_reconstruct_loss", s)]`` of one scale (already divided by ``num_scales``).
 
     Returns ``(loss, winner_u8, min_index|None, [warped...])``.  ``noise``: list of B×H×W tensors for the
     identity terms (tests) or None for the in-kernel Philox draw scaled by ``noise_scale``.
     """
     cfg = dict(F=len(sources), num_scales=num_scales, automask=automask, min_depth=min_depth, max_depth=max_depth,
-               noise_scale=noise_scale, seed=seed, stream=stream, step=step, debug_outputs=debug_outputs)
+               noise_scale=noise_scale, seed=seed, stream=stream, step=step, debug_outputs=debug_outputs,
+               keep_warped=KEEP_WARPED if keep_warped is None else bool(keep_warped))
     rest = list(sources) + list(Ts) + (list(noise) if noise is not None else [])
     out = _Photometric.apply(disp, K, invK, target, cfg, *rest)
     loss, winner = out[0], out[1]

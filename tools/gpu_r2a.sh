@@ -14,6 +14,12 @@ for v in 2 3; do for b in 4 8; do
   python -c "
 import json; d=json.load(open('gpurun_out/photo_v${v}_b${b}.json')); print('photometric variant', d['fwd_variant'], 'B', d['B'], 'fwd ms', round(d['fwd_ms'],4), 'frac', round(d['fwd_frac'],4), 'bwd ms', round(d['bwd_ms'],4))"
 done; done
+# 2b. photometric backward staging the forward's warped frames (opt-in JPB_PHOTO_KEEP_WARPED=1): compare bwd_ms with 2. above
+for b in 4 8; do
+  JPB_PHOTO_KEEP_WARPED=1 timeout 120 python tools/bench_photometric.py --B $b --variant 2 > gpurun_out/photo_keep_b${b}.json 2> gpurun_out/photo_keep_b${b}.err
+  python -c "
+import json; d=json.load(open('gpurun_out/photo_keep_b${b}.json')); print('photometric keep-warped B', d['B'], 'fwd ms', round(d['fwd_ms'],4), 'bwd ms', round(d['bwd_ms'],4))"
+done
 # 3. the memory-bound network kernels (BatchNorm, max-pool), with the opt-in pool schedules if present
 timeout 200 python tools/bench_misc.py > gpurun_out/misc_default.txt 2>&1; tail -12 gpurun_out/misc_default.txt
 if grep -q JPB_POOL_VARIANT jperceiver_b200/_lib.py 2>/dev/null; then
@@ -22,9 +28,10 @@ fi
 # 4. the bench line with the default kernels, then with the packed photometric forward
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 JPB_PHOTO_FWD=3 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_photo3.json 2> gpurun_out/bench_n1_photo3.err
+JPB_PHOTO_KEEP_WARPED=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_keep.json 2> gpurun_out/bench_n1_keep.err
 python - <<'EOF'
 import json
-for f in ("gpurun_out/bench_n1.json", "gpurun_out/bench_n1_photo3.json"):
+for f in ("gpurun_out/bench_n1.json", "gpurun_out/bench_n1_photo3.json", "gpurun_out/bench_n1_keep.json"):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, round(d["value"], 2), "img/s", round(d["ms_per_step"], 3), "ms  e2e", round(d["e2e"]["value"], 2),
