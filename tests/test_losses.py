@@ -60,9 +60,9 @@ def _photo_case(B=2, H=24, W=40, s=0, F=2, seed=0):
 @pytest.fixture(params=[2, 3], ids=["fwd2", "fwd3"])
 def photo_variant(request, dev):
     """Both forward schedules of the fused photometric kernel (include/jpb200.h: jpb_photometric_set_variant).  The packed
-    one is opt-in until it has been measured; its GPU parity cases live in tests/test_zz_photometric_packed.py (sorted last)."""
+    one is opt-in until it has been measured; its GPU parity cases live in tests/test_zzy_photometric_packed.py (sorted last)."""
     if request.param == 3 and dev.type == "cuda":
-        pytest.skip("packed schedule on the GPU: tests/test_zz_photometric_packed.py")
+        pytest.skip("packed schedule on the GPU: tests/test_zzy_photometric_packed.py")
     _lib.check(_lib.lib().jpb_photometric_set_variant(request.param), "jpb_photometric_set_variant")
     yield request.param
     _lib.check(_lib.lib().jpb_photometric_set_variant(2), "jpb_photometric_set_variant")
@@ -129,7 +129,7 @@ def test_photometric_single_source_and_inkernel_noise(dev, photo_variant):
 def test_photometric_variants_agree(dev):
     """The packed forward schedule reproduces the default one: same arg-min except at fp32 ties, same loss to 1e-6 relative."""
     if dev.type == "cuda":
-        pytest.skip("packed schedule on the GPU: tests/test_zz_photometric_packed.py")
+        pytest.skip("packed schedule on the GPU: tests/test_zzy_photometric_packed.py")
     target, sources, disp, K, invK, Ts = _photo_case(B=2, H=64, W=96, s=1, seed=11)
     args = (D(disp, dev), D(target, dev), D(sources, dev), D(Ts, dev), D(K, dev), D(invK, dev))
     out = {}
