@@ -91,3 +91,48 @@ def test_product_path_refuses_cpu_tensors_and_missing_library():
     from jperceiver_b200 import netops as ops
     with pytest.raises(_lib.JpbError):
         ops.conv2d(torch.zeros(1, 4, 8, 8), torch.zeros(4, 4, 3, 3), pad=1)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every argument struct of include/jpb200.h against its ctypes mirror in jperceiver_b200/_lib.py: same size, same number of
+    members, same offset and size per member (compiled with gcc from the header itself).  Guards the structs that no CPU test can
+    exercise (the tcgen05 convolution arguments)."""
+    import ctypes as C
+    import re
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "jpb200.h")
+    text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    structs = {}
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", text, flags=re.S):
+        names = []
+        for decl in m.group(2).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.search(r"(\w+)\s*(\[[^\]]*\])*\s*$", first).group(1))
+            names += [re.search(r"(\w+)", r).group(1) for r in rest]
+        structs[m.group(3)] = names
+    mirror = {"JpbPhotoArgs": _lib.PhotoArgs, "JpbPhotoGrad": _lib.PhotoGrad, "JpbPyramid": _lib.Pyramid, "JpbScaleLabelArgs": _lib.ScaleLabelArgs,
+              "JpbScaleLossArgs": _lib.ScaleLossArgs, "JpbBevArgs": _lib.BevArgs, "JpbConvArgs": _lib.ConvArgs, "JpbConvWgradArgs": _lib.ConvWgradArgs,
+              "JpbWeightT": _lib.WeightT, "JpbDepthEvalArgs": _lib.DepthEvalArgs, "JpbResizeArgs": _lib.ResizeArgs, "JpbJitterArgs": _lib.JitterArgs,
+              "JpbAdamArgs": _lib.AdamArgs}
+    assert set(mirror) == set(structs), (sorted(set(structs) ^ set(mirror)))
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % hdr, "int main(void) {"]
+    for name, fields in structs.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in fields:
+            src.append('printf("%s.%s %%zu %%zu\\n", offsetof(%s, %s), sizeof(((%s*)0)->%s));' % (name, f, name, f, name, f))
+    src += ["return 0;", "}"]
+    cfile, exe = str(tmp_path / "layout.c"), str(tmp_path / "layout")
+    open(cfile, "w").write("\n".join(src))
+    subprocess.run(["gcc", "-o", exe, cfile], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    layout = {l.split()[0]: tuple(int(v) for v in l.split()[1:]) for l in out if l.strip()}
+    for name, cls in mirror.items():
+        assert C.sizeof(cls) == layout[name][0], (name, C.sizeof(cls), layout[name])
+        assert len(cls._fields_) == len(structs[name]), (name, [f[0] for f in cls._fields_], structs[name])
+        for (pyname, *_), cname in zip(cls._fields_, structs[name]):
+            d = getattr(cls, pyname)
+            assert (d.offset, d.size) == layout["%s.%s" % (name, cname)], (name, pyname, cname, d.offset, d.size, layout["%s.%s" % (name, cname)])
