@@ -210,7 +210,7 @@ def run_ours(args):
         for (name, tag), evs in JF.PROFILE_DETAIL.items():
             if name in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
                 M_, N_, K_, kh_ = float(tag[0]), float(tag[1]), float(tag[2]), float(max(int(tag[3]), 1))
-                t_tensor = 2.0 * M_ * N_ * K_ / (pk0["bf16_tflops"] / 2.0 * 1e12)
+                t_tensor = 2.0 * M_ * N_ * K_ / (pk0.get("bf16_tflops_sustained", pk0["bf16_tflops"]) / 2.0 * 1e12)
                 t_hbm = 4.0 * (M_ * N_ + N_ * K_ + M_ * K_ / (kh_ * kh_)) / (pk0["hbm_gbs"] * 1e9)
                 tot += max(t_tensor, t_hbm) * 1e3 * len(evs) / prof_steps
         conv_bound_ms = tot
@@ -264,6 +264,9 @@ def run_ours(args):
         _finish(world)
         return
     pk, pk_src = peaks()
+    # the convolutions are timed inside a long step: their denominator is the SUSTAINED tensor figure when the driver measured one
+    tf32_peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2.0
+    tf32_src = pk_src + (" sustained" if "bf16_tflops_sustained" in pk else "") + " bf16 dense peak / 2 (kind::tf32 issues at half the bf16 rate)"
     ms_step = ms / args.steps
     value = B * world / (ms_step / 1e3)
     e2e_value = B * world / (ms_e2e / args.steps / 1e3)
@@ -291,9 +294,9 @@ def run_ours(args):
         "roofline": {"kernel": "conv_tc_fwd / conv_tc_fwd2 / conv_tc_wgrad (tcgen05 kind::tf32, all %d launches of a step)"
                                % sum(kern.get(k, {}).get("launches_per_step", 0) for k in ("conv_fwd", "conv_dgrad", "conv_wgrad")),
                      "bound": "tensor", "achieved": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
-                     "peak": pk["bf16_tflops"] / 2.0, "unit": "TFLOP/s",
-                     "frac": (conv_flops / (conv_ms * 1e-3) / 1e12) / (pk["bf16_tflops"] / 2.0) if conv_ms else None,
-                     "traffic": None, "peak_source": pk_src + " bf16 dense peak / 2 (kind::tf32 issues at half the bf16 rate)",
+                     "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": (conv_flops / (conv_ms * 1e-3) / 1e12) / tf32_peak if conv_ms else None,
+                     "traffic": None, "peak_source": tf32_src,
                      "algorithmic_flops_per_step": conv_flops, "ms_per_step": conv_ms,
                      "per_kernel_bound_ms_per_step": conv_bound_ms,
                      "frac_of_per_kernel_bound": (conv_bound_ms / conv_ms) if (conv_bound_ms and conv_ms) else None,
