@@ -11,7 +11,12 @@ Contents
                    reference file:line it follows.  This is what travels to the GPU box.
 ``ref_loader.py``  Imports the reference's *own* modules from ``/root/reference`` under an
                    import shim (authoring container only; the GPU box has no reference).
-``make_golden.py`` Runs the real reference and writes ``tests/golden/*.npz`` fixtures.
+``make_golden.py`` Runs the real reference and writes ``tests/golden/*.npz`` fixtures (KAT vectors, one full
+                   forward+backward run per ``opt.type``).
+``make_golden_bev.py`` / ``make_golden_eval.py`` / ``make_golden_pipeline.py`` / ``make_golden_sampler.py``
+                   The same for the BEV loss variants, the validation metrics (``pixel_error.py``),
+                   ``MonoDataset.preprocess`` and the samplers' index sequences.
+``eval_port.py`` / ``pipeline_port.py``  Restatements of the validation-hook body and of ``preprocess``.
 
 Parity status: the reference ships no tests or golden vectors.  The port is pinned against
 (a) outputs of the reference itself executed here through ``ref_loader`` (fixtures committed
