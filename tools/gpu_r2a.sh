@@ -20,11 +20,8 @@ for b in 4 8; do
   python -c "
 import json; d=json.load(open('gpurun_out/photo_keep_b${b}.json')); print('photometric keep-warped B', d['B'], 'fwd ms', round(d['fwd_ms'],4), 'bwd ms', round(d['bwd_ms'],4))"
 done
-# 3. the memory-bound network kernels (BatchNorm, max-pool), with the opt-in pool schedules if present
+# 3. the memory-bound network kernels (BatchNorm, max-pool): achieved GB/s per call at the step's largest shapes
 timeout 200 python tools/bench_misc.py > gpurun_out/misc_default.txt 2>&1; tail -12 gpurun_out/misc_default.txt
-if grep -q JPB_POOL_VARIANT jperceiver_b200/_lib.py 2>/dev/null; then
-  JPB_POOL_VARIANT=1 timeout 200 python tools/bench_misc.py > gpurun_out/misc_pool1.txt 2>&1; grep -i pool gpurun_out/misc_pool1.txt | tail -6
-fi
 # 4. the bench line with the default kernels, then with the packed photometric forward
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 JPB_PHOTO_FWD=3 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_photo3.json 2> gpurun_out/bench_n1_photo3.err
