@@ -158,6 +158,15 @@ def test_other_types_small(dev, typ):
     run_case(dev, typ, 128, 384, 64, 2, hw, fids=(0, -1), rel=2e-4)
 
 
+def test_baseline_config0_b1_192x640(dev):
+    """BASELINE.json configs[0] — ``cfg_kitti_baseline_odometry_boundary_ce_iou_1024_20_B1``: one 192x640 3-frame snippet (B=1: the
+    reference's ``shape[0]==256`` squeeze hack in compute_topview_loss, net.py:557-559), occ_map_size 256, type static, full
+    375x1242 frame for the CGT label; forward + losses + backward against the oracle."""
+    if dev.type == "cuda":
+        pytest.skip("B=1 plumbing case; the GPU parity cases run at the bench shape (test_full_size_gpu)")
+    run_case(dev, "static", 192, 640, 256, 1, (375, 1242), fids=(0, -1, 1), rel=2e-4)
+
+
 @pytest.mark.gpu
 def test_full_size_gpu_tf32():
     """The product configuration: tcgen05 TF32 convolutions.  A TF32 rounding can flip one of the network's hard

@@ -32,3 +32,14 @@ def test_scale_label_dynamic_vs_oracle(dev, split):
     if split == "odometry":   # the static label of the same inputs differs by the 0.27 m offset (net.py:229-233 vs 323-326)
         opt["type"] = "static"
         assert not torch.equal(O.scale_label(opt, inp), ref)
+
+
+def test_scale_loss_of_an_empty_label_is_nan_like_the_reference(dev):
+    """``get_scale_loss`` takes ``torch.mean`` of a masked selection (net.py:207-210): with no labelled pixel the reference's loss is
+    NaN (mean of an empty tensor) — the kernels reproduce that instead of inventing a zero."""
+    g = torch.Generator().manual_seed(0)
+    disp = torch.rand(2, 1, 16, 32, generator=g) * 0.9 + 0.05
+    label = torch.zeros(2, 1, 40, 90)
+    ref = O.scale_term(disp, label, "static")
+    got = JF.scale_loss(D(disp, dev), D(label, dev), 0.1, False)
+    assert ref.item() != ref.item() and got.item() != got.item()
