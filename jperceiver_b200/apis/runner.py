@@ -141,7 +141,8 @@ class LogBuffer:
 
 class Runner:
     def __init__(self, model, optimizer_cfg=None, optimizer_config=None, work_dir=None, log_level="INFO", logger=None, engine=None):
-        grad_clip = (optimizer_config or {}).get("grad_clip")
+        # a dict (cfg.optimizer_config) or a DistOptimizerHook built from it (trainer.py:183: DistOptimizerHook(**cfg.optimizer_config))
+        grad_clip = optimizer_config.grad_clip if hasattr(optimizer_config, "grad_clip") else (optimizer_config or {}).get("grad_clip")
         self.engine = engine if engine is not None else TrainEngine(model, optimizer_cfg, grad_clip)
         self.model = self.engine.model
         self.work_dir = work_dir

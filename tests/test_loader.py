@@ -136,3 +136,39 @@ def test_two_ranks_take_disjoint_slices_of_one_plan_gloo(tmp_path):
         assert got.shape == (2, 12)                                  # 21 -> 24 padded, 12 per rank
         assert np.array_equal(got.numpy(), ref.plan(epoch))
         assert set(got.reshape(-1).tolist()) == set(range(21))
+
+
+def _grads_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mono.core import DistOptimizerHook, allreduce_grads        # the reference's import path (mono/core/__init__.py:6)
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+        net[0].bias.requires_grad_(False)                                # a parameter without gradient is skipped, as in the reference
+        x = torch.randn(6, 5, generator=torch.Generator().manual_seed(10 + rank))
+        net(x).square().sum().backward()
+        local = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+        gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+        for g, buf in zip(local, gathered):
+            dist.all_gather(buf, g)
+        expect = [sum(buf) / world for buf in gathered]
+        for coalesce in (True, False):
+            for p, g in zip([p for p in net.parameters() if p.grad is not None], local):
+                p.grad.copy_(g)
+            allreduce_grads(net, coalesce=coalesce, bucket_size_mb=25)
+            got = [p.grad for p in net.parameters() if p.grad is not None]
+            assert all((a - b).abs().max().item() < 1e-6 for a, b in zip(got, expect)), coalesce
+        hook = DistOptimizerHook(grad_clip=dict(max_norm=35, norm_type=2))
+        assert hook.grad_clip["max_norm"] == 35 and hook.coalesce and hook.bucket_size_mb == -1
+        if rank == 0:
+            torch.save(True, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_grads_is_the_mean_over_ranks_gloo(tmp_path):
+    """``mono.core.utils.allreduce_grads`` (dist_utils.py:34-44): every ``param.grad`` becomes the mean over ranks, coalesced or not."""
+    out = str(tmp_path / "ok.pt")
+    mp.spawn(_grads_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out) is True
