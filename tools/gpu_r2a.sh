@@ -20,6 +20,12 @@ for b in 4 8; do
   python -c "
 import json; d=json.load(open('gpurun_out/photo_keep_b${b}.json')); print('photometric keep-warped B', d['B'], 'fwd ms', round(d['fwd_ms'],4), 'bwd ms', round(d['bwd_ms'],4))"
 done
+# 2c. prepared patch: backward accumulators in registers (tools/experiments/README.md) — built into a scratch copy of the tree
+rm -rf /tmp/jpb_exp && mkdir -p /tmp/jpb_exp && cp -r bench.py tools tests include jperceiver_b200 oracle mono mmcv MEASURED_PEAKS.json /tmp/jpb_exp/ 2>/dev/null
+( cd /tmp/jpb_exp && patch -p1 -s < tools/experiments/photometric_bwd_regs.patch && rm -f jperceiver_b200/csrc/libjpb200.so && python -m jperceiver_b200.build > /dev/null 2>&1 \
+  && for b in 4 8; do timeout 120 python tools/bench_photometric.py --B $b --variant 2 > $OLDPWD/gpurun_out/photo_bwdregs_b${b}.json 2> $OLDPWD/gpurun_out/photo_bwdregs_b${b}.err; \
+     python -c "
+import json; d=json.load(open('$OLDPWD/gpurun_out/photo_bwdregs_b${b}.json')); print('photometric bwd-in-registers B', d['B'], 'bwd ms', round(d['bwd_ms'],4))"; done )
 # 3. the memory-bound network kernels (BatchNorm, max-pool): achieved GB/s per call at the step's largest shapes
 timeout 200 python tools/bench_misc.py > gpurun_out/misc_default.txt 2>&1; tail -12 gpurun_out/misc_default.txt
 # 4. the bench line with the default kernels, then with the packed photometric forward
