@@ -283,7 +283,7 @@ def run_ours(args):
                                "(fwd + compute_losses + bwd + allreduce + clip + Adam)" % (CONFIG_NAME, H, W, B),
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (activations, several GB) exceeds the 126 MB L2; no explicit flush",
-                   "frames_per_s": value * (1 + F_src), "operator_backends": dict(netops.BACKEND),
+                   "frames_per_s": value * (1 + F_src), "operator_kernels": dict(netops.KERNELS),
                    "execution": "one CUDA graph per step (captured from the eager step)" if args.graph else "eager"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": synthetic.batch_bytes(host),
                 "d2h_bytes_per_step": 4 * (len(engine.last_names)),

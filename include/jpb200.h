@@ -212,6 +212,8 @@ typedef struct JpbConvWgradArgs {
   int splits;
   float* dbg;                /* debug only: first pipeline stage (A then B tile) is copied here when non-NULL */
   int accumulate;            /* 1: always add into dw (dw aliases the parameter's slot of the flat gradient buffer) */
+  int dy_pitch;              /* floats between consecutive pixels of dy; 0 = N (dense).  The 3xTF32 mode passes the hi or lo
+                                half of a split gradient tensor (jpb_tf32_split): pitch = 2 * N */
 } JpbConvWgradArgs;
 int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
 
@@ -224,6 +226,11 @@ int jpb_conv3x3_smalln_fwd(const float* x, const float* w, const float* bias, fl
                            int up, int N, int reflect, int act, void* stream);
 int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const float* dz, float* work, float* dw, float* dx, int B, int Hs, int Ws,
                            int C, int up, int N, int reflect, void* stream);
+
+/* ---- 3xTF32 operand split (precision mode of the tensor-core convolutions that reproduces the reference's fp32 arithmetic,
+ * torch.backends.cudnn.allow_tf32 = False): x [rows][C] -> out [rows][2*Cp], Cp = C rounded up to 4; columns [0,Cp) hold
+ * hi = x rounded to TF32 (nearest even), [Cp,2Cp) hold lo = x - hi; padding columns are zero.                    */
+int jpb_tf32_split(const float* x, float* out, long long rows, int C, void* stream);
 
 /* ---- backward of the convolution epilogue: dz = dy * act'(y) (act as in JpbConvArgs, from the OUTPUT y) and
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */

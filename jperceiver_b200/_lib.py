@@ -91,7 +91,7 @@ class ConvWgradArgs(C.Structure):
         ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
         ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("table", C.c_void_p), ("nchunks", C.c_int),
         ("dy", C.c_void_p), ("dw", C.c_void_p), ("w_row", C.c_longlong), ("w_cols", C.c_int), ("splits", C.c_int),
-        ("dbg", C.c_void_p), ("accumulate", C.c_int),
+        ("dbg", C.c_void_p), ("accumulate", C.c_int), ("dy_pitch", C.c_int),
     ]
 
 
@@ -174,6 +174,7 @@ class _Signatures:
     jpb_conv2d_wgrad = [C.POINTER(ConvWgradArgs), V]
     jpb_act_bwd = [P, P, P, C.c_longlong, I, I, P, V]
     jpb_bias_act = [P, P, P, C.c_longlong, I, I, V]
+    jpb_tf32_split = [P, P, C.c_longlong, I, V]
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]

@@ -73,18 +73,24 @@ class StepLrPolicy:
 
 # ------------------------------------------------------------------------------------------------ checkpoint format
 def optimizer_state_dict(engine):
-    """FusedAdam's flat moments as a ``torch.optim.Adam.state_dict()`` (one param group, parameters in model order)."""
+    """FusedAdam's flat moments as a ``torch.optim.Adam.state_dict()`` (one param group, parameters in ``model.parameters()``
+    order — every parameter is trainable, ``FlatParameters`` checks it — so indices agree with the reference's optimizer).
+    Like ``torch.optim.Adam``, parameters that never received a gradient (the three unused ResNet ``fc`` layers, the CCT
+    ``res_conv``) have no state entry: their second moment is still exactly zero.  ``initial_lr`` is stored as mmcv's
+    ``LrUpdaterHook.before_run`` does, so a resume (here or in the reference) restarts the schedule from the base rate."""
     opt, flat = engine.optimizer, engine.flat
     step = int(opt.step_count.item())
     state = {}
-    for i, (p, (off, n)) in enumerate(zip(flat.params, flat.views)):
-        if step == 0:
-            continue
-        state[i] = {"step": torch.tensor(float(step)),
-                    "exp_avg": flat._view(opt.exp_avg, off, p).detach().cpu().clone().contiguous(),
-                    "exp_avg_sq": flat._view(opt.exp_avg_sq, off, p).detach().cpu().clone().contiguous()}
+    if step > 0:
+        m_host, v_host = opt.exp_avg.detach().cpu(), opt.exp_avg_sq.detach().cpu()      # two copies, then host-side views
+        for i, (p, (off, n)) in enumerate(zip(flat.params, flat.views)):
+            v = flat._view(v_host, off, p)
+            if not bool(v.any()):
+                continue
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": flat._view(m_host, off, p).clone().contiguous(),
+                        "exp_avg_sq": v.clone().contiguous()}
     group = {"lr": opt.lr, "betas": tuple(opt.betas), "eps": opt.eps, "weight_decay": opt.weight_decay, "amsgrad": False,
-             "params": list(range(len(flat.params)))}
+             "initial_lr": float(getattr(opt, "initial_lr", opt.lr)), "params": list(range(len(flat.params)))}
     return {"state": state, "param_groups": [group]}
 
 
@@ -95,6 +101,8 @@ def load_optimizer_state_dict(engine, sd):
     if len(order) != len(flat.params):
         raise ValueError("optimizer state has %d parameters, the model has %d trainable ones" % (len(order), len(flat.params)))
     step = 0
+    opt.exp_avg.zero_()
+    opt.exp_avg_sq.zero_()                      # parameters without a state entry never received a gradient
     for pos, key in enumerate(order):
         st = sd["state"].get(key)
         if st is None:
@@ -106,6 +114,8 @@ def load_optimizer_state_dict(engine, sd):
     opt.step_count.fill_(step)
     if groups:
         opt.lr = float(groups[0].get("lr", opt.lr))
+        if "initial_lr" in groups[0]:
+            opt.initial_lr = float(groups[0]["initial_lr"])
 
 
 def save_checkpoint(engine, path, meta):
@@ -142,8 +152,13 @@ class LogBuffer:
 class Runner:
     def __init__(self, model, optimizer_cfg=None, optimizer_config=None, work_dir=None, log_level="INFO", logger=None, engine=None):
         # a dict (cfg.optimizer_config) or a DistOptimizerHook built from it (trainer.py:183: DistOptimizerHook(**cfg.optimizer_config))
-        grad_clip = optimizer_config.grad_clip if hasattr(optimizer_config, "grad_clip") else (optimizer_config or {}).get("grad_clip")
-        self.engine = engine if engine is not None else TrainEngine(model, optimizer_cfg, grad_clip)
+        # ``grad_clip=None`` in the config means NO clipping, as in the reference's DistOptimizerHook (dist_utils.py:56-58); only a
+        # runner built without any optimizer_config falls back to the engine default (the configs' max_norm=35)
+        if optimizer_config is None:
+            self.engine = engine if engine is not None else TrainEngine(model, optimizer_cfg)
+        else:
+            grad_clip = optimizer_config.grad_clip if hasattr(optimizer_config, "grad_clip") else dict(optimizer_config).get("grad_clip")
+            self.engine = engine if engine is not None else TrainEngine(model, optimizer_cfg, grad_clip)
         self.model = self.engine.model
         self.work_dir = work_dir
         if work_dir:
@@ -163,7 +178,7 @@ class Runner:
 
     # ---- mmcv Runner API used by the reference
     def register_training_hooks(self, lr_config, optimizer_config=None, checkpoint_config=None, log_config=None):
-        self.lr_policy = StepLrPolicy(self.engine.optimizer.lr, **dict(lr_config)) if lr_config else None
+        self.lr_policy = StepLrPolicy(getattr(self.engine.optimizer, "initial_lr", self.engine.optimizer.lr), **dict(lr_config)) if lr_config else None
         if checkpoint_config is not None:
             self.checkpoint_interval = int(dict(checkpoint_config).get("interval", 1))
         if log_config is not None:
@@ -192,6 +207,8 @@ class Runner:
         return self.engine.world
 
     def _after_train_epoch(self):
+        if self._hooks:
+            self.engine.sync_buffers()      # validation scores rank 0's BatchNorm statistics (the ones in the checkpoint) on every rank
         for hook in self._hooks:
             hook.after_train_epoch(self)
         if self.log_buffer.ready:
@@ -235,6 +252,9 @@ class Runner:
         self.epoch, self.iter = int(ck["meta"]["epoch"]), int(ck["meta"]["iter"])
         if "optimizer" in ck and resume_optimizer:
             load_optimizer_state_dict(self.engine, ck["optimizer"])
+            if self.lr_policy is not None:          # the schedule restarts from the BASE rate, not from the decayed one in 'lr'
+                self.lr_policy.base_lr = float(self.engine.optimizer.initial_lr)
+        self.engine._graph = None
         self.logger.info("resumed epoch %d, iter %d", self.epoch, self.iter)
 
     # ---- training

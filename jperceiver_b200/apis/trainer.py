@@ -75,7 +75,12 @@ class FlatParameters:
     """Re-home every parameter (and its gradient) of ``model`` as a view into one flat fp32 buffer."""
 
     def __init__(self, model):
-        params = [p for p in model.parameters() if p.requires_grad]
+        params = list(model.parameters())
+        frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+        if frozen:
+            # checkpoint optimizer state is indexed over model.parameters() (torch.optim.Adam layout, as the reference's); a
+            # frozen parameter would shift every index after it
+            raise NotImplementedError("frozen parameters are not supported by the flat optimizer (%s ...)" % frozen[0])
         dev = params[0].device
         # every tensor starts on a 256-byte boundary: TMA / cp.async / vectorised loads need >= 16-byte alignment
         n = sum(self._padded(p.numel()) for p in params)
@@ -120,6 +125,7 @@ class FusedAdam:
     def __init__(self, flat, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=None):
         self.flat = flat
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.initial_lr = lr          # mmcv LrUpdaterHook's 'initial_lr': base of the schedule, saved with every checkpoint
         self.max_norm = max_norm
         dev = flat.param.device
         self.exp_avg = torch.zeros_like(flat.param)
@@ -170,16 +176,33 @@ def build_optimizer(model, optimizer_cfg, grad_clip=None):
 class TrainEngine:
     """One object per process (= per GPU): forward, backward, gradient exchange, optimizer step."""
 
-    def __init__(self, model, optimizer_cfg=None, grad_clip=None):
+    DEFAULT_CLIP = dict(max_norm=35, norm_type=2)     # optimizer_config of every reference config
+
+    def __init__(self, model, optimizer_cfg=None, grad_clip="default"):
+        """``grad_clip``: ``dict(max_norm=..., norm_type=2)``; ``None`` / ``{}`` = no clipping (DistOptimizerHook with
+        grad_clip=None, dist_utils.py:56-58); omitted = the reference configs' ``max_norm=35``."""
         self.model = model
-        self.optimizer = build_optimizer(model, optimizer_cfg or dict(type="Adam", lr=1e-4, weight_decay=0),
-                                         grad_clip if grad_clip is not None else dict(max_norm=35, norm_type=2))
+        if isinstance(grad_clip, str):
+            grad_clip = dict(self.DEFAULT_CLIP)
+        self.optimizer = build_optimizer(model, optimizer_cfg or dict(type="Adam", lr=1e-4, weight_decay=0), grad_clip)
         self.flat = model._jpb_flat
         self.rank, self.world = get_dist_info()
+        if self.world > 1:
+            # what MMDistributedDataParallel does at construction: every rank starts from rank 0's parameters and buffers
+            dist.broadcast(self.flat.param, src=0)
+            self.sync_buffers()
         self.last_names = None
         if hasattr(model, "step_counter"):
             model.step_counter = self.optimizer.step_count   # fresh automask noise per step, also under graph replay
         self._graph = None
+
+    def sync_buffers(self):
+        """Broadcast every module buffer (BatchNorm running statistics, ``num_batches_tracked``) from rank 0.  Statistics stay
+        per-GPU DURING training (no SyncBN, as the reference); rank 0's are the ones a checkpoint holds, so they are what
+        distributed validation must score on every rank."""
+        if self.world > 1:
+            for b in self.model.buffers():
+                dist.broadcast(b, src=0)
 
     def exchange_gradients(self):
         """The path's only collective: all-reduce(sum) of the flat gradient buffer (dist_utils.py:27);

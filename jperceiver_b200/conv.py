@@ -17,7 +17,6 @@ from ._lib import check, ptr, stream_of
 CL = torch.channels_last
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3}
 SMALLN = True      # route 3x3 convolutions with <= 2 output channels to the CUDA-core kernels (csrc/conv_smalln.cu)
-BACKWARD = "jpb"   # "jpb": tcgen05 dgrad/wgrad kernels; "torch": library backward on a re-materialised input (debug)
 _TABLES: dict = {}
 _ORDERS: dict = {}
 import os as _os
@@ -27,6 +26,46 @@ KORDER = _os.environ.get("JPB_CONV_KORDER", "cb")
 DBG_SKIP = int(_os.environ.get('JPB_CONV_SKIP', '0'))   # timing experiments (wrong results): 1 no A gather, 2 no weight TMA
 DBG_STAMPS = None   # int64 [512, 6, 8] device tensor: per-CTA timeline of the next forward launches (tools/conv_timeline.py)
 L1_GATHER = int(_os.environ.get("JPB_CONV_L1", "1"))
+# Arithmetic of the tensor-core convolutions (same kernels, same path):
+#   "tf32"   one TF32 product per term — what the reference gets from cuDNN with torch.backends.cudnn.allow_tf32 = True (torch default)
+#   "3xtf32" operands split into TF32 hi + lo parts (jpb_tf32_split), hi*hi + hi*lo + lo*hi accumulated in the same TMEM tile
+#            as a 3x longer K — fp32-grade results (reference with allow_tf32 = False / its CPU path), ~3x the tensor work
+PRECISION = _os.environ.get("JPB_CONV_PRECISION", "tf32")
+
+
+class precision:
+    """``with conv.precision("3xtf32"): ...`` — scoped switch of the convolution arithmetic (tests, parity runs)."""
+
+    def __init__(self, mode):
+        if mode not in ("tf32", "3xtf32"):
+            raise ValueError("conv precision %r (tf32 | 3xtf32)" % (mode,))
+        self.mode = mode
+
+    def __enter__(self):
+        global PRECISION
+        self.old, PRECISION = PRECISION, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global PRECISION
+        PRECISION = self.old
+
+
+def tf32_split(x):
+    """[B, C, H, W] channels-last (or [rows, C] row-major) -> the hi | lo halves side by side: [B, 2*Cp, H, W] / [rows, 2*Cp]."""
+    if x.dim() == 4:
+        x = _cl(x)
+        B, Cc, H, W = x.shape
+        Cp = _pad4(Cc)
+        out = torch.empty((B, 2 * Cp, H, W), dtype=torch.float32, device=x.device, memory_format=CL)
+        rows = B * H * W
+    else:
+        x = x.contiguous()
+        rows, Cc = x.shape
+        Cp = _pad4(Cc)
+        out = torch.empty((rows, 2 * Cp), dtype=torch.float32, device=x.device)
+    check(_launch("tf32_split", x, lambda: _lib.lib().jpb_tf32_split(ptr(x), ptr(out), rows, Cc, stream_of(x))), "jpb_tf32_split")
+    return out
 
 
 class _WTCache:
@@ -106,15 +145,39 @@ def chunk_table(src_channels, kh, kw, device):
     return t
 
 
-def ordered_table(src_channels, kh, kw, device):
+def split_table(src_cp, kh, kw, device, part):
+    """Chunk table over split sources (``tf32_split``: pixel stride 2*Cp, hi half at channel 0, lo half at channel Cp).
+    ``part``: "hi" / "lo" = one half (weight-gradient launches); "3x" = the K extension hi | hi | lo that pairs with the weight
+    matrix [W_hi | W_lo | W_hi] (forward and data gradient)."""
+    key = ("split", part, tuple(src_cp), kh, kw, str(device))
+    t = _TABLES.get(key)
+    if t is None:
+        hi, lo = [], []
+        nsrc = len(src_cp)
+        for ky in range(kh):
+            for kx in range(kw):
+                tap = ky * kw + kx
+                for si, c in enumerate(src_cp):
+                    for coff in range(0, c, 4):
+                        hi.append((si | ((tap * nsrc + si) << 8), (ky << 16) | (kx & 0xFFFF), coff, 16))
+                        lo.append((si | ((tap * nsrc + si) << 8), (ky << 16) | (kx & 0xFFFF), c + coff, 16))
+        rows = {"hi": hi, "lo": lo, "3x": hi + hi + lo}[part]
+        while len(rows) % 8:
+            rows.append((-1, 0, 0, 0))
+        t = _TABLES[key] = torch.tensor(rows, dtype=torch.int32, device=device).contiguous()
+    return t
+
+
+def ordered_table(src_channels, kh, kw, device, split3=False):
     """(table, kcol): the chunk table with its K blocks (8 rows each) re-ordered channel-block major, and the weight column
     of each K block (int32 [nkb]) for the weight TMA.  Any order is valid — K is the GEMM reduction."""
+    base = (lambda: split_table(src_channels, kh, kw, device, "3x")) if split3 else (lambda: chunk_table(src_channels, kh, kw, device))
     if KORDER != "cb" or kh * kw == 1:
-        return chunk_table(src_channels, kh, kw, device), None
-    key = (tuple(src_channels), kh, kw, str(device))
+        return base(), None
+    key = (tuple(src_channels), kh, kw, str(device), bool(split3))
     r = _ORDERS.get(key)
     if r is None:
-        t = chunk_table(src_channels, kh, kw, device).cpu().view(-1, 8, 4)
+        t = base().cpu().view(-1, 8, 4)
         first = t[:, 0, :]                                       # first chunk of each K block: (src | tapsrc<<8, dydx, coff, bytes)
         nsrc = len(src_channels)
         keys = []
@@ -150,25 +213,20 @@ def gemm_weight(weight, src_channels, weight_channels):
     return wp.reshape(N, -1), wp.shape[1] * wp.shape[2] * wp.shape[3]
 
 
-def _torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual):
-    """Library formulation of the same operator (used for the interim backward and under host emulation)."""
-    ts = [F.interpolate(t, scale_factor=2, mode="nearest") if up else t for t, up in zip(xs, ups)]
-    x = ts[0] if len(ts) == 1 else torch.cat(ts, 1)
-    if x.shape[1] > weight.shape[1]:     # zero-padded stem channels
-        x = x[:, :weight.shape[1]]
-    if reflect and pad:
-        x = F.pad(x, (pad,) * 4, mode="reflect")
-        pad = 0
-    y = F.conv2d(x.contiguous(memory_format=CL), weight, bias, stride=stride, padding=pad)
-    if residual is not None:
-        y = y + residual
-    if act == "relu":
-        y = F.relu(y)
-    elif act == "leaky":
-        y = F.leaky_relu(y, 0.01)
-    elif act == "sigmoid":
-        y = torch.sigmoid(y)
-    return y
+def gemm_weight3(weight, src_channels, weight_channels):
+    """3xTF32 operand [N, 3*K1] = [W_hi | W_lo | W_hi] over the zero-padded packed K layout (every source padded to 4 channels),
+    matching ``split_table(..., "3x")``."""
+    N, Cin, kh, kw = weight.shape
+    w = weight.permute(0, 2, 3, 1)
+    parts, off = [], 0
+    for c_t, c_w in zip(src_channels, weight_channels):
+        parts.append(F.pad(w[..., off:off + c_w], (0, _pad4(c_t) - c_w)))
+        off += c_w
+    wp = (parts[0] if len(parts) == 1 else torch.cat(parts, -1)).contiguous().reshape(N, -1)
+    K1 = wp.shape[1]
+    hl = tf32_split(wp)                         # [N, 2*K1]: hi | lo
+    w3 = torch.cat([hl, hl[:, :K1]], 1).contiguous()
+    return w3, 3 * K1
 
 
 SPLIT_EPILOGUE = int(_os.environ.get('JPB_SPLIT_EPILOGUE', '1'))   # split-K also for convolutions with bias / activation (finishing pass)
@@ -229,13 +287,20 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     W = xs[0].shape[3] * (2 if ups[0] else 1)
     dev = dz.device
     Nc = dz.shape[1]                                   # possibly channel-padded dz
+    three = PRECISION == "3xtf32"
     wT = WT.lookup(weight) if (Nc == N and N % 4 == 0 and weight.is_contiguous(memory_format=CL)) else None
     if wT is None:
         wT = weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=CL)   # [Cin][kh][kw][Cout]
         if Nc == N and N % 4 == 0 and weight.is_contiguous(memory_format=CL):
             WT.register(weight)
-    wmat, wcols = gemm_weight(wT, [Nc], [N])
-    table, kcol = ordered_table([Nc], kh, kw, dev)
+    if three:
+        dz_k = tf32_split(dz)                           # [B, 2*Nc, Ho, Wo]: hi | lo halves of every pixel
+        wmat, wcols = gemm_weight3(wT, [Nc], [N])
+        table, kcol = ordered_table([Nc], kh, kw, dev, split3=True)
+    else:
+        dz_k = dz
+        wmat, wcols = gemm_weight(wT, [Nc], [N])
+        table, kcol = ordered_table([Nc], kh, kw, dev)
     src_C = [x.shape[1] for x in xs]
     if len(xs) == 1 and src_C[0] != Cin:                # zero-padded stem input: gradient not needed (images)
         return [None]
@@ -244,8 +309,8 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     for x, up in zip(xs, ups):
         grads.append(torch.empty_like(x, memory_format=CL) if simple else torch.zeros_like(x, memory_format=CL))
     a = _lib.ConvArgs()
-    a.src[0] = ptr(dz)
-    a.src_C[0], a.src_H[0], a.src_W[0], a.src_up[0] = Nc, Ho, Wo, 0
+    a.src[0] = ptr(dz_k)
+    a.src_C[0], a.src_H[0], a.src_W[0], a.src_up[0] = dz_k.shape[1], Ho, Wo, 0
     a.nsrc = 1
     a.B, a.Hin, a.Win = B, Ho, Wo
     a.N = Cin
@@ -300,6 +365,7 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None)
     dev = dz.device
     src_C = [x.shape[1] for x in xs]
     w_C = [Cin] if (len(xs) == 1 and src_C[0] != Cin) else src_C
+    three = PRECISION == "3xtf32"
     table = chunk_table(src_C, kh, kw, dev)
     raw = all(c % 4 == 0 for c in src_C) and src_C == w_C
     Cpad = sum(_pad4(c) for c in src_C)
@@ -325,7 +391,20 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None)
     if dbg is not None:
         a.dbg = ptr(dbg)
     tag = (B * Ho * Wo, Nc, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), a.splits)
-    check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_wgrad")
+    if three:
+        # dW = im2col(x_hi)^T dz_hi + im2col(x_hi)^T dz_lo + im2col(x_lo)^T dz_hi: three accumulating launches of the same kernel
+        src_cp = [_pad4(c) for c in src_C]
+        xs_k = [tf32_split(x) for x in xs]
+        dz_k = tf32_split(dz)
+        _fill_sources(a, xs_k, ups)
+        a.accumulate, a.dy_pitch = 1, dz_k.shape[1]
+        t_hi, t_lo = split_table(src_cp, kh, kw, dev, "hi"), split_table(src_cp, kh, kw, dev, "lo")
+        assert t_hi.shape[0] == table.shape[0]
+        for tab, dyoff in ((t_hi, 0), (t_hi, Nc), (t_lo, 0)):
+            a.table, a.dy = ptr(tab), ptr(dz_k) + 4 * dyoff
+            check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_wgrad(3xtf32)")
+    else:
+        check(_launch("conv_wgrad", dz, lambda: _lib.lib().jpb_conv2d_wgrad(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_wgrad")
     if direct:
         return None
     dw = dw[:N]
@@ -401,8 +480,14 @@ class _ConvTC(torch.autograd.Function):
         Ho = (Hin + 2 * pad - kh) // stride + 1
         Wo = (Win + 2 * pad - kw) // stride + 1
         dev = xs[0].device
-        table, kcol = ordered_table(src_C, kh, kw, dev)
-        wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
+        xs_k = xs
+        if PRECISION == "3xtf32":
+            xs_k = [tf32_split(x) for x in xs]             # per pixel: hi | lo halves, each padded to 4 channels
+            table, kcol = ordered_table([_pad4(c) for c in src_C], kh, kw, dev, split3=True)
+            wmat, wcols = gemm_weight3(weight.detach(), src_C, w_C)
+        else:
+            table, kcol = ordered_table(src_C, kh, kw, dev)
+            wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
         nkb = table.shape[0] // 8
         ks = _ksplit(B * Ho * Wo, N, nkb)
         has_epi = bias is not None or residual is not None or act != "none"
@@ -415,7 +500,7 @@ class _ConvTC(torch.autograd.Function):
             out.zero_()
         a = _lib.ConvArgs()
         a.ksplit = ks
-        _fill_sources(a, xs, ups)
+        _fill_sources(a, xs_k, ups)
         a.B, a.Hin, a.Win, a.Ho, a.Wo, a.N = B, Hin, Win, Ho, Wo, N
         a.stride, a.pad, a.reflect = stride, pad, int(reflect)
         a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
@@ -452,8 +537,6 @@ class _ConvTC(torch.autograd.Function):
     def backward(ctx, gy):
         cfg = ctx.cfg
         weight, bias, residual, out, *xs = ctx.saved_tensors
-        if BACKWARD == "torch":
-            return _ConvTC._backward_library(ctx, gy)
         ups, stride, pad, reflect, act = cfg["ups"], cfg["stride"], cfg["pad"], cfg["reflect"], cfg["act"]
         N = weight.shape[0]
         from .functional import direct_grad_target
@@ -473,23 +556,6 @@ class _ConvTC(torch.autograd.Function):
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
         gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=direct_grad_target(weight)) if ctx.needs_input_grad[1] else None
         return (None, gw, gb, gr) + tuple(gxs)
-
-    @staticmethod
-    def _backward_library(ctx, gy):
-        cfg = ctx.cfg
-        weight, bias, residual, out, *xs = ctx.saved_tensors
-        with torch.enable_grad():
-            xs_ = [x.detach().requires_grad_(True) for x in xs]
-            w_ = weight.detach().requires_grad_(True)
-            b_ = bias.detach().requires_grad_(True) if bias is not None else None
-            r_ = residual.detach().requires_grad_(True) if residual is not None else None
-            y = _torch_conv(xs_, cfg["ups"], w_, b_, cfg["stride"], cfg["pad"], cfg["reflect"], cfg["act"], r_)
-            wanted = [w_] + ([b_] if b_ is not None else []) + ([r_] if r_ is not None else []) + xs_
-            grads = list(torch.autograd.grad(y, wanted, gy, allow_unused=True))
-        gw = grads.pop(0)
-        gb = grads.pop(0) if b_ is not None else None
-        gr = grads.pop(0) if r_ is not None else None
-        return (None, gw, gb, gr) + tuple(grads)
 
 
 STATS_FUSED = [False]   # set by the last forward launch: its epilogue accumulated the BatchNorm statistics of its output

@@ -1240,7 +1240,9 @@ extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
   const long long P = (long long)a->B * a->Ho * a->Wo;
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)a->N, (cuuint64_t)P};
-  const cuuint64_t gstr[1] = {(cuuint64_t)a->N * 4};
+  const int pitch = a->dy_pitch > 0 ? a->dy_pitch : a->N;
+  if (pitch < a->N || (pitch & 3)) return JPB_ERR_ARG;
+  const cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
   const cuuint32_t box[2] = {32, 32};
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

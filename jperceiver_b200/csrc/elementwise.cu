@@ -80,6 +80,33 @@ __global__ void __launch_bounds__(256) bias_act_kernel(float* z, const float* bi
   }
 }
 
+
+// 3xTF32 operand split (precision mode "3xtf32" of the tensor-core convolutions): every fp32 value x becomes
+//   hi = x rounded to the nearest TF32 (10 explicit mantissa bits, ties to even), lo = x - hi (exact in fp32).
+// rows x C in, rows x 2*Cp out (Cp = C rounded up to 4): hi in columns [0, Cp), lo in [Cp, 2*Cp), padding columns zero.
+// The convolution then runs  hi*Whi + hi*Wlo + lo*Whi  as ONE GEMM over a 3x longer K (the split halves are extra K chunks of
+// the same gather table), all three products accumulating in the same fp32 TMEM tile.
+__global__ void __launch_bounds__(256) tf32_split_kernel(const float* x, float* out, long long rows, int C, int Cp) {
+  const long long n = rows * Cp;
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n; i += (long long)gridDim.x * JPB_NT) {
+    const long long r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    float hi = 0.f, lo = 0.f;
+    if (c < C) {
+      const float v = x[r * C + c];
+      uint32_t b = __float_as_uint(v);
+      if ((b & 0x7f800000u) != 0x7f800000u) {       // finite: round to nearest even at bit 13
+        b += 0xfffu + ((b >> 13) & 1u);
+        b &= 0xffffe000u;
+      }
+      hi = __uint_as_float(b);
+      lo = v - hi;
+    }
+    out[r * 2 * Cp + c] = hi;
+    out[r * 2 * Cp + Cp + c] = lo;
+  }
+}
+
 }  // namespace
 
 extern "C" int jpb_bias_act(float* z, const float* bias, const float* residual, long long rows, int C, int act, void* stream) {
@@ -96,5 +123,14 @@ extern "C" int jpb_act_bwd(const float* dy, const float* y, float* dz, long long
   long long blocks = rows / 16 + 1;   // small-extent layers (rows = 480..5120) need many short slabs, not 8 blocks of 64 serial rows
   if (blocks > 148 * 8) blocks = 148 * 8;
   JPB_LAUNCH(act_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, dy, y, dz, rows, C, act, dbias);
+  return jpb_status();
+}
+
+extern "C" int jpb_tf32_split(const float* x, float* out, long long rows, int C, void* stream) {
+  if (!x || !out || rows < 1 || C < 1) return JPB_ERR_ARG;
+  const int Cp = (C + 3) & ~3;
+  long long blocks = (rows * Cp + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  JPB_LAUNCH(tf32_split_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, out, rows, C, Cp);
   return jpb_status();
 }

@@ -1,48 +1,36 @@
 """Network operators used by the model mirror (``jperceiver_b200.model``).
 
 Activations are logical ``(B, C, H, W)`` tensors stored channels-last (physically NHWC), fp32.
-Each operator below is one fused unit of the B200 design; ``BACKEND[name]`` says
-whether it currently runs as a hand-written sm_100a kernel from ``libjpb200.so`` ("jpb") or still as a
-library call ("torch": cuDNN/ATen on the same device, same memory format).  There is no CPU path: every
-operator refuses non-CUDA tensors.
+Each operator below is one fused unit of the B200 design and runs as a hand-written sm_100a kernel
+from ``libjpb200.so`` — there is one path: no library (cuDNN/ATen) formulation, no CPU path; every operator refuses
+non-CUDA tensors and unsupported shapes raise.  (The library formulations the kernels are tested against live in
+``tests/emu/torch_ops.py``.)
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from . import conv as _conv
 
 CL = torch.channels_last
 
-BACKEND = {
-    "conv2d": "jpb",        # tcgen05 implicit GEMM: forward, dgrad, wgrad (csrc/conv_tc.cu) + epilogue backward (elementwise.cu)
-    "maxpool": "jpb",       # csrc/pool.cu
-    "batchnorm": "jpb",     # csrc/bn.cu: batch statistics + normalise + residual + ReLU fused, fwd and bwd
-    "dropout": "jpb",       # csrc/heads.cu: counter-based keep mask, one launch per direction
-    "image_prep": "jpb",    # csrc/heads.cu: normalise + bilinear resize + pair concatenation + NHWC/channel padding in one launch
-    "pose_head": "jpb",     # csrc/heads.cu: spatial mean + Rodrigues + 4x4 assembly, forward and hand-derived backward
-    "cvp_mlp": "jpb",       # csrc/heads.cu: both Linear+ReLU layers of a transform module in one launch per direction
-    "cct_attention": "jpb", # csrc/heads.cu: energies + hard max/arg-max + gather, and the S-weighted residual + attn @ value_d
+# operator -> kernels (documentation; printed by bench.py)
+KERNELS = {
+    "conv2d": "csrc/conv_tc.cu (tcgen05 implicit GEMM: forward, dgrad, wgrad) + csrc/elementwise.cu + csrc/conv_smalln.cu",
+    "maxpool": "csrc/pool.cu",
+    "batchnorm": "csrc/bn.cu",
+    "dropout": "csrc/heads.cu",
+    "image_prep": "csrc/heads.cu",
+    "pose_head": "csrc/heads.cu",
+    "cvp_mlp": "csrc/heads.cu",
+    "cct_attention": "csrc/heads.cu",
 }
 
 
 def _need_cuda(x):
     if not x.is_cuda and not _lib.is_emulated():
         raise _lib.JpbError("jperceiver_b200 runs on CUDA tensors only (got %s); there is no CPU fallback" % x.device)
-
-
-def _act(y, act):
-    if act == "none":
-        return y
-    if act == "relu":
-        return F.relu(y)
-    if act == "leaky":
-        return F.leaky_relu(y, 0.01)
-    if act == "sigmoid":
-        return torch.sigmoid(y)
-    raise ValueError(act)
 
 
 FUSE_BN_STATS = True   # accumulate BatchNorm statistics in the epilogue of the convolution that feeds a training-mode BatchNorm
@@ -60,51 +48,41 @@ def conv2d(inputs, weight, bias=None, *, stride=1, pad=0, reflect=False, act="no
         inputs = [(inputs, False)]
     _need_cuda(inputs[0][0])
     xs, ups = [t for t, _ in inputs], [u for _, u in inputs]
-    if inputs[0][0].is_cuda and BACKEND["conv2d"] == "jpb":
-        y = _conv.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual,
-                            bn_stats=bool(bn_next and FUSE_BN_STATS and BACKEND["batchnorm"] == "jpb"))
-        if bn_next and _conv.STATS_FUSED[0]:
-            y._jpb_bn_stats = True      # consumed (and cleared) by the batchnorm() call that follows
-        return y
-    return _conv._torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, residual)   # host emulation (tests) / library mode
+    y = _conv.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, residual, bn_stats=bool(bn_next and FUSE_BN_STATS))
+    if bn_next and _conv.STATS_FUSED[0]:
+        y._jpb_bn_stats = True      # consumed (and cleared) by the batchnorm() call that follows
+    return y
 
 
 def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1e-5):
     """BatchNorm2d (+residual) (+ReLU).  Training mode uses per-GPU batch statistics and updates the
     running statistics in place, as nn.BatchNorm2d does."""
     _need_cuda(x)
-    if BACKEND["batchnorm"] == "jpb" and x.shape[1] % 4 == 0:
-        from . import functional as JF
-        if training:
-            k = getattr(bn, "stat_updates", 1)
-            nbt = bn.num_batches_tracked
-            if not (torch.is_tensor(nbt) and nbt.is_cuda and nbt.dtype == torch.int64):
-                bn.num_batches_tracked += k
-                nbt = None
-            ready = bool(getattr(x, "_jpb_bn_stats", False))
-            if ready:
-                x._jpb_bn_stats = False
-            return JF.batchnorm_train(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                      1.0 - (1.0 - momentum) ** k, eps, relu, nbt, k, stats_ready=ready)
-        return JF.batchnorm_eval(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, eps, relu)
+    if x.shape[1] % 4:
+        raise _lib.JpbError("batchnorm kernel needs a multiple of 4 channels (got %d)" % x.shape[1])
+    from . import functional as JF
     if training:
         # ``stat_updates`` = 2 on the road-head BNs reproduces the reference's duplicated forward pass
         # (net.py:73-74): two momentum updates with the same batch statistics == one with 1-(1-m)^2.
         k = getattr(bn, "stat_updates", 1)
-        bn.num_batches_tracked += k
-        momentum = 1.0 - (1.0 - momentum) ** k
-    y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, momentum, eps)
-    if residual is not None:
-        y = y + residual
-    return F.relu(y) if relu else y
+        nbt = bn.num_batches_tracked
+        if not (torch.is_tensor(nbt) and nbt.is_cuda and nbt.dtype == torch.int64):
+            bn.num_batches_tracked += k
+            nbt = None
+        ready = bool(getattr(x, "_jpb_bn_stats", False))
+        if ready:
+            x._jpb_bn_stats = False
+        return JF.batchnorm_train(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                  1.0 - (1.0 - momentum) ** k, eps, relu, nbt, k, stats_ready=ready)
+    return JF.batchnorm_eval(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, eps, relu)
 
 
 def maxpool(x, k, stride, pad):
     _need_cuda(x)
-    if BACKEND["maxpool"] == "jpb" and x.shape[1] % 4 == 0:
-        from . import functional as JF
-        return JF.maxpool(x, k, stride, pad)
-    return F.max_pool2d(x, k, stride, pad)
+    if x.shape[1] % 4:
+        raise _lib.JpbError("maxpool kernel needs a multiple of 4 channels (got %d)" % x.shape[1])
+    from . import functional as JF
+    return JF.maxpool(x, k, stride, pad)
 
 
 class _Dropout(torch.autograd.Function):
@@ -142,10 +120,6 @@ def dropout(x, p, training, mask=None, step=None, seed=0):
     if not training or p == 0.0:
         return x
     _need_cuda(x)
-    if BACKEND["dropout"] != "jpb":
-        if mask is None:
-            mask = (torch.rand_like(x) >= p).to(x.dtype)
-        return x * mask * (1.0 / (1.0 - p))
     _DROPOUT_CALLS[0] = (_DROPOUT_CALLS[0] + 1) % 4096
     return _Dropout.apply(x, p, mask, seed, 1000 + _DROPOUT_CALLS[0], step)
 
@@ -156,31 +130,28 @@ def image_prep(images, out_hw=None):
     if not isinstance(images, (list, tuple)):
         images = [images]
     _need_cuda(images[0])
-    if BACKEND["image_prep"] == "jpb" and len(images) <= 2 and all(im.shape[1] == 3 and im.dtype == torch.float32 for im in images):
-        from ._lib import check, ptr, stream_of
-        ims = [im.contiguous() for im in images]
-        B, _, Hs, Ws = ims[0].shape
-        Ho, Wo = (Hs, Ws) if out_hw is None else tuple(out_hw)
-        Cpad = 4 * len(ims)
-        out = torch.empty((B, Cpad, Ho, Wo), dtype=torch.float32, device=ims[0].device, memory_format=CL)
-        check(_lib.lib().jpb_image_prep(ptr(ims[0]), ptr(ims[1]) if len(ims) == 2 else None, ptr(out), B, Hs, Ws, Ho, Wo, Cpad,
-                                        stream_of(out)), "jpb_image_prep")
-        return out
-    outs = []
-    for im in images:
-        if out_hw is not None and tuple(im.shape[2:]) != tuple(out_hw):
-            im = F.interpolate(im, list(out_hw), mode="bilinear", align_corners=False)
-        outs.append((im - 0.45) / 0.225)
-    x = outs[0] if len(outs) == 1 else torch.cat(outs, 1)
-    if x.shape[1] % 4:   # 3 -> 4 / 6 -> 8 zero channels: every pixel is a whole number of 16-byte gather chunks
-        x = F.pad(x, (0, 0, 0, 0, 0, 4 - x.shape[1] % 4))
-    return x.contiguous(memory_format=CL)
+    if len(images) == 1 and images[0].shape[1] == 6:     # an already concatenated frame pair (scripts/draw_odometry.py:66)
+        images = [images[0][:, :3], images[0][:, 3:]]
+    if len(images) > 2 or any(im.shape[1] != 3 or im.dtype != torch.float32 for im in images):
+        raise _lib.JpbError("image_prep takes one or two 3-channel fp32 frames")
+    from ._lib import check, ptr, stream_of
+    ims = [im.contiguous() for im in images]
+    B, _, Hs, Ws = ims[0].shape
+    Ho, Wo = (Hs, Ws) if out_hw is None else tuple(out_hw)
+    Cpad = 4 * len(ims)
+    out = torch.empty((B, Cpad, Ho, Wo), dtype=torch.float32, device=ims[0].device, memory_format=CL)
+    check(_lib.lib().jpb_image_prep(ptr(ims[0]), ptr(ims[1]) if len(ims) == 2 else None, ptr(out), B, Hs, Ws, Ho, Wo, Cpad,
+                                    stream_of(out)), "jpb_image_prep")
+    return out
 
 
 def resize_bilinear(x, out_hw):
+    """Bilinear resize (align_corners=False) of the CCT depth feature under the non-square rule: identity at
+    the reference's 1024x1024; otherwise one ATen ``upsample_bilinear2d`` on a B x 512 x 10 x 32 map (the only library
+    arithmetic left on the path)."""
     if tuple(x.shape[2:]) == tuple(out_hw):
         return x
-    return F.interpolate(x, list(out_hw), mode="bilinear", align_corners=False)
+    return torch.nn.functional.interpolate(x, list(out_hw), mode="bilinear", align_corners=False)
 
 
 def _nhwc(t):
@@ -222,13 +193,9 @@ class _CvpMlp(torch.autograd.Function):
 def cvp_mlp(x, fc0, fc2):
     """Per-channel MLP over the flattened (h*w) positions: Linear+ReLU twice (CycledViewProjection.py:27-67)."""
     _need_cuda(x)
-    if BACKEND["cvp_mlp"] == "jpb" and x.dtype == torch.float32:
-        return _CvpMlp.apply(x, fc0.weight, fc0.bias, fc2.weight, fc2.bias)
-    B, C, h, w = x.shape
-    y = x.reshape(B, C, h * w)  # logical NCHW order, as the reference's .view does
-    y = F.relu(F.linear(y, fc0.weight, fc0.bias))
-    y = F.relu(F.linear(y, fc2.weight, fc2.bias))
-    return y.reshape(B, C, h, w).contiguous(memory_format=CL)
+    if x.dtype != torch.float32:
+        raise _lib.JpbError("cvp_mlp takes fp32 activations")
+    return _CvpMlp.apply(x, fc0.weight, fc0.bias, fc2.weight, fc2.bias)
 
 
 class _CctSelect(torch.autograd.Function):
@@ -303,31 +270,17 @@ def cct_attention(front, cross, front_hat, dfeat, p):
     (h x w) matrix product broadcast over channels."""
     _need_cuda(front)
     B, C, a, b = front.shape
-    n = a * b
-    if BACKEND["cct_attention"] == "jpb" and a == b and n <= 256:
-        q = conv2d(cross, p.query_conv.weight, p.query_conv.bias)
-        k = conv2d(front, p.key_conv.weight, p.key_conv.bias)
-        v = conv2d(front_hat, p.value_conv.weight, p.value_conv.bias)
-        qd = conv2d(cross, p.query_conv_depth.weight, p.query_conv_depth.bias)
-        kd = conv2d(front, p.key_conv_depth.weight, p.key_conv_depth.bias)
-        vd = conv2d(dfeat, p.value_conv_depth.weight, p.value_conv_depth.bias)
-        T, S, attn = _CctSelect.apply(q, k, v, qd, kd)
-        fused = conv2d([(front, False), (T, False)], p.f_conv.weight, p.f_conv.bias, pad=1)
-        return _CctCombine.apply(front, fused, S, attn, vd), S, attn
-    q = conv2d(cross, p.query_conv.weight, p.query_conv.bias).reshape(B, -1, n)
-    k = conv2d(front, p.key_conv.weight, p.key_conv.bias).reshape(B, -1, n).permute(0, 2, 1)
-    energy = torch.bmm(k, q)
-    star, arg = energy.max(dim=1)
-    v = conv2d(front_hat, p.value_conv.weight, p.value_conv.bias).reshape(B, -1, n)
-    T = torch.gather(v, 2, arg.view(B, 1, n).expand(-1, v.shape[1], -1)).reshape(B, -1, a, b)
-    S = star.view(B, 1, a, b)
-    fused = conv2d([(front, False), (T, False)], p.f_conv.weight, p.f_conv.bias, pad=1)
-    out = front + fused * S
-    qd = conv2d(cross, p.query_conv_depth.weight, p.query_conv_depth.bias).reshape(B, -1, n)
-    kd = conv2d(front, p.key_conv_depth.weight, p.key_conv_depth.bias).reshape(B, -1, n).permute(0, 2, 1)
+    if a != b or a * b > 256:
+        raise _lib.JpbError("cct_attention kernels take square maps of at most 256 positions (got %dx%d)" % (a, b))
+    q = conv2d(cross, p.query_conv.weight, p.query_conv.bias)
+    k = conv2d(front, p.key_conv.weight, p.key_conv.bias)
+    v = conv2d(front_hat, p.value_conv.weight, p.value_conv.bias)
+    qd = conv2d(cross, p.query_conv_depth.weight, p.query_conv_depth.bias)
+    kd = conv2d(front, p.key_conv_depth.weight, p.key_conv_depth.bias)
     vd = conv2d(dfeat, p.value_conv_depth.weight, p.value_conv_depth.bias)
-    attn = torch.bmm(kd, qd).max(dim=1)[0].view(B, 1, a, b)
-    return (out + attn @ vd).contiguous(memory_format=CL), S, attn
+    T, S, attn = _CctSelect.apply(q, k, v, qd, kd)
+    fused = conv2d([(front, False), (T, False)], p.f_conv.weight, p.f_conv.bias, pad=1)
+    return _CctCombine.apply(front, fused, S, attn, vd), S, attn
 
 
 class _PoseHead(torch.autograd.Function):
@@ -358,29 +311,6 @@ def pose_head(x, invert):
     """Spatial mean of the 6-channel PoseDecoder output, x0.01, Rodrigues, 4x4 assembly
     (pose_decoder.py:22-26, net.py:704-756)."""
     _need_cuda(x)
-    if BACKEND["pose_head"] == "jpb" and x.dtype == torch.float32 and x.shape[1] >= 6:
-        return _PoseHead.apply(x, bool(invert))
-    return _pose_head_torch(x, invert)
-
-
-def _pose_head_torch(x, invert):
-    v = 0.01 * x.mean(3).mean(2)
-    aa, t = v[:, :3], v[:, 3:]
-    B = aa.shape[0]
-    ang = aa.norm(dim=1, keepdim=True)
-    ax = aa / (ang + 1e-7)
-    ca, sa = torch.cos(ang)[:, 0], torch.sin(ang)[:, 0]
-    Cc = 1 - ca
-    x_, y_, z_ = ax[:, 0], ax[:, 1], ax[:, 2]
-    R3 = torch.stack([x_ * x_ * Cc + ca, x_ * y_ * Cc - z_ * sa, z_ * x_ * Cc + y_ * sa,
-                      x_ * y_ * Cc + z_ * sa, y_ * y_ * Cc + ca, y_ * z_ * Cc - x_ * sa,
-                      z_ * x_ * Cc - y_ * sa, y_ * z_ * Cc + x_ * sa, z_ * z_ * Cc + ca], 1).view(B, 3, 3)
-    R = torch.zeros(B, 4, 4, dtype=x.dtype, device=x.device)
-    R[:, :3, :3] = R3
-    R[:, 3, 3] = 1
-    T = torch.eye(4, dtype=x.dtype, device=x.device).repeat(B, 1, 1)
-    if invert:
-        T[:, :3, 3] = -t
-        return R.transpose(1, 2) @ T
-    T[:, :3, 3] = t
-    return T @ R
+    if x.dtype != torch.float32 or x.shape[1] < 6:
+        raise _lib.JpbError("pose_head takes an fp32 map with at least 6 channels")
+    return _PoseHead.apply(x, bool(invert))

@@ -2,11 +2,16 @@
 
 TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.  Not imported by ``jperceiver_b200``.
 
-Plain functional torch on the CPU, driven by a flat ``{state_dict key: tensor}`` parameter
+Plain functional torch (the parity oracle runs it on the CPU in fp32), driven by a flat ``{state_dict key: tensor}`` parameter
 dictionary that uses the *reference's* key names, so the same weights can be loaded into the
 reference (``oracle/ref_loader.py``), into this port and into the CUDA product.  Every function
 cites the reference file:line it restates (paths relative to ``/root/reference``; ``M/`` is
 ``mono/model/mono_baseline/``).
+
+The same functions run on a CUDA device when parameters and inputs live there and the caller wraps the call in
+``with torch.device("cuda"):`` (tensor factories then follow the default device): that is the reference's own arithmetic on
+a GPU — eager ATen + cuDNN, TF32 convolutions under torch's default ``cudnn.allow_tf32=True`` — used by
+tests/test_model_parity.py to calibrate the product's TF32 deviation and by ``bench.py``'s ``gpu_eager_baseline`` leg.
 
 Parity status
 -------------
@@ -407,13 +412,13 @@ def static_quad_mask(Minv0, occ, height, width):
            [occ - pr[3][1] - 1, pr[1][0] - 1],
            [occ - pr[3][1] + (pr[2][1] - pr[1][1]) - 1, pr[1][0] - 1]]
     pts = torch.tensor(rot, dtype=torch.float32)
-    ph = torch.cat([pts, torch.ones(4, 1)], 1) @ Minv0.float().T
-    proj = torch.round(ph[:, :2] / ph[:, 2:3]).int().numpy()
+    ph = torch.cat([pts, torch.ones(4, 1)], 1) @ Minv0.float().T.to(pts.device)
+    proj = torch.round(ph[:, :2] / ph[:, 2:3]).int().cpu().numpy()
     poly = np.array([proj[0], proj[2], proj[3], proj[1]], dtype=np.int32).reshape(-1, 1, 2)
     canvas = np.zeros((height, width, 3), dtype=np.uint8)
     canvas = cv2.fillConvexPoly(canvas, poly, (0, 255, 255), 1)
     gray = cv2.cvtColor(canvas, cv2.COLOR_RGB2GRAY)
-    return torch.from_numpy((gray > 0).astype(np.float32))
+    return torch.from_numpy((gray > 0).astype(np.float32)).to(Minv0.device)
 
 
 def scale_label(opt, inputs, warp_align_corners=True):
@@ -498,7 +503,7 @@ def bev_head_loss(logits, label, w_fg, loss_weight=20.0, loss2_weight=20.0, loss
             raise ValueError(loss_type)
     if loss_sum == 1:
         return loss_weight * region
-    phi = torch.from_numpy(np.stack([signed_distance(m) for m in y.numpy()])).to(torch.float32)
+    phi = torch.from_numpy(np.stack([signed_distance(m) for m in y.cpu().numpy()])).to(torch.float32).to(logits.device)
     bd = (p[:, 1] * phi).mean()
     if loss_sum == 2:
         return loss_weight * region + loss2_weight * bd

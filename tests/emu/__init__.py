@@ -23,6 +23,8 @@ EXCLUDE = ("conv_tc.cu", "tma_util.cu")
 def build_emulation(mt: bool | None = None) -> str:
     """``mt=False``: one "thread" per block (fast; kernel arithmetic and indexing).  ``mt=True``: ``-DJPB_HOST_EMU_MT`` — every
     block runs with its real thread count on OS threads with real barriers / shuffles (slow; synchronisation and reductions)."""
+    from .torch_ops import install_conv_patch
+    install_conv_patch()   # the emulation build has no tcgen05 convolution: library convolution while it is installed
     if mt is None:   # JPB_EMU_MT=1 python -m pytest tests/<file> -m "not gpu": any emulation suite with real block threads
         mt = os.environ.get("JPB_EMU_MT", "0") not in ("", "0")
     os.makedirs(OUT, exist_ok=True)

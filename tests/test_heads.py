@@ -14,6 +14,7 @@ from conftest import GOLDEN
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from emu import build_emulation  # noqa: E402
+from emu.torch_ops import cct_attention_torch, pose_head_torch  # noqa: E402
 
 from jperceiver_b200 import _lib, netops as ops  # noqa: E402
 
@@ -74,7 +75,7 @@ def test_pose_head_forward_backward_vs_torch(dev, invert):
     g = torch.Generator().manual_seed(2)
     x = (torch.randn(3, 6, 6, 20, generator=g) * 3 + 1.0)
     x0 = x.clone().requires_grad_(True)
-    ref = ops._pose_head_torch(x0, invert)
+    ref = pose_head_torch(x0, invert)
     G = torch.randn(3, 4, 4, generator=g)
     (g0,) = torch.autograd.grad(ref, x0, G)
     x1 = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
@@ -139,16 +140,14 @@ def test_cct_attention_forward_backward_vs_torch(dev):
         setattr(p, name, m.to(dev).to(memory_format=torch.channels_last))
     res = {}
     for backend in ("torch", "jpb"):
-        ops.BACKEND["cct_attention"] = backend
         ins = [t.clone().to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in tensors]
-        out, S, attn = ops.cct_attention(*ins, p)
+        out, S, attn = ops.cct_attention(*ins, p) if backend == "jpb" else cct_attention_torch(*ins, p, ops.conv2d)
         G = torch.Generator().manual_seed(9)
         go = torch.randn(out.shape, generator=G).to(dev)
         loss = (out * go).sum() + (S * 0.7).sum() - (attn * 0.3).sum()
         params = [getattr(p, n_).weight for n_ in ("query_conv", "key_conv", "value_conv", "f_conv", "key_conv_depth", "value_conv_depth")]
         grads = torch.autograd.grad(loss, ins + params)
         res[backend] = [out.detach().cpu(), S.detach().cpu(), attn.detach().cpu()] + [t.cpu() for t in grads]
-    ops.BACKEND["cct_attention"] = "jpb"
     for a, b in zip(res["torch"], res["jpb"]):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1.0)

@@ -14,6 +14,7 @@ from conftest import GOLDEN, pat
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from emu import build_emulation  # noqa: E402
+from emu.torch_ops import torch_conv  # noqa: E402
 from oracle import port as O  # noqa: E402
 
 from jperceiver_b200 import _lib, functional as JF  # noqa: E402
@@ -342,12 +343,12 @@ def test_small_n_conv_forward_backward_vs_torch(dev, C, N, up, reflect, act):
     w = torch.randn(N, C, 3, 3, generator=g) / (C * 9) ** 0.5
     b = torch.randn(N, generator=g)
     x0, w0 = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
-    ref = JC._torch_conv([x0], [bool(up)], w0, b, 1, 1, bool(reflect), act, None)
+    ref = torch_conv([x0], [bool(up)], w0, b, 1, 1, bool(reflect), act, None)
     x1 = D(x, dev).contiguous(memory_format=torch.channels_last)
     w1 = D(w, dev).contiguous(memory_format=torch.channels_last)
     got = JC.smalln_fwd(x1, bool(up), w1, D(b, dev), bool(reflect), act)
     assert (got.cpu() - ref.detach()).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
-    z = JC._torch_conv([x0], [bool(up)], w0, b, 1, 1, bool(reflect), "none", None)
+    z = torch_conv([x0], [bool(up)], w0, b, 1, 1, bool(reflect), "none", None)
     dz = torch.randn(z.shape, generator=g)
     z.backward(dz)
     gw, gx = JC.smalln_bwd(x1, bool(up), D(dz, dev).contiguous(memory_format=torch.channels_last), w1, bool(reflect))

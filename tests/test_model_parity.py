@@ -44,7 +44,8 @@ def test_state_dict_layout_matches_reference():
     assert sum(p.numel() for p in model.parameters()) == 53737194
 
 
-def run_case(dev, typ, H, W, occ, B, hw_full, fids=(0, -1, 1), rel=1e-3, loose=False):
+def run_case(dev, typ, H, W, occ, B, hw_full, fids=(0, -1, 1), rel=1e-3, loose=False, precision="3xtf32"):
+    """``precision``: arithmetic of the tcgen05 convolutions on the GPU (``conv.precision``); ignored under emulation."""
     torch.set_num_threads(os.cpu_count() or 1)
     split = "argo" if typ.startswith("Argo") else "odometry"
     opt = default_options(type=typ, split=split, height=H, width=W, occ_map_size=occ, frame_ids=list(fids), imgs_per_gpu=B)
@@ -84,9 +85,11 @@ def run_case(dev, typ, H, W, occ, B, hw_full, fids=(0, -1, 1), rel=1e-3, loose=F
         d = (mine - ref).abs()
         assert (d > 2e-3).float().mean().item() < 2e-3 and d.mean().item() < 5e-5
         model.scale_label_override = ref.to(dev)
-    po, pl = model({k: v.to(dev) for k, v in inp.items()})
-    pt = sum(v for v in pl.values())
-    pt.backward()
+    from jperceiver_b200 import conv as JC
+    with JC.precision(precision):
+        po, pl = model({k: v.to(dev) for k, v in inp.items()})
+        pt = sum(v for v in pl.values())
+        pt.backward()
     assert set(map(str, pl.keys())) == set(map(str, ol.keys()))
     for k in ol:
         a, b = float(pl[k]), float(ol[k])
@@ -128,23 +131,22 @@ def run_case(dev, typ, H, W, occ, B, hw_full, fids=(0, -1, 1), rel=1e-3, loose=F
     return worst
 
 
+def _rel(dev):
+    """Emulation: fp32 library convolutions, tight.  GPU: the product's tcgen05 convolutions in 3xTF32 mode at the north-star 1e-3."""
+    return 2e-4 if dev.type == "cpu" else 1e-3
+
+
 def test_argo_both_small(dev):
-    if dev.type == "cuda":
-        pytest.skip("covered at full size in test_full_size_gpu")
-    run_case(dev, "Argo_both", 256, 256, 64, 2, (120, 400), rel=2e-4)
+    run_case(dev, "Argo_both", 256, 256, 64, 2, (120, 400), rel=_rel(dev))
 
 
 def test_static_nonsquare_small(dev):
-    if dev.type == "cuda":
-        pytest.skip("covered at full size in test_full_size_gpu")
-    run_case(dev, "static", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
+    run_case(dev, "static", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=_rel(dev))
 
 
 def test_dynamic_small(dev):
     """``type='dynamic'`` (/net.py:119-159): vehicle heads only + the dynamic CGT label (net.py:311-402)."""
-    if dev.type == "cuda":
-        pytest.skip("the dynamic label kernel is covered on the GPU by tests/test_zz_dynamic_label.py")
-    run_case(dev, "dynamic", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=2e-4)
+    run_case(dev, "dynamic", 128, 384, 64, 2, (120, 400), fids=(0, -1), rel=_rel(dev))
 
 
 @pytest.mark.parametrize("typ", ["static_eigen", "Argo_static", "Argo_dynamic"])
@@ -152,62 +154,99 @@ def test_other_types_small(dev, typ):
     """The remaining ``opt.type`` values: ``static_eigen`` (BASELINE.json config 5; neither reference net defines it — pinned to
     depth + pose only, SURVEY.md §8 a-0 iii) and the Argoverse single-head types of /net.py:114-159 (oracle pinned by
     tests/golden/e2e_Argo_static_1024.npz / e2e_Argo_dynamic_1024.npz)."""
-    if dev.type == "cuda":
-        pytest.skip("type dispatch is host logic; its kernels are covered on the GPU by test_full_size_gpu / test_zz_dynamic_label")
     hw = (120, 400) if typ == "static_eigen" else (200, 240)
-    run_case(dev, typ, 128, 384, 64, 2, hw, fids=(0, -1), rel=2e-4)
+    run_case(dev, typ, 128, 384, 64, 2, hw, fids=(0, -1), rel=_rel(dev))
 
 
 def test_baseline_config0_b1_192x640(dev):
     """BASELINE.json configs[0] — ``cfg_kitti_baseline_odometry_boundary_ce_iou_1024_20_B1``: one 192x640 3-frame snippet (B=1: the
     reference's ``shape[0]==256`` squeeze hack in compute_topview_loss, net.py:557-559), occ_map_size 256, type static, full
     375x1242 frame for the CGT label; forward + losses + backward against the oracle."""
-    if dev.type == "cuda":
-        pytest.skip("B=1 plumbing case; the GPU parity cases run at the bench shape (test_full_size_gpu)")
-    run_case(dev, "static", 192, 640, 256, 1, (375, 1242), fids=(0, -1, 1), rel=2e-4)
+    run_case(dev, "static", 192, 640, 256, 1, (375, 1242), fids=(0, -1, 1), rel=_rel(dev))
+
+
+def _setup_case(typ, H, W, occ, B, hw_full, fids=(0, -1, 1)):
+    split = "argo" if typ.startswith("Argo") else "odometry"
+    opt = default_options(type=typ, split=split, height=H, width=W, occ_map_size=occ, frame_ids=list(fids), imgs_per_gpu=B)
+    model = MONO.module_dict["Baseline"](opt)
+    P = O.synth_params(model.state_dict(), seed=5)
+    model.load_state_dict(P)
+    inp = O.synth_inputs(opt, B, seed=2, hw_full=hw_full)
+    g = torch.Generator().manual_seed(9)
+    masks = ((torch.rand(B, 512, H // 32, W // 32, generator=g) >= 0.5).float(), (torch.rand(B, 256, H // 16, W // 16, generator=g) >= 0.5).float())
+    noise = {s: [1e-5 * torch.randn(B, 1, H, W, generator=g) for _ in range(len(fids) - 1)] for s in range(4)}
+    return opt, model, P, inp, masks, noise
 
 
 @pytest.mark.gpu
-def test_full_size_gpu_tf32():
-    """The product configuration: tcgen05 TF32 convolutions.  A TF32 rounding can flip one of the network's hard
-    arg-max selections or move a 128-sample BatchNorm statistic, so whole-model agreement with the fp32 oracle is
-    statistical: 1e-2 on the photometric / smoothness terms, 1e-1 on the scale term (depth = 1/(a+b*disp) amplifies disparity noise), 5e-2 on the BEV terms, disparity
-    maps within 3e-2 max / 2e-3 mean absolute.  (Layer-level TF32 parity: tests/test_conv.py, 3e-3 of max|y|.)"""
-    from jperceiver_b200 import netops
+def test_full_size_gpu_tf32_calibrated_against_cudnn_tf32():
+    """The BENCHMARKED arithmetic (tcgen05 kind::tf32, one product per term) against the reference's own GPU arithmetic.
+
+    Three runs of the same training step (320x1024, B=2, type static) on identical weights / inputs / dropout masks / noise:
+      (o) the fp32 oracle on the CPU — the parity anchor;
+      (c) the same oracle code on cuda:0 with torch's defaults (``cudnn.allow_tf32=True``): what the reference computes on a GPU;
+      (p) the product with ``conv.precision("tf32")``.
+    A TF32 rounding can flip a hard arg-max (CrossViewTransformer) or move a small BatchNorm statistic, so neither (c) nor (p)
+    meets 1e-3 against (o); the claim checked here is that the product is no further from fp32 than cuDNN-TF32 is:
+    deviation(p) <= 1.5 x deviation(c) on every disparity map (mean absolute difference — a statistic over >= 5k pixels) and on
+    every loss term (with the north-star 1e-3 relative floor under which a deviation counts as zero)."""
+    from jperceiver_b200 import conv as JC
     _lib._handle, _lib._emulated = None, False
-    assert netops.BACKEND["conv2d"] == "jpb"
-    run_case(torch.device("cuda:0"), "static", 320, 1024, 256, 2, (375, 1242), loose=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    dev = torch.device("cuda:0")
+    opt, model, P, inp, masks, noise = _setup_case("static", 320, 1024, 256, 2, (375, 1242))
+    with torch.no_grad():
+        oo, ol = O.forward({k: v.clone() for k, v in P.items()}, opt, {k: v.clone() for k, v in inp.items()}, training=True,
+                           drop_masks=masks, noise=noise)
+        assert torch.backends.cudnn.allow_tf32, "torch default (the reference's GPU arithmetic) expected"
+        with torch.device(dev):
+            co, cl = O.forward({k: v.clone().to(dev) for k, v in P.items()}, opt, {k: v.to(dev) for k, v in inp.items()}, training=True,
+                               drop_masks=tuple(m.to(dev) for m in masks), noise={s: [n.to(dev) for n in noise[s]] for s in noise})
+    model.to(dev).train()
+    model.DepthDecoder.drop_masks = tuple(m.to(dev) for m in masks)
+    model.noise_override = {s: [n[:, 0].to(dev) for n in noise[s]] for s in noise}
+    with JC.precision("tf32"), torch.no_grad():
+        po, pl = model({k: v.to(dev) for k, v in inp.items()})
+    report = []
+    for s_ in range(4):
+        ref = oo[("disp", 0, s_)]
+        d_c = (co[("disp", 0, s_)].cpu() - ref).abs().mean().item()
+        d_p = (po[("disp", 0, s_)].cpu() - ref).abs().mean().item()
+        report.append((("disp", s_), d_p, d_c))
+        assert d_p <= 1.5 * d_c + 1e-7, ("disp", s_, d_p, d_c)
+    for k in ol:
+        b = float(ol[k])
+        d_c, d_p = abs(float(cl[k]) - b), abs(float(pl[k]) - b)
+        report.append((k, d_p / max(abs(b), 1e-6), d_c / max(abs(b), 1e-6)))
+        assert d_p <= max(1.5 * d_c, 1e-3 * max(abs(b), 1e-6)), (k, float(pl[k]), float(cl[k]), b)
+    print("\nTF32 calibration (deviation from the fp32 oracle: product, cuDNN-TF32):")
+    for k, dp, dc in report:
+        print("  %-32s %.3e  %.3e" % (str(k), dp, dc))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("typ", ["static", "Argo_both", "static_raw"])
+@pytest.mark.parametrize("typ", ["static", "Argo_both", "static_raw", "static_eigen"])
 def test_full_size_gpu(typ):
-    """BASELINE.json shape 320x1024 (non-square rule a-8), B=2, frames [0,-1,1]; tolerance 1e-3 relative on
-    every loss scalar (north star), 5e-3 of max-abs on output maps, 5e-2 relative L2 on parameter gradients
-    (conv math runs in TF32 on the GPU, the oracle in fp32)."""
+    """BASELINE.json shape 320x1024 (non-square rule a-8), B=2, frames [0,-1,1], THROUGH THE PRODUCT'S tcgen05 CONVOLUTIONS in
+    their 3xTF32 precision mode (hi*hi + hi*lo + lo*hi in one TMEM accumulator): tolerance 1e-3 relative on every loss scalar
+    (north star), 5e-3 of max-abs on output maps, 5e-2 relative L2 on parameter gradients.  (The TF32 mode the bench runs is
+    held against cuDNN-TF32 by the calibration test above.)"""
     _lib._handle, _lib._emulated = None, False
     hw = (2056, 2464) if typ == "Argo_both" else (375, 1242)
-    # The network contains hard arg-max selections (CrossViewTransformer) and batch-statistics BatchNorm over as
-    # few as 128 values: TF32 rounding in a convolution can flip a selection, which is a discontinuous change of
-    # every downstream value (the reference's own GPU run differs from its CPU run the same way).  Whole-model
-    # parity is therefore taken with library convolutions held to true fp32; the tensor-core convolution kernels
-    # are compared layer by layer (tests/test_conv.py) at a TF32-appropriate tolerance.
-    from jperceiver_b200 import netops
-    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, netops.BACKEND["conv2d"]
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-    netops.BACKEND["conv2d"] = "torch"
-    try:
-        run_case(torch.device("cuda:0"), typ, 320, 1024, 256, 2, hw, rel=1e-3)
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, netops.BACKEND["conv2d"] = old
+    run_case(torch.device("cuda:0"), typ, 320, 1024, 256, 2, hw, rel=1e-3, precision="3xtf32")
+
+
+@pytest.mark.gpu
+def test_argo_both_native_1024_gpu():
+    """BASELINE.json configs[3] at its file-native shape: 1024x1024, dual BEV heads + CCT, frames [0,-1], B=1 (the shape at which
+    the reference's layout branch is defined without the non-square rule)."""
+    _lib._handle, _lib._emulated = None, False
+    run_case(torch.device("cuda:0"), "Argo_both", 1024, 1024, 256, 1, (2056, 2464), fids=(0, -1), rel=1e-3, precision="3xtf32")
 
 
 def test_eval_mode_outputs_match_oracle(dev):
     """Inference path (SURVEY.md §8(f)-4, ``model.eval()``): BatchNorm running statistics, no dropout, no pose / loss branch;
     ``Baseline.forward`` returns the outputs dict only (net.py:77-82).  Host emulation (fp32 library convolutions): tight."""
-    if dev.type == "cuda":
-        pytest.skip("training-mode parity covers the GPU kernels at full size; the eval-only kernel (BatchNorm with running "
-                    "statistics) is checked under emulation")
     torch.set_num_threads(os.cpu_count() or 1)
     opt = default_options(type="Argo_both", split="argo", height=256, width=256, occ_map_size=64, frame_ids=[0, -1, 1], imgs_per_gpu=2)
     model = MONO.module_dict["Baseline"](opt)
@@ -215,7 +254,8 @@ def test_eval_mode_outputs_match_oracle(dev):
     model.load_state_dict(P)
     model.to(dev).eval()
     inp = O.synth_inputs(opt, 2, seed=4, hw_full=(120, 400))
-    with torch.no_grad():
+    from jperceiver_b200 import conv as JC
+    with torch.no_grad(), JC.precision("3xtf32"):
         ref = O.forward({k: v.clone() for k, v in P.items()}, opt, {k: v.clone() for k, v in inp.items()}, training=False)
         got = model({k: v.to(dev) for k, v in inp.items()})
     assert isinstance(got, dict)
@@ -236,8 +276,6 @@ def test_standalone_pose_modules_copy_weights_by_name(dev):
     """``scripts/draw_odometry.py:49-69``: ``PoseEncoder(18, None, 2)`` / ``PoseDecoder(num_ch_enc)`` built on their own, weights
     copied from a training checkpoint by ``'PoseEncoder.' + name`` / ``'PoseDecoder.' + name``, eval-mode forward of a
     concatenated frame pair -> (axisangle, translation).  The state_dict key names are part of the API."""
-    if dev.type == "cuda":
-        pytest.skip("module surface is host logic; the pose kernels are covered by tests/test_heads.py and test_full_size_gpu")
     from jperceiver_b200.model.mono_baseline.networks import PoseDecoder, PoseEncoder
     opt = default_options(type="static", split="odometry", height=128, width=384, occ_map_size=64, frame_ids=[0, -1], imgs_per_gpu=1)
     full = MONO.module_dict["Baseline"](opt)
@@ -252,7 +290,8 @@ def test_standalone_pose_modules_copy_weights_by_name(dev):
     pose_decoder.to(dev).eval()
     g = torch.Generator().manual_seed(5)
     pair = torch.rand(2, 6, 192, 640, generator=g)
-    with torch.no_grad():
+    from jperceiver_b200 import conv as JC
+    with torch.no_grad(), JC.precision("3xtf32"):
         axisangle, translation = pose_decoder(pose_encoder(pair.to(dev)))
         feats = O.resnet18_features(checkpoint["state_dict"], "PoseEncoder.encoder", pair, False)
         aa, t = O.pose_decoder(checkpoint["state_dict"], "PoseDecoder", feats[-1])

@@ -8,6 +8,12 @@ import pytest
 import torch
 
 from jperceiver_b200 import _lib
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu.torch_ops import torch_conv  # noqa: E402
+
 from jperceiver_b200 import conv as JC
 
 pytestmark = pytest.mark.gpu
@@ -45,8 +51,8 @@ def test_conv_forward_many_tiles_per_cta(case):
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        ref0 = JC._torch_conv(xs, ups, weight, bias, stride, pad, reflect, "none", None)
-        ref = JC._torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, None)
+        ref0 = torch_conv(xs, ups, weight, bias, stride, pad, reflect, "none", None)
+        ref = torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, None)
     finally:
         torch.backends.cudnn.allow_tf32 = old
     for rep in range(2):                      # twice: the second launch meets warm caches and a different block schedule
