@@ -191,7 +191,12 @@ typedef struct JpbConvArgs {
   int dbg_skip;                         /* timing experiments only (results are wrong): bit 0 = no A gather, bit 1 = no weight TMA */
   double* stats;                        /* optional BatchNorm statistics fused into the epilogue: stats[c] += sum over rows of
                                            out[.][c], stats[N + c] += sum of squares (jpb_bn_stats_accumulator; no split-K, N % 4 == 0) */
+  float acc_scale;                      /* 0 = 1.  tcgen05 kind::tf32 TRUNCATES both operands to 10 mantissa bits (cuDNN rounds to nearest):
+                                           every product is short by 2 * 2^-11 * ln 2 = 6.8e-4 on average, a coherent bias that compounds
+                                           through the BatchNorm-free decoder.  The raw accumulator is multiplied by this factor
+                                           (JPB_TF32_TRUNC_COMP for plain fp32 operands, 1 for pre-split 3xTF32 operands) before the epilogue. */
 } JpbConvArgs;
+#define JPB_TF32_TRUNC_COMP 1.00067702f  /* 1 + 2 * 2^-11 * ln 2 */
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);
 
 /* weight gradient of the same operator: dw[n][k] (+)= sum_p im2col[p][k] * dy[p][n], k in the chunk order of `table`.
@@ -212,6 +217,7 @@ typedef struct JpbConvWgradArgs {
   int splits;
   float* dbg;                /* debug only: first pipeline stage (A then B tile) is copied here when non-NULL */
   int accumulate;            /* 1: always add into dw (dw aliases the parameter's slot of the flat gradient buffer) */
+  float acc_scale;           /* as JpbConvArgs.acc_scale */
   int dy_pitch;              /* floats between consecutive pixels of dy; 0 = N (dense).  The 3xTF32 mode passes the hi or lo
                                 half of a split gradient tensor (jpb_tf32_split): pitch = 2 * N */
 } JpbConvWgradArgs;

@@ -81,7 +81,7 @@ class ConvArgs(C.Structure):
         ("dst", C.c_void_p * 3), ("dst_C", C.c_int * 3), ("dst_H", C.c_int * 3), ("dst_W", C.c_int * 3), ("dst_up", C.c_int * 3),
         ("ndst", C.c_int), ("fold_pad", C.c_int), ("fold_reflect", C.c_int), ("fold_H", C.c_int), ("fold_W", C.c_int),
         ("ntaps", C.c_int), ("kw", C.c_int), ("ksplit", C.c_int), ("kcol", C.c_void_p), ("l1_gather", C.c_int),
-        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p),
+        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p), ("acc_scale", C.c_float),
     ]
 
 
@@ -91,7 +91,7 @@ class ConvWgradArgs(C.Structure):
         ("nsrc", C.c_int), ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("N", C.c_int),
         ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("table", C.c_void_p), ("nchunks", C.c_int),
         ("dy", C.c_void_p), ("dw", C.c_void_p), ("w_row", C.c_longlong), ("w_cols", C.c_int), ("splits", C.c_int),
-        ("dbg", C.c_void_p), ("accumulate", C.c_int), ("dy_pitch", C.c_int),
+        ("dbg", C.c_void_p), ("accumulate", C.c_int), ("acc_scale", C.c_float), ("dy_pitch", C.c_int),
     ]
 
 

@@ -31,6 +31,31 @@ L1_GATHER = int(_os.environ.get("JPB_CONV_L1", "1"))
 #   "3xtf32" operands split into TF32 hi + lo parts (jpb_tf32_split), hi*hi + hi*lo + lo*hi accumulated in the same TMEM tile
 #            as a 3x longer K — fp32-grade results (reference with allow_tf32 = False / its CPU path), ~3x the tensor work
 PRECISION = _os.environ.get("JPB_CONV_PRECISION", "tf32")
+# kind::tf32 truncates its operands (cuDNN's TF32 kernels round to nearest); the mean shortfall of a product of two truncated
+# operands, 2 * 2^-11 * ln 2, is folded back into the accumulator (include/jpb200.h: JpbConvArgs.acc_scale).  Measured effect on
+# the whole network: tests/test_model_parity.py::test_full_size_gpu_tf32_calibrated_against_cudnn_tf32.
+TRUNC_COMP = float(_os.environ.get("JPB_TF32_TRUNC_COMP", "1.00067702"))
+
+
+def _acc_scale():
+    return 1.0 if PRECISION == "3xtf32" else TRUNC_COMP
+
+
+class trunc_comp:
+    """``with conv.trunc_comp(1.0): ...`` — scoped override of the truncation compensation (tests that feed operands which ARE
+    TF32-representable, so that nothing is truncated and the products are exact)."""
+
+    def __init__(self, value):
+        self.value = float(value)
+
+    def __enter__(self):
+        global TRUNC_COMP
+        self.old, TRUNC_COMP = TRUNC_COMP, self.value
+        return self
+
+    def __exit__(self, *exc):
+        global TRUNC_COMP
+        TRUNC_COMP = self.old
 
 
 class precision:
@@ -329,6 +354,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     a.ntaps, a.kw = kh * kw, kw
     a.kcol, a.l1_gather = (ptr(kcol) if kcol is not None else None), int(L1_GATHER and kcol is not None)
     a.act = 0
+    a.acc_scale = _acc_scale()
     ks = _ksplit(B * a.Ho * a.Wo, Cin, table.shape[0] // 8)
     if ks > 1:
         a.ksplit = ks
@@ -374,6 +400,7 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None)
     dw = target if direct else torch.zeros(Nc, wcols, dtype=torch.float32, device=dev)
     a = _lib.ConvWgradArgs()
     a.accumulate = int(direct)
+    a.acc_scale = _acc_scale()
     _fill_sources(a, xs, ups)
     a.B = B
     a.Hin = xs[0].shape[2] * (2 if ups[0] else 1)
@@ -500,6 +527,7 @@ class _ConvTC(torch.autograd.Function):
             out.zero_()
         a = _lib.ConvArgs()
         a.ksplit = ks
+        a.acc_scale = _acc_scale()
         _fill_sources(a, xs_k, ups)
         a.B, a.Hin, a.Win, a.Ho, a.Wo, a.N = B, Hin, Win, Ho, Wo, N
         a.stride, a.pad, a.reflect = stride, pad, int(reflect)

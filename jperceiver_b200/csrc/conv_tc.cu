@@ -133,7 +133,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+// `scale`: truncation-bias compensation of kind::tf32 (JpbConvArgs.acc_scale), applied to the raw accumulator
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v, float scale = 1.f) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -141,10 +142,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * scale;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v, float scale = 1.f) {
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -155,7 +156,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * scale;
 }
 
 // BatchNorm statistics fused into the convolution epilogue: lanes l, l+8, l+16, l+24 hold sums of the same four output
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.B * a.Ho * a.Wo;
+  const float acc_scale = a.acc_scale != 0.f ? a.acc_scale : 1.f;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT;
   // debug timeline (tools/conv_timeline.py): stamps[cta][warp][slot] = globaltimer ns at fixed points of each role
 #define JPB_STAMP(slot)                                                                                         \
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       const int c4 = (lane & 7) * 4, r0 = lane >> 3;
       for (int j = 0; j < NT; j += 32) {
         float v[32];
-        tmem_ld32(taddr + (uint32_t)j, v);
+        tmem_ld32(taddr + (uint32_t)j, v, acc_scale);
         for (int q = 0; q < 32; q += 4)
           sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
         __syncwarp();
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     } else {
     for (int j = 0; j < NT; j += 16) {
       float v[16];
-      tmem_ld16(taddr + (uint32_t)j, v);   // warp-collective: every lane executes it, even for rows >= M
+      tmem_ld16(taddr + (uint32_t)j, v, acc_scale);   // warp-collective: every lane executes it, even for rows >= M
       if (m < M) {
         const int nleft = nvalid - j;
         if (nleft >= 16 && vec_ok) {
@@ -575,6 +577,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = a.B * a.Ho * a.Wo;
+  const float acc_scale = a.acc_scale != 0.f ? a.acc_scale : 1.f;
   const int mtiles = (M + BM - 1) / BM, ntiles = (a.N + NT - 1) / NT;
   const int ks = a.ksplit > 1 ? a.ksplit : 1;
   const int total = mtiles * ntiles * ks;
@@ -810,7 +813,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.bias && vec_ok && col < nvalid) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);   // issued early: overlaps the TMEM load
         float v[32];
-        tmem_ld32(taddr + (uint32_t)j, v);
+        tmem_ld32(taddr + (uint32_t)j, v, acc_scale);
         for (int q = 0; q < 32; q += 4)
           sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
         __syncwarp();
@@ -917,6 +920,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = a.B * a.Ho * a.Wo;
+  const float acc_scale = a.acc_scale != 0.f ? a.acc_scale : 1.f;
   const int mt = blockIdx.x, n0 = blockIdx.y * NT;
   // pixel range of this split, in 32-pixel steps
   const int steps_total = (P + 31) / 32;
@@ -1019,7 +1023,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
     const bool use_atomic = gridDim.z > 1 || a.accumulate;
     for (int j = 0; j < NT; j += 16) {
       float v[16];
-      tmem_ld16(taddr + (uint32_t)j, v);
+      tmem_ld16(taddr + (uint32_t)j, v, acc_scale);
       if (k < a.w_cols) {
         for (int c = 0; c < 16; ++c) {
           const int n = n0 + j + c;

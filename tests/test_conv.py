@@ -85,7 +85,8 @@ def test_conv_forward_matches_fp32_library(case, mode):
         ref = torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, res)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    with JC.precision(prec):
+    # TF32-representable operands are not truncated by the tensor core: no truncation bias to compensate
+    with JC.precision(prec), JC.trunc_comp(1.0 if exact else JC.TRUNC_COMP):
         got = JC.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, res)
     torch.cuda.synchronize()
     assert got.shape == ref.shape and got.is_contiguous(memory_format=CL)
@@ -129,7 +130,7 @@ def test_conv_backward_matches_fp32_library(case, mode):
         res = torch.randn(z.shape, generator=g).to(dev).contiguous(memory_format=CL) if has_res else None
         rr = res.clone().requires_grad_(True) if has_res else None
         rm = res.clone().requires_grad_(True) if has_res else None
-        with JC.precision(prec):
+        with JC.precision(prec), JC.trunc_comp(1.0 if exact else JC.TRUNC_COMP):
             got = JC.conv2d_tc(xm, ups, wm, bm, stride, pad, reflect, act, rm)
         ref = torch_conv(xr, ups, wr, br, stride, pad, reflect, act, rr)      # the reference's OWN activation masks
         gy = rnd(torch.randn(ref.shape, generator=g)).to(dev).contiguous(memory_format=CL)
@@ -142,7 +143,7 @@ def test_conv_backward_matches_fp32_library(case, mode):
         ref.backward(gy)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    with JC.precision(prec):
+    with JC.precision(prec), JC.trunc_comp(1.0 if exact else JC.TRUNC_COMP):
         got.backward(gy)
     torch.cuda.synchronize()
 

@@ -168,7 +168,7 @@ def test_train_mono_runner_checkpoint_resume_eval_on_cuda(tmp_path):
     step LR policy, per-epoch checkpoints in the reference's format, JSON log lines and the device-side ``DistEvalMonoHook``;
     then a fresh process-equivalent resumes from ``latest.pth`` and continues."""
     from jperceiver_b200.apis import Config, train_mono
-    from jperceiver_b200.datasets import get_dataset
+    from jperceiver_b200.datasets.get_dataset import get_dataset
     from jperceiver_b200.model import MONO
     path = tmp_path / "cfg_small.py"
     path.write_text(CFG)

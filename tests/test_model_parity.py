@@ -188,8 +188,10 @@ def test_full_size_gpu_tf32_calibrated_against_cudnn_tf32():
       (p) the product with ``conv.precision("tf32")``.
     A TF32 rounding can flip a hard arg-max (CrossViewTransformer) or move a small BatchNorm statistic, so neither (c) nor (p)
     meets 1e-3 against (o); the claim checked here is that the product is no further from fp32 than cuDNN-TF32 is:
-    deviation(p) <= 1.5 x deviation(c) on every disparity map (mean absolute difference — a statistic over >= 5k pixels) and on
-    every loss term (with the north-star 1e-3 relative floor under which a deviation counts as zero)."""
+    deviation(p) <= 1.5 x deviation(c) on every disparity map (mean absolute difference — a statistic over >= 5k pixels) and
+    <= 2 x on every family of loss terms (see below).  This test is what exposed that ``kind::tf32`` truncates its operands:
+    without the accumulator compensation (``conv.TRUNC_COMP``) the product sat 3-25 x further from fp32 than cuDNN
+    (profiles/r2_tf32_calibration.txt)."""
     from jperceiver_b200 import conv as JC
     _lib._handle, _lib._emulated = None, False
     torch.set_num_threads(os.cpu_count() or 1)
@@ -207,21 +209,34 @@ def test_full_size_gpu_tf32_calibrated_against_cudnn_tf32():
     model.noise_override = {s: [n[:, 0].to(dev) for n in noise[s]] for s in noise}
     with JC.precision("tf32"), torch.no_grad():
         po, pl = model({k: v.to(dev) for k, v in inp.items()})
-    report = []
+    report, bad = [], []
     for s_ in range(4):
         ref = oo[("disp", 0, s_)]
         d_c = (co[("disp", 0, s_)].cpu() - ref).abs().mean().item()
         d_p = (po[("disp", 0, s_)].cpu() - ref).abs().mean().item()
         report.append((("disp", s_), d_p, d_c))
-        assert d_p <= 1.5 * d_c + 1e-7, ("disp", s_, d_p, d_c)
+        if not d_p <= 1.5 * d_c + 1e-7:
+            bad.append((("disp", s_), d_p, d_c))
+    # loss scalars: one number each, i.e. ONE draw of a random deviation — a per-term ratio of two single draws is not a
+    # statistic (two draws from the same half-normal differ by more than 1.5x four times out of ten).  Terms are pooled per
+    # family (the four scales of a term / the BEV head terms): RMS relative deviation of the family, product <= 2 x cuDNN-TF32,
+    # with the north-star 1e-3 as the floor under which a family counts as exact.
+    fam = {}
     for k in ol:
         b = float(ol[k])
-        d_c, d_p = abs(float(cl[k]) - b), abs(float(pl[k]) - b)
-        report.append((k, d_p / max(abs(b), 1e-6), d_c / max(abs(b), 1e-6)))
-        assert d_p <= max(1.5 * d_c, 1e-3 * max(abs(b), 1e-6)), (k, float(pl[k]), float(cl[k]), b)
-    print("\nTF32 calibration (deviation from the fp32 oracle: product, cuDNN-TF32):")
+        d_c, d_p = abs(float(cl[k]) - b) / max(abs(b), 1e-6), abs(float(pl[k]) - b) / max(abs(b), 1e-6)
+        report.append((k, d_p, d_c))
+        fam.setdefault(k[0] if isinstance(k, tuple) else "bev", []).append((d_p, d_c))
+    for name, vals in fam.items():
+        r_p = (sum(v[0] ** 2 for v in vals) / len(vals)) ** 0.5
+        r_c = (sum(v[1] ** 2 for v in vals) / len(vals)) ** 0.5
+        report.append(("family rms " + name, r_p, r_c))
+        if not r_p <= max(2.0 * r_c, 1e-3):
+            bad.append((name, r_p, r_c))
+    print("\nTF32 calibration (deviation from the fp32 oracle: product, cuDNN-TF32; relative for the loss terms):")
     for k, dp, dc in report:
         print("  %-32s %.3e  %.3e" % (str(k), dp, dc))
+    assert not bad, bad
 
 
 @pytest.mark.gpu

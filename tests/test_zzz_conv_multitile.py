@@ -56,7 +56,8 @@ def test_conv_forward_many_tiles_per_cta(case):
     finally:
         torch.backends.cudnn.allow_tf32 = old
     for rep in range(2):                      # twice: the second launch meets warm caches and a different block schedule
-        got = JC.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, None)
+        with JC.trunc_comp(1.0):      # TF32-representable operands: nothing is truncated
+            got = JC.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, None)
         torch.cuda.synchronize()
         err = (got - ref).abs().max().item()
         scale = max(ref0.abs().max().item(), 1e-6)
