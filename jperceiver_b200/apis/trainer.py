@@ -221,6 +221,12 @@ class TrainEngine:
             names, vals, total = loss_scalars(losses)
             JF.DIRECT_GRAD = True  # backward kernels add parameter gradients straight into the flat gradient buffer
             total.backward()
+            # branch-concurrent model: its side streams ran backward nodes that wrote parameter gradients straight into the flat
+            # buffer (no AccumulateGrad node, so autograd's end-of-backward stream sync does not cover them)
+            if hasattr(self.model, "side_streams") and self.flat.grad.is_cuda:
+                cur = torch.cuda.current_stream(self.flat.grad.device)
+                for st in self.model.side_streams():
+                    cur.wait_stream(st)
         finally:
             JF.DIRECT_GRAD = False
             JC.WT.enabled = JC.WT.fresh = False

@@ -419,11 +419,13 @@ def direct_grad_target(p):
 
 
 def _bn_workspace(C, device):
-    """One zero-initialised workspace per device, shared by every BatchNorm launch (they are stream-ordered)."""
+    """One zero-initialised workspace per (device, stream): the BatchNorm launches of a stream are ordered, launches of
+    different streams (the branch-concurrent forward/backward of ``Baseline``) must not share accumulators."""
     need = _lib.lib().jpb_bn_workspace_doubles(max(C, 512))
-    ws = _BN_WS.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream) if device.type == "cuda" else (device, 0)
+    ws = _BN_WS.get(key)
     if ws is None or ws.numel() < need:
-        ws = _BN_WS[device] = torch.zeros(need, dtype=torch.float64, device=device)
+        ws = _BN_WS[key] = torch.zeros(need, dtype=torch.float64, device=device)
     return ws
 
 

@@ -111,6 +111,10 @@ class Baseline(nn.Module):
         self._step = 0
         self.step_counter = None     # optional device int64 step counter (the optimizer's): decorrelates the automask noise per step
         self._quad_cache = {}
+        # three-stream forward/backward (depth | pose | layout trunks); JPB_BRANCH_STREAMS=0 or options['branch_streams']=False: one stream
+        import os as _os
+        self.branch_streams = bool(o.get("branch_streams", _os.environ.get("JPB_BRANCH_STREAMS", "1") not in ("", "0")))
+        self._side = None
         if self.bn_double_update:   # second running-stat update of the reference's duplicated road-head pass
             for m in (self.LayoutEncoder, self.LayoutDecoder, self.LayoutTransformDecoder):
                 for bn in m.modules():
@@ -123,8 +127,11 @@ class Baseline(nn.Module):
         if not inputs[("color_aug", 0, 0)].is_cuda and not JF._lib.is_emulated():
             raise JF._lib.JpbError("Baseline.forward needs CUDA tensors: jperceiver_b200 has no CPU path")
         JF._lib.lib()  # fail loudly if the CUDA library is missing
-        depth_feature = self.DepthEncoder(inputs[("color_aug", 0, 0)])
         self.DepthDecoder.step_counter = getattr(self, "step_counter", None)
+        x = inputs[("color_aug", 0, 0)]
+        if self.branch_streams and x.is_cuda and self.training:
+            return self._forward_branch_streams(inputs)
+        depth_feature = self.DepthEncoder(x)
         outputs = dict(self.DepthDecoder(depth_feature))
         if o["type"] != "static_eigen":
             outputs.update(self.predict_layouts(inputs, depth_feature))
@@ -134,6 +141,54 @@ class Baseline(nn.Module):
             self._step += 1
             return outputs, loss_dict
         return outputs
+
+    def side_streams(self, device=None):
+        """The two side streams of the branch-concurrent forward (created on first use).  Autograd runs every backward node on
+        the stream of its forward, so the pose and layout trunks are concurrent with the depth trunk in both directions; a
+        caller that consumes parameter gradients (``TrainEngine``) must wait for these streams after ``backward()``."""
+        if self._side is None and device is not None:
+            self._side = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        return self._side or ()
+
+    def _forward_branch_streams(self, inputs):
+        """Same operators, three streams: the depth trunk (encoder -> decoder) on the caller's stream, the pose trunk and the
+        layout trunk on two side streams — the three ResNet-18 stacks are independent until the losses (the layout heads need
+        only the depth encoder's last feature map), and their deep, small-extent layers are latency-sized kernels that cannot
+        fill 148 SMs on their own (DESIGN.md §4 "branch streams").  Fork: the side streams wait for the caller's stream;
+        join: the caller's stream waits for both before ``compute_losses``."""
+        o = self.opt
+        x = inputs[("color_aug", 0, 0)]
+        main = torch.cuda.current_stream(x.device)
+        s_pose, s_layout = self.side_streams(x.device)
+        s_pose.wait_stream(main)
+        s_layout.wait_stream(main)
+        outputs = {}
+        with torch.cuda.stream(s_pose):
+            pose_out = self.predict_poses(inputs)
+        layout = o["type"] != "static_eigen"
+        occ = o.occ_map_size
+        if layout:
+            with torch.cuda.stream(s_layout):
+                feat = self.LayoutEncoder(x, (4 * occ, 4 * occ))
+        depth_feature = self.DepthEncoder(x)
+        if layout:
+            l4_ready = torch.cuda.Event()
+            l4_ready.record(main)
+            with torch.cuda.stream(s_layout):
+                s_layout.wait_event(l4_ready)
+                l4 = ops.resize_bilinear(depth_feature[-1], (occ // 8, occ // 8))
+                lay = {"origin_features": feat}
+                lay.update(self._head(feat, l4, "", "road"))
+                lay.update(self._head(feat, l4, "B", "car"))
+        outputs.update(self.DepthDecoder(depth_feature))
+        main.wait_stream(s_pose)
+        main.wait_stream(s_layout)
+        if layout:
+            outputs.update(lay)
+        outputs.update(pose_out)
+        loss_dict = self.compute_losses(inputs, outputs)
+        self._step += 1
+        return outputs, loss_dict
 
     def predict_poses(self, inputs):
         outputs = {}

@@ -90,6 +90,8 @@ def run_case(dev, typ, H, W, occ, B, hw_full, fids=(0, -1, 1), rel=1e-3, loose=F
         po, pl = model({k: v.to(dev) for k, v in inp.items()})
         pt = sum(v for v in pl.values())
         pt.backward()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()      # the branch-concurrent model ran backward nodes on its side streams
     assert set(map(str, pl.keys())) == set(map(str, ol.keys()))
     for k in ol:
         a, b = float(pl[k]), float(ol[k])
