@@ -195,6 +195,11 @@ typedef struct JpbConvArgs {
                                            every product is short by 2 * 2^-11 * ln 2 = 6.8e-4 on average, a coherent bias that compounds
                                            through the BatchNorm-free decoder.  The raw accumulator is multiplied by this factor
                                            (JPB_TF32_TRUNC_COMP for plain fp32 operands, 1 for pre-split 3xTF32 operands) before the epilogue. */
+  int patch;                            /* != 0 (1 = one or two tiles per CTA chosen by the library, 2 / 3 = forced to one / two): 3x3 / stride 1 / zero pad 1 over ONE dense source with C % 32 == 0 and W % 8 == 0: the A operand is
+                                           read as 18 x 16 pixel TMA patches (one per 32-channel block and 16 x 8 output tile) shared by all nine
+                                           taps instead of the per-tap gather; weight columns must be tap-major (tap * C + c); table / kcol unused */
+  int patch_desc_mode;                  /* debug: 2 = set the UMMA matrix-descriptor base offset for the shifted patch start addresses (WRONG on
+                                           B200: the swizzle follows absolute address bits; kept to reproduce the measurement) */
 } JpbConvArgs;
 #define JPB_TF32_TRUNC_COMP 1.00067702f  /* 1 + 2 * 2^-11 * ln 2 */
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);

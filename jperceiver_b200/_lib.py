@@ -81,7 +81,7 @@ class ConvArgs(C.Structure):
         ("dst", C.c_void_p * 3), ("dst_C", C.c_int * 3), ("dst_H", C.c_int * 3), ("dst_W", C.c_int * 3), ("dst_up", C.c_int * 3),
         ("ndst", C.c_int), ("fold_pad", C.c_int), ("fold_reflect", C.c_int), ("fold_H", C.c_int), ("fold_W", C.c_int),
         ("ntaps", C.c_int), ("kw", C.c_int), ("ksplit", C.c_int), ("kcol", C.c_void_p), ("l1_gather", C.c_int),
-        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p), ("acc_scale", C.c_float),
+        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p), ("acc_scale", C.c_float), ("patch", C.c_int), ("patch_desc_mode", C.c_int),
     ]
 
 

@@ -227,6 +227,8 @@ class TrainEngine:
                 cur = torch.cuda.current_stream(self.flat.grad.device)
                 for st in self.model.side_streams():
                     cur.wait_stream(st)
+            if self.flat.grad.is_cuda:
+                JC.join_wgrad_streams(self.flat.grad.device)    # weight gradients launched on companion streams (conv.py)
         finally:
             JF.DIRECT_GRAD = False
             JC.WT.enabled = JC.WT.fresh = False

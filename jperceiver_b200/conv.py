@@ -362,6 +362,8 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
             grads[0].zero_()
     if simple:
         a.out = ptr(grads[0])
+        if (not three) and wcols == kh * kw * Nc and _patch_ok(Nc, Cin, H, W, B, kh, kw, stride, pad, False, 1, False, ks) and a.pad == 1:
+            a.patch, a.patch_desc_mode = 1 + PATCH_TILE_ROWS, PATCH_DESC_MODE
     else:
         a.scatter = 1
         a.ndst = len(xs)
@@ -550,6 +552,8 @@ class _ConvTC(torch.autograd.Function):
         if DBG_STAMPS is not None:
             a.dbg = ptr(DBG_STAMPS)
         a.dbg_skip = DBG_SKIP
+        if src_C == w_C and wcols == kh * kw * Cin and _patch_ok(Cin, N, Hin, Win, B, kh, kw, stride, pad, reflect, len(xs), ups[0], ks):
+            a.patch, a.patch_desc_mode = 1 + PATCH_TILE_ROWS, PATCH_DESC_MODE
         tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
         check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd")
         if finish:
@@ -580,10 +584,77 @@ class _ConvTC(torch.autograd.Function):
         if N % 4:                                    # e.g. the 6-channel pose head: pad dz so rows are whole 16-byte chunks
             dzp = F.pad(dz, (0, 0, 0, 0, 0, _pad4(N) - N)).contiguous(memory_format=CL)
         gxs = [None] * len(xs)
-        if any(ctx.needs_input_grad[4:]):
+        target = direct_grad_target(weight)
+        want_dx = any(ctx.needs_input_grad[4:])
+        if ctx.needs_input_grad[1] and want_dx and target is not None and WGRAD_STREAMS and dzp.is_cuda and PRECISION == "tf32":
+            # engine step: the weight gradient goes straight into the flat gradient buffer and nobody reads it before the end of
+            # backward, so it runs on a companion stream, concurrent with the data gradient of this layer and with whatever
+            # follows on this stream.  Its operands are kept alive until the engine has joined the stream (join_wgrad_streams).
+            cur = torch.cuda.current_stream(dzp.device)
+            ws = _wgrad_stream(cur, dzp.device)
+            _WGRAD_USED.add(ws)
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=target)
+            _WGRAD_KEEP.append((dzp, xs))
+            if gw is not None:          # packed-K layers return a tensor: autograd must see it on its own stream
+                cur.wait_stream(ws)
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
-        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=direct_grad_target(weight)) if ctx.needs_input_grad[1] else None
+            return (None, gw, gb, gr) + tuple(gxs)
+        if want_dx:
+            gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
+        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=target) if ctx.needs_input_grad[1] else None
         return (None, gw, gb, gr) + tuple(gxs)
+
+
+# ---- weight gradients on companion streams (engine steps only) ----
+WGRAD_STREAMS = _os.environ.get("JPB_WGRAD_STREAMS", "1") not in ("", "0")
+_WGRAD_STREAM: dict = {}      # (device, home stream handle) -> companion stream
+_WGRAD_KEEP: list = []        # operands of weight-gradient launches in flight on companion streams
+_WGRAD_USED: set = set()      # companion streams with launches since the last join (only these may be waited on: a stream that
+                              # was last used OUTSIDE a graph capture must not be joined from inside one)
+
+
+def _wgrad_stream(cur, device):
+    key = (str(device), cur.cuda_stream)
+    st = _WGRAD_STREAM.get(key)
+    if st is None:
+        st = _WGRAD_STREAM[key] = torch.cuda.Stream(device)
+    return st
+
+
+def join_wgrad_streams(device):
+    """Make the current stream wait for every companion stream, then release the operands kept for them (TrainEngine calls
+    this right after ``backward()``, before the gradient exchange)."""
+    if not _WGRAD_KEEP:
+        return
+    cur = torch.cuda.current_stream(device)
+    for st in _WGRAD_USED:
+        cur.wait_stream(st)
+    _WGRAD_USED.clear()
+    _WGRAD_KEEP.clear()
+
+
+# ---- TMA-patch kernel (csrc/conv_tc.cu: conv_tc_patch_kernel) ----
+PATCH = int(_os.environ.get("JPB_CONV_PATCH", "1"))            # 0: always the gather kernels
+PATCH_DESC_MODE = int(_os.environ.get("JPB_CONV_PATCH_DESC", "0"))
+PATCH_MIN_TILES = int(_os.environ.get("JPB_CONV_PATCH_MIN_TILES", "96"))
+PATCH_TILE_ROWS = int(_os.environ.get("JPB_CONV_PATCH_TR", "0"))   # 0: the library picks 1 or 2 tiles per CTA; 1 / 2: forced (tests)
+
+
+def _patch_ok(C, N, H, W, B, kh, kw, stride, pad, reflect, nsrc, up, ks):
+    """3x3 / stride 1 / zero pad 1 over one dense source, channels in whole 32-blocks, rows in whole 8-pixel tiles, enough
+    16x8 tiles to occupy the machine (smaller layers keep the split-K gather kernels)."""
+    if not PATCH or PRECISION != "tf32" or ks > 1:
+        return False
+    if not (kh == 3 and kw == 3 and stride == 1 and pad == 1 and not reflect and nsrc == 1 and not up):
+        return False
+    if C % 32 or N % 16 or W % 8:
+        return False
+    nt = 16
+    while nt < N and nt < 256:
+        nt *= 2
+    return ((N + nt - 1) // nt) * B * ((H + 15) // 16) * (W // 8) >= PATCH_MIN_TILES
 
 
 STATS_FUSED = [False]   # set by the last forward launch: its epilogue accumulated the BatchNorm statistics of its output

@@ -193,6 +193,76 @@ __device__ __forceinline__ void bn_stats_to_smem(uint32_t dst, int NT, int lane,
   }
 }
 
+
+// ---- lean MMA issue (measured: the issuing warp, not the tensor pipe, bounded every kernel of this file) ----
+// `if (lane == 0) tcgen05.mma ...` makes the uniform-datapath instructions execute in divergent code: ptxas wraps EACH of them in
+// an ELECT / BRA.U.ANY "waterfall" loop and moves the descriptors through R2UR, ~100 dependent scalar instructions (~700 cycles)
+// per 32-float K block — more than the 128..512 cycles the four MMAs of that block take on the tensor pipe (ncu source view of
+// conv_tc_patch_kernel<64>: the issuing warp never waits on a barrier, the TMA producer spins on the empty barriers).
+// Here the whole warp stays converged and ONE elect.sync predicate guards the four MMAs of a K block inside a single asm
+// statement; descriptors are 32-bit low words + constant high words, so the advance along K is one integer add.
+__device__ __forceinline__ void umma_tf32_k4(uint32_t tacc, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t acc_first, uint32_t enable) {
+  asm volatile(
+      "{\n"
+      " .reg .pred pe, pa, pt, pv;\n"
+      " .reg .b64 da, db;\n"
+      " .reg .b32 al, bl;\n"
+      " elect.sync _|pe, 0xffffffff;\n"
+      " setp.ne.b32 pv, %7, 0;\n"
+      " and.pred pe, pe, pv;\n"
+      " setp.ne.b32 pa, %6, 0;\n"
+      " setp.eq.b32 pt, %6, %6;\n"
+      " mov.b64 da, {%1, %3};\n"
+      " mov.b64 db, {%2, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pa;\n"
+      " add.u32 al, %1, 2;\n add.u32 bl, %2, 2;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
+      " add.u32 al, %1, 4;\n add.u32 bl, %2, 4;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
+      " add.u32 al, %1, 6;\n add.u32 bl, %2, 6;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
+      "}" ::"r"(tacc), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(enable) : "memory");
+}
+// two independent accumulators, instruction-interleaved (acc0 k0, acc1 k0, acc0 k1, ...): the same weight tile, two A tiles
+__device__ __forceinline__ void umma_tf32_k4x2(uint32_t tacc0, uint32_t tacc1, uint32_t a0_lo, uint32_t a1_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t enable1) {
+  asm volatile(
+      "{\n"
+      " .reg .pred pe, p1, pa, pt, pv;\n"
+      " .reg .b64 da, dc, db;\n"
+      " .reg .b32 al, cl, bl;\n"
+      " elect.sync _|pe, 0xffffffff;\n"
+      " setp.ne.b32 pv, %9, 0;\n"
+      " and.pred p1, pe, pv;\n"
+      " setp.ne.b32 pa, %8, 0;\n"
+      " setp.eq.b32 pt, %8, %8;\n"
+      " mov.b64 da, {%2, %5};\n mov.b64 dc, {%3, %5};\n mov.b64 db, {%4, %6};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pa;\n"
+      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pa;\n"
+      " add.u32 al, %2, 2;\n add.u32 cl, %3, 2;\n add.u32 bl, %4, 2;\n mov.b64 da, {al, %5};\n mov.b64 dc, {cl, %5};\n mov.b64 db, {bl, %6};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pt;\n"
+      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pt;\n"
+      " add.u32 al, %2, 4;\n add.u32 cl, %3, 4;\n add.u32 bl, %4, 4;\n mov.b64 da, {al, %5};\n mov.b64 dc, {cl, %5};\n mov.b64 db, {bl, %6};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pt;\n"
+      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pt;\n"
+      " add.u32 al, %2, 6;\n add.u32 cl, %3, 6;\n add.u32 bl, %4, 6;\n mov.b64 da, {al, %5};\n mov.b64 dc, {cl, %5};\n mov.b64 db, {bl, %6};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pt;\n"
+      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pt;\n"
+      "}" ::"r"(tacc0), "r"(tacc1), "r"(a0_lo), "r"(a1_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(enable1) : "memory");
+}
+// tcgen05.commit -> mbarrier arrive, issued by one elected lane of a converged warp
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_saddr) {
+  asm volatile(
+      "{\n"
+      " .reg .pred pe;\n"
+      " elect.sync _|pe, 0xffffffff;\n"
+      " @pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}" ::"r"(bar_saddr) : "memory");
+}
+constexpr uint32_t DESC_HI_SW128(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }   // bits [32,64) of the descriptor
+constexpr uint32_t DESC_LO_LBO1 = 1u << 16;
+
 struct SrcDev {
   const float* ptr;
   int C, H, W, up;
@@ -1083,6 +1153,271 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
   }
 }
 
+
+// ======================================================================================== 3x3 / stride 1 / zero pad: A from TMA patches
+// The gather kernels above read every input pixel 9 times from L2 (once per filter tap) through 16-byte cp.async — measured to be
+// what bounds them (profiles/README.md).  For the convolutions that are plain 3x3 windows over ONE dense NHWC source (every
+// non-strided ResNet block convolution of the three encoders, forward and data gradient) no gather is needed at all:
+//   * an output tile is 16 image rows x 8 pixels (= 128 GEMM rows); for one block of 32 input channels its whole receptive
+//     field is an 18 x 10 pixel patch.  ONE 4-D TMA box {32 ch, 16 px, 18 rows, 1 image} (zero fill outside the image = the
+//     convolution's zero padding) lands it in shared memory as 18 x 16 rows of 128 bytes, 128-byte swizzled;
+//   * GEMM row i = (tile row i / 8, pixel i % 8) of filter tap (ky, kx) is patch row (i / 8 + ky), pixel (i % 8 + kx): exactly
+//     the canonical K-major SWIZZLE_128B operand with an 8-row group stride of 2048 bytes whose start address is moved by
+//     ky * 2048 + kx * 128 bytes.  All nine taps of a channel block are tcgen05.mma instructions on the SAME patch.
+// L2 -> SM traffic of the A operand drops from 9 x 16 KB to one 36 KB box per channel block, and no thread touches A.
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..), warp 4 TMA (patches + weight tiles), warp 5 MMA issue.
+// Persistent over tiles with the accumulator double-buffered in TMEM.
+constexpr int PATCH_PX = 16;
+// TR: vertically adjacent 16x8 tiles handled together by one CTA (a "super-tile" of 16*TR rows x 8 pixels): one patch of
+// 16*TR + 2 rows and ONE weight tile per (channel block, tap) feed TR accumulators — the weight stream, which dominated the L2 -> SM
+// traffic of the one-tile version (ncu: 302 of 378 MB for 128 -> 128 channels), is halved per output for TR = 2.
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <int NT, int TR, int PSTAGES, int BSTAGES>
+__global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
+                                                                     JpbConvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int B_STAGE = NT * BK * 4;
+  constexpr int ACC_STRIDE = NT < 32 ? 32 : NT;
+  constexpr uint32_t TMEM_COLS = 2 * TR * ACC_STRIDE;
+  static_assert(TMEM_COLS <= 512, "TMEM columns");
+  constexpr int PATCH_ROWS = 16 * TR + 2;
+  constexpr int PATCH_BYTES = PATCH_ROWS * PATCH_PX * 128;
+  constexpr int EPI_WARP_FLOATS = 32 * 36 + 64;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* s_patch = smem;                                   // [PSTAGES][PATCH_BYTES]
+  unsigned char* s_b = smem + PSTAGES * PATCH_BYTES;               // [BSTAGES][B_STAGE]
+  float* epi = reinterpret_cast<float*>(s_b + BSTAGES * B_STAGE);  // [4][EPI_WARP_FLOATS]
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(epi + 4 * EPI_WARP_FLOATS);
+  uint64_t* pempty = pfull + PSTAGES;
+  uint64_t* bfull = pempty + PSTAGES;
+  uint64_t* bempty = bfull + BSTAGES;
+  uint64_t* accf_bar = bempty + BSTAGES;
+  uint64_t* acce_bar = accf_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce_bar + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float acc_scale = a.acc_scale != 0.f ? a.acc_scale : 1.f;
+  const int H = a.Ho, W = a.Wo;                   // stride 1, pad 1: output extent == input extent
+  const int TX = W >> 3, TY = (H + 16 * TR - 1) / (16 * TR);
+  const int ntiles = (a.N + NT - 1) / NT;
+  const int total = ntiles * a.B * TY * TX;
+  const int ncb = a.src_C[0] >> 5;                // 32-channel blocks
+  const int C = a.src_C[0];
+
+  if (tid == 32) {
+    // with two tile rows each has its own MMA-issuing warp: barriers released by MMA completion count TR arrivals
+    for (int i = 0; i < 2; ++i) { mbar_init(&accf_bar[i], TR); mbar_init(&acce_bar[i], 4); }
+    for (int i = 0; i < PSTAGES; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], TR); }
+    for (int s = 0; s < BSTAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], TR); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&wmap)) : "memory");
+    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile t -> (n tile, image, tile row, tile column): neighbouring CTAs work on neighbouring patches of the same N tile
+#define JPB_PTILE(t)                                   \
+  const int tx_ = (t) % TX, r1_ = (t) / TX;            \
+  const int ty_ = r1_ % TY, r2_ = r1_ / TY;            \
+  const int b_ = r2_ % a.B, n0 = (r2_ / a.B) * NT;     \
+  const int ox0 = tx_ * 8, oy0 = ty_ * 16 * TR;
+
+  if (warp == 4) {
+    // ===================================================== TMA producer: one patch per channel block, one weight tile per (block, tap)
+    if (lane == 0) {
+      int pring = 0, bring = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        JPB_PTILE(t)
+        for (int cb = 0; cb < ncb; ++cb, ++pring) {
+          const int ps = pring % PSTAGES;
+          mbar_wait(&pempty[ps], (((uint32_t)(pring / PSTAGES)) & 1u) ^ 1u);
+          if (a.dbg_skip & 1) mbar_arrive(&pfull[ps]);            // timing experiment (wrong results): no patch traffic
+          else {
+            mbar_expect_tx(&pfull[ps], (uint32_t)PATCH_BYTES);
+            tma_load_4d(smem_u32(s_patch + ps * PATCH_BYTES), &xmap, &pfull[ps], cb * 32, ox0 - 1, oy0 - 1, b_);
+          }
+          for (int tap = 0; tap < 9; ++tap, ++bring) {
+            if (a.dbg_skip & 8) continue;                          // timing experiment: no per-tap weight hand-shake at all
+            const int s = bring % BSTAGES;
+            mbar_wait(&bempty[s], (((uint32_t)(bring / BSTAGES)) & 1u) ^ 1u);
+            if (a.dbg_skip & 2) { mbar_arrive(&bfull[s]); continue; }   // timing experiment: no weight traffic
+            mbar_expect_tx(&bfull[s], (uint32_t)B_STAGE);
+            tma_load_2d(smem_u32(s_b + s * B_STAGE), &wmap, &bfull[s], tap * C + cb * 32, n0);
+          }
+        }
+      }
+    }
+  } else if (warp >= 5) {
+    // ===================================================== MMA issuer(s): warp 5 owns tile row 0, warp 6 (TR == 2) tile row 1 — two
+    // independent instruction streams into the tensor pipe; each whole warp walks the loop converged, one elected lane issues
+    const int mr = warp - 5;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t a_hi = DESC_HI_SW128(2048), b_hi = DESC_HI_SW128(1024);
+    const uint32_t patch0 = smem_u32(s_patch), b0addr = smem_u32(s_b);
+    const uint32_t bempty0 = smem_u32(bempty), pempty0 = smem_u32(pempty), accf0 = smem_u32(accf_bar);
+    int ps = 0, bs = 0, it = 0;
+    uint32_t pph = 0, bph = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acce_bar[buf], (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * TR * ACC_STRIDE);
+      const int oy0m = ((t / TX) % TY) * 16 * TR;
+      const uint32_t lower_ok = (TR > 1 && oy0m + 16 < H) ? 1u : 0u;   // the lower tile of the last super-tile row may lie outside the image
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(&pfull[ps], pph);
+        tc_fence_after();
+        const uint32_t a_lo0 = (((patch0 + (uint32_t)(ps * PATCH_BYTES)) >> 4) & 0x3FFFu) | DESC_LO_LBO1;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const bool nosync = (a.dbg_skip & 8) != 0;
+          if (!nosync) {
+            mbar_wait(&bfull[bs], bph);
+            tc_fence_after();
+          }
+          // tap (ky, kx): the same patch, start address moved by ky rows (2048 B) and kx pixels (128 B).  The swizzle follows
+          // the ABSOLUTE shared-memory address bits (measured: tests/test_conv.py patch cases), so the base-offset field stays 0.
+          const uint32_t a_lo = a_lo0 + (uint32_t)(((tap / 3) * 2048 + (tap % 3) * 128) >> 4);
+          const uint32_t b_lo = (((b0addr + (uint32_t)(bs * B_STAGE)) >> 4) & 0x3FFFu) | DESC_LO_LBO1;
+          const uint32_t first = (cb | tap) ? 1u : 0u;
+          umma_tf32_k4(tacc + (uint32_t)(mr * ACC_STRIDE), a_lo + (uint32_t)((mr * 16 * 2048) >> 4), b_lo, a_hi, b_hi, idesc, first,
+                       mr == 0 ? 1u : lower_ok);
+          if (!nosync) umma_commit_elect(bempty0 + (uint32_t)bs * 8u);
+          if (tap == 8) {
+            umma_commit_elect(pempty0 + (uint32_t)ps * 8u);
+            if (cb == ncb - 1) umma_commit_elect(accf0 + (uint32_t)buf * 8u);
+          }
+          if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
+        }
+        if (++ps == PSTAGES) { ps = 0; pph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 0-3)
+    const uint32_t sbuf = smem_u32(epi) + (uint32_t)(warp * EPI_WARP_FLOATS) * 4u;
+    const uint32_t rowptr = sbuf + 32 * 36 * 4;
+    const int c4 = (lane & 7) * 4, r0 = lane >> 3;
+    // fused BatchNorm statistics: when the layer has ONE N tile every tile of this CTA covers the same channels, so the column
+    // sums stay in registers across tiles and are folded once per CTA (a flush per tile put thousands of same-address double
+    // atomics on 2*N accumulators and tripled the kernel time)
+    constexpr int RS_PASSES = NT <= 128 ? (NT + 31) / 32 : 1;
+    const bool run_ok = a.stats != nullptr && ntiles == 1 && NT <= 128;
+    float run_stats[RS_PASSES][8];
+#pragma unroll
+    for (int pz = 0; pz < RS_PASSES; ++pz)
+#pragma unroll
+      for (int qz = 0; qz < 8; ++qz) run_stats[pz][qz] = 0.f;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      JPB_PTILE(t)
+      const int buf = it & 1;
+      const int row = warp * 32 + lane;
+      int nvalid = a.N - n0;
+      if (nvalid > NT) nvalid = NT;
+      mbar_wait(&accf_bar[buf], ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int r = 0; r < TR; ++r) {
+      if (r > 0 && oy0 + 16 * r >= H) break;
+      if (a.dbg_skip & 4) break;                                   // timing experiment: no epilogue
+      const int oy = oy0 + 16 * r + (row >> 3), ox = ox0 + (row & 7);
+      const bool rowok = oy < H;
+      const long long pix = ((long long)b_ * H + oy) * W + ox;
+      __syncwarp();
+      // pixel index (+1, 0 = row outside the image) of every tile row: output and residual share it
+      sts64(rowptr + (uint32_t)lane * 8u, rowok ? (unsigned long long)pix + 1ull : 0ull);
+      __syncwarp();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((buf * TR + r) * ACC_STRIDE);
+      for (int j = 0; j < NT && j < nvalid; j += 32) {
+        const int col = j + c4;
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias && col < nvalid) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)j, v, acc_scale);
+        for (int q = 0; q < 32; q += 4)
+          sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
+        __syncwarp();
+        float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < nvalid) {
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 4 * i;
+            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
+            if (!rp) continue;
+            const size_t off = (size_t)(rp - 1ull) * a.N + n0 + col;
+            float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
+            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+            if (a.residual) {
+              const float4 rq = *reinterpret_cast<const float4*>(a.residual + off);
+              o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+            }
+            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+            *reinterpret_cast<float4*>(a.out + off) = o;
+            st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
+            st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
+          }
+        }
+        if (a.stats) {
+          if (run_ok) {
+#pragma unroll
+            for (int pz = 0; pz < RS_PASSES; ++pz)
+              if (pz == j / 32) {
+                run_stats[pz][0] += st1.x; run_stats[pz][1] += st1.y; run_stats[pz][2] += st1.z; run_stats[pz][3] += st1.w;
+                run_stats[pz][4] += st2.x; run_stats[pz][5] += st2.y; run_stats[pz][6] += st2.z; run_stats[pz][7] += st2.w;
+              }
+          } else {
+            bn_stats_flush(a.stats, a.N, n0 + col, col < nvalid, lane, st1, st2);
+          }
+        }
+        __syncwarp();
+      }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acce_bar[buf]);
+    }
+    if (run_ok) {
+      // warp partials -> this warp's (idle) staging tile as [2][NT] -> fold the four warps -> 2*N double-precision adds per CTA
+#pragma unroll
+      for (int pz = 0; pz < RS_PASSES; ++pz) {
+        const float4 a1 = make_float4(run_stats[pz][0], run_stats[pz][1], run_stats[pz][2], run_stats[pz][3]);
+        const float4 a2 = make_float4(run_stats[pz][4], run_stats[pz][5], run_stats[pz][6], run_stats[pz][7]);
+        bn_stats_to_smem(sbuf + (uint32_t)(pz * 32) * 4u, NT, lane, a1, a2);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int tt = tid; tt < 2 * NT; tt += 128) {
+        const int cc = tt % NT, which = tt / NT;
+        if (cc < a.N) {
+          float v = 0.f;
+          for (int ww = 0; ww < 4; ++ww)
+            v += __int_as_float(lds32(smem_u32(epi) + (uint32_t)(ww * EPI_WARP_FLOATS + which * NT + cc) * 4u));
+          atomicAdd(a.stats + (size_t)which * a.N + cc, (double)v);
+        }
+      }
+    }
+  }
+#undef JPB_PTILE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1141,11 +1476,90 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
   return jpb_status();
 }
 
+
+template <int NT, int TR, int PSTAGES, int BSTAGES>
+int launch_patch(const JpbConvArgs* a, const CUtensorMap& xmap, const CUtensorMap& wmap, cudaStream_t st) {
+  constexpr int smem = PSTAGES * (16 * TR + 2) * PATCH_PX * 128 + BSTAGES * NT * BK * 4 + 4 * (32 * 36 + 64) * 4 + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "patch kernel shared memory");
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc_patch_kernel<NT, TR, PSTAGES, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = true;
+  }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const long long total = (long long)((a->N + NT - 1) / NT) * a->B * ((a->Ho + 16 * TR - 1) / (16 * TR)) * (a->Wo / 8);
+  const int waves = (int)((total + sms - 1) / sms);
+  const int grid = (int)((total + waves - 1) / waves);
+  conv_tc_patch_kernel<NT, TR, PSTAGES, BSTAGES><<<grid, 192 + 32 * (TR - 1), smem, st>>>(xmap, wmap, *a);
+  return jpb_status();
+}
+
+// 3x3 / stride 1 / zero pad 1 / one dense source with C % 32 == 0 / W % 8 == 0: the TMA-patch kernel
+int conv2d_patch(const JpbConvArgs* a, cudaStream_t st) {
+  if (a->nsrc != 1 || a->src_up[0] || a->stride != 1 || a->pad != 1 || a->reflect || a->ntaps != 9 || a->kw != 3 || a->in_div || a->scatter ||
+      a->ksplit > 1 || (a->src_C[0] & 31) || (a->Wo & 7) || a->Ho != a->src_H[0] || a->Wo != a->src_W[0] || (a->N & 15) || a->w_cols != 9 * a->src_C[0])
+    return JPB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(a->src[0]) & 15) || (reinterpret_cast<uintptr_t>(a->weight) & 15) || (a->w_row & 3)) return JPB_ERR_ARG;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return JPB_ERR_UNSUPPORTED;
+  int nt = 16;
+  while (nt < a->N && nt < 256) nt <<= 1;
+  if (a->nt) nt = a->nt;
+  const int C = a->src_C[0], H = a->src_H[0], W = a->src_W[0];
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  // two tiles per CTA (shared weight tiles) when that still leaves at least ~2 super-tiles per SM; a.patch == 2 / 3 force 1 / 2
+  const long long tiles2 = (long long)((a->N + nt - 1) / nt) * a->B * ((H + 31) / 32) * (W / 8);
+  // measured (tools/bench_conv.py, JPB_CONV_PATCH_TR): two tiles per CTA halve the weight stream but do not change the time — the
+  // kernel sits on the cta_group::1 kind::tf32 issue ceiling (~355 TFLOP/s with every load and the epilogue removed), so one tile
+  // per CTA (more CTAs, better balance) stays the default; a.patch == 3 forces two
+  (void)tiles2;
+  int tr = 1;
+  if (a->patch == 3 && nt <= 128) tr = 2;
+  CUtensorMap xmap, wmap;
+  {
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a->B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)PATCH_PX, (cuuint32_t)(16 * tr + 2), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->src[0]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return JPB_ERR_ARG;
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)a->w_cols, (cuuint64_t)a->N};
+    const cuuint64_t gstr[1] = {(cuuint64_t)a->w_row * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)nt};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->weight), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return JPB_ERR_ARG;
+  }
+  // patch buffers x weight stages: a tap of a narrow tile is a ~110 ns MMA burst, so the weight ring must cover the TMA latency
+  if (tr == 2) {
+    switch (nt) {
+      case 16: return launch_patch<16, 2, 2, 8>(a, xmap, wmap, st);
+      case 32: return launch_patch<32, 2, 2, 8>(a, xmap, wmap, st);
+      case 64: return launch_patch<64, 2, 2, 8>(a, xmap, wmap, st);
+      default: return launch_patch<128, 2, 2, 4>(a, xmap, wmap, st);
+    }
+  }
+  switch (nt) {
+    case 16: return launch_patch<16, 1, 3, 8>(a, xmap, wmap, st);
+    case 32: return launch_patch<32, 1, 3, 8>(a, xmap, wmap, st);
+    case 64: return launch_patch<64, 1, 3, 8>(a, xmap, wmap, st);
+    case 128: return launch_patch<128, 1, 2, 6>(a, xmap, wmap, st);
+    default: return launch_patch<256, 1, 2, 4>(a, xmap, wmap, st);
+  }
+}
+
 }  // namespace
 
 extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   if (!a || !a->weight || !a->table || (!a->out && !a->scatter) || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nkb < 1) return JPB_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(a->weight) & 15) || (a->w_row & 3)) return JPB_ERR_ARG;   // TMA: 16-byte aligned base and row pitch
+  if (a->patch) return conv2d_patch(a, (cudaStream_t)stream);
   EncodeTiledFn enc = get_encode();
   if (!enc) return JPB_ERR_UNSUPPORTED;
   int nt = 16;

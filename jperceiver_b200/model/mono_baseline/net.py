@@ -142,51 +142,90 @@ class Baseline(nn.Module):
             return outputs, loss_dict
         return outputs
 
+    N_SIDE = 5   # pose | layout trunk + road head | road transform decoder | car head | car transform decoder
+
     def side_streams(self, device=None):
-        """The two side streams of the branch-concurrent forward (created on first use).  Autograd runs every backward node on
-        the stream of its forward, so the pose and layout trunks are concurrent with the depth trunk in both directions; a
-        caller that consumes parameter gradients (``TrainEngine``) must wait for these streams after ``backward()``."""
+        """The side streams of the branch-concurrent forward (created on first use).  Autograd runs every backward node on
+        the stream of its forward, so the trunks / heads are concurrent in both directions; a caller that consumes parameter
+        gradients (``TrainEngine``) must wait for these streams after ``backward()``."""
         if self._side is None and device is not None:
-            self._side = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            self._side = tuple(torch.cuda.Stream(device) for _ in range(self.N_SIDE))
         return self._side or ()
 
+    def _head_on_streams(self, feat, l4, sfx, car, s_head, s_aux):
+        """``_head`` with the transform decoder (needs only the CVP output) on ``s_aux``, concurrent with CVT -> decoder on
+        ``s_head``.  The caller has made ``s_head`` wait for ``feat`` / ``l4``."""
+        cvp = getattr(self, "CycledViewProjection" + sfx)
+        cvt = getattr(self, "CrossViewTransformer" + sfx)
+        with torch.cuda.stream(s_head):
+            tf, rtf = cvp(feat)
+            tf_ready = torch.cuda.Event()
+            tf_ready.record(s_head)
+        with torch.cuda.stream(s_aux):
+            s_aux.wait_event(tf_ready)
+            ttv = getattr(self, "LayoutTransformDecoder" + sfx)(tf)
+        with torch.cuda.stream(s_head):
+            fused, S, attn = cvt(feat, tf, rtf, l4)
+            tv = getattr(self, "LayoutDecoder" + sfx)(fused)
+        out = {"topview" + sfx: tv, "transform_topview" + sfx: ttv}
+        out["features" + sfx] = out["features_" + car] = fused
+        out["transform_feature_" + car] = tf
+        out["retransform_features" + sfx] = out["retransform_features_" + car] = rtf
+        out["cv_attn_" + car] = S
+        out["cm_attn_" + car] = attn
+        return out
+
     def _forward_branch_streams(self, inputs):
-        """Same operators, three streams: the depth trunk (encoder -> decoder) on the caller's stream, the pose trunk and the
-        layout trunk on two side streams — the three ResNet-18 stacks are independent until the losses (the layout heads need
-        only the depth encoder's last feature map), and their deep, small-extent layers are latency-sized kernels that cannot
-        fill 148 SMs on their own (DESIGN.md §4 "branch streams").  Fork: the side streams wait for the caller's stream;
-        join: the caller's stream waits for both before ``compute_losses``."""
+        """Same operators, several streams: the depth trunk (encoder -> decoder) on the caller's stream, the pose trunk, the
+        layout trunk and the four BEV decoders on side streams — the three ResNet-18 stacks are independent until the losses
+        (the layout heads need only the depth encoder's last feature map), and their deep, small-extent layers are
+        latency-sized kernels that cannot fill 148 SMs on their own (DESIGN.md §4 "branch streams").  Fork: the side streams
+        wait for the caller's stream; join: the caller's stream waits for all of them before ``compute_losses``."""
         o = self.opt
         x = inputs[("color_aug", 0, 0)]
         main = torch.cuda.current_stream(x.device)
-        s_pose, s_layout = self.side_streams(x.device)
+        s_pose, s_road, s_road2, s_car, s_car2 = self.side_streams(x.device)
         s_pose.wait_stream(main)
-        s_layout.wait_stream(main)
+        s_road.wait_stream(main)
         outputs = {}
         with torch.cuda.stream(s_pose):
             pose_out = self.predict_poses(inputs)
         layout = o["type"] != "static_eigen"
         occ = o.occ_map_size
         if layout:
-            with torch.cuda.stream(s_layout):
+            with torch.cuda.stream(s_road):
                 feat = self.LayoutEncoder(x, (4 * occ, 4 * occ))
         depth_feature = self.DepthEncoder(x)
         if layout:
             l4_ready = torch.cuda.Event()
             l4_ready.record(main)
-            with torch.cuda.stream(s_layout):
-                s_layout.wait_event(l4_ready)
+            with torch.cuda.stream(s_road):
+                s_road.wait_event(l4_ready)
                 l4 = ops.resize_bilinear(depth_feature[-1], (occ // 8, occ // 8))
-                lay = {"origin_features": feat}
-                lay.update(self._head(feat, l4, "", "road"))
-                lay.update(self._head(feat, l4, "B", "car"))
+                heads_ready = torch.cuda.Event()
+                heads_ready.record(s_road)
+            s_car.wait_event(heads_ready)
+            lay = {"origin_features": feat}
+            # both heads always run, as in the reference (net.py:73-74 / 644-689): the head without a loss term still emits outputs
+            lay.update(self._head_on_streams(feat, l4, "", "road", s_road, s_road2))
+            lay.update(self._head_on_streams(feat, l4, "B", "car", s_car, s_car2))
+            # each head pair's losses on its own stream: their backward then starts there, concurrent with the photometric chain
+            bev_done = {}
+            with torch.cuda.stream(s_road):
+                s_road.wait_stream(s_road2)
+                bev_done.update(self.bev_losses(inputs, lay, "road"))
+            with torch.cuda.stream(s_car):
+                s_car.wait_stream(s_car2)
+                bev_done.update(self.bev_losses(inputs, lay, "car"))
+        else:
+            bev_done = {}
         outputs.update(self.DepthDecoder(depth_feature))
-        main.wait_stream(s_pose)
-        main.wait_stream(s_layout)
+        for st in (s_pose, s_road, s_road2, s_car, s_car2):
+            main.wait_stream(st)
         if layout:
             outputs.update(lay)
         outputs.update(pose_out)
-        loss_dict = self.compute_losses(inputs, outputs)
+        loss_dict = self.compute_losses(inputs, outputs, bev_done)
         self._step += 1
         return outputs, loss_dict
 
@@ -261,29 +300,43 @@ class Baseline(nn.Module):
                               (height, width), split=o.split, mode="static", quad=self._quad_mask(inputs, height, width),
                               align_corners=self.warp_align_corners)
 
-    def compute_losses(self, inputs, outputs):
+    def bev_losses(self, inputs, outputs, which):
+        """The four loss_dict entries of one BEV head pair (``which``: "road" -> topview_loss ..., "car" -> topview_lossB ...;
+        net.py:107-138), or {} when ``opt.type`` does not train that head."""
         o = self.opt
         typ = o["type"]
-        L = {}
         lw, l2w = o.loss_weight, o.loss2_weight
-        lwS, l2wS = o.get("loss_weightS", lw), o.get("loss2_weightS", l2w)
         if o.get("loss2_type", "boundary") != "boundary" and typ != "static_eigen":
             raise NotImplementedError("loss2_type %r: the reference only defines 'boundary' (net.py:574-575)" % (o.get("loss2_type"),))
         bev = dict(loss_type=o.get("loss_type", "iou"), loss_sum=o.get("loss_sum", 3))
-        if typ in ROAD_TYPES:
+        L = {}
+        if which == "road" and typ in ROAD_TYPES:
+            lwS, l2wS = o.get("loss_weightS", lw), o.get("loss2_weightS", l2w)
             y = inputs[("bothS", 0, 0)]
             sdf = JF.signed_distance(y.reshape(y.shape[0], y.shape[-2], y.shape[-1]))
             L["topview_loss"] = JF.bev_head_loss(outputs["topview"], y, sdf, o.static_weight, lwS, l2wS, **bev)
             L["transform_topview_loss"] = JF.bev_head_loss(outputs["transform_topview"], y, sdf, o.static_weight, lwS, l2wS, **bev)
             L["transform_loss"] = JF.l1_mean(outputs["features"], outputs["retransform_features"])
             L["layout_loss"] = L["topview_loss"] + 0.001 * L["transform_loss"] + L["transform_topview_loss"]
-        if typ in CAR_TYPES:
+        if which == "car" and typ in CAR_TYPES:
             y = inputs[("bothD", 0, 0)]
             sdf = JF.signed_distance(y.reshape(y.shape[0], y.shape[-2], y.shape[-1]))
             L["topview_lossB"] = JF.bev_head_loss(outputs["topviewB"], y, sdf, o.dynamic_weight, lw, l2w, **bev)
             L["transform_topview_lossB"] = JF.bev_head_loss(outputs["transform_topviewB"], y, sdf, o.dynamic_weight, lw, l2w, **bev)
             L["transform_lossB"] = JF.l1_mean(outputs["featuresB"], outputs["retransform_featuresB"])
             L["layout_lossB"] = L["topview_lossB"] + 0.001 * L["transform_lossB"] + L["transform_topview_lossB"]
+        return L
+
+    def compute_losses(self, inputs, outputs, bev_done=None):
+        """``bev_done``: BEV head losses already computed (on their heads' streams) by the branch-concurrent forward."""
+        o = self.opt
+        typ = o["type"]
+        L = {}
+        if bev_done is not None:
+            L.update(bev_done)
+        else:
+            L.update(self.bev_losses(inputs, outputs, "road"))
+            L.update(self.bev_losses(inputs, outputs, "car"))
         label = None
         if typ in LABEL_TYPES:
             label = self.get_scale_label(inputs) if self.scale_label_override is None else self.scale_label_override

@@ -205,3 +205,68 @@ def test_bn_statistics_fused_into_conv_epilogue(C, Cout, H, W, stride, bias):
     t = torch.randn(2, Cout, 8, 8, device=dev).contiguous(memory_format=torch.channels_last)
     ref = torch.nn.functional.batch_norm(t, None, None, bn2.weight, bn2.bias, True)
     assert (ops.batchnorm(t, bn2, True) - ref).abs().max().item() < 1e-5
+
+
+PATCH_CASES = [
+    # C, N, H, W, act, bias, residual   (3x3 / stride 1 / zero pad 1 / one dense source: the TMA-patch kernel)
+    (64, 64, 40, 64, "none", 0, 0),        # partial tile rows (40 = 2.5 x 16)
+    (64, 64, 32, 32, "relu", 1, 1),
+    (128, 128, 20, 64, "none", 0, 0),
+    (256, 256, 20, 32, "leaky", 1, 0),
+    (512, 512, 10, 16, "none", 0, 0),      # two N tiles, one tile row
+    (32, 16, 64, 64, "none", 1, 0),
+    (256, 64, 16, 8, "none", 0, 0),        # a single tile column
+]
+
+
+@pytest.mark.parametrize("tile_rows", [1, 2], ids=["one-tile", "two-tiles"])
+@pytest.mark.parametrize("desc_mode", [0, 2], ids=["no-base-offset", "base-offset"])
+@pytest.mark.parametrize("case", PATCH_CASES, ids=["%dx%d@%dx%d" % c[:4] for c in PATCH_CASES])
+def test_conv_patch_kernel_forward_and_dgrad(case, desc_mode, tile_rows):
+    """conv_tc_patch_kernel (A operand from 18x16 TMA patches, all nine taps on one patch through shifted UMMA descriptors)
+    against the fp32 library convolution with TF32-representable operands: forward with the fused epilogue, and the data
+    gradient (the same kernel on dz with flipped / transposed weights)."""
+    import os
+    want = int(os.environ.get("JPB_CONV_PATCH_DESC", "0"))
+    if desc_mode != want and not os.environ.get("JPB_TEST_BOTH_DESC"):
+        pytest.skip("descriptor variant %d (base offset set) is the measured-wrong experiment switch (JPB_TEST_BOTH_DESC=1 runs it)" % desc_mode)
+    C, N, H, W, act, has_bias, has_res = case
+    _lib._handle, _lib._emulated = None, False
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(C + N + H)
+    B = 2
+    x = tf32(torch.randn(B, C, H, W, generator=g)).to(dev).contiguous(memory_format=CL)
+    weight = tf32(torch.randn(N, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(dev).contiguous(memory_format=CL)
+    bias = torch.randn(N, generator=g).to(dev) if has_bias else None
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr, wr = x.clone().requires_grad_(True), weight.clone().requires_grad_(True)
+        z = torch_conv([xr], [False], wr, bias, 1, 1, False, "none", None)
+        res = torch.randn(z.shape, generator=g).to(dev).contiguous(memory_format=CL) if has_res else None
+        ref = torch_conv([xr], [False], wr, bias, 1, 1, False, act, res)
+        gy = tf32(torch.randn(ref.shape, generator=g)).to(dev).contiguous(memory_format=CL)
+        if act in ("relu", "leaky"):
+            zz = (z + res).detach() if has_res else z.detach()
+            gy = gy * (zz.abs() > 1e-4 * zz.abs().max()).to(gy.dtype)
+        ref.backward(gy)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    saved = JC.PATCH, JC.PATCH_MIN_TILES, JC.PATCH_DESC_MODE, JC.KSPLIT_SLOTS, JC.PATCH_TILE_ROWS
+    JC.PATCH, JC.PATCH_MIN_TILES, JC.PATCH_DESC_MODE, JC.KSPLIT_SLOTS, JC.PATCH_TILE_ROWS = 1, 1, desc_mode, 0, tile_rows
+    try:
+        xm, wm = x.clone().requires_grad_(True), weight.clone().requires_grad_(True)
+        with JC.trunc_comp(1.0):
+            assert JC._patch_ok(C, N, H, W, B, 3, 3, 1, 1, False, 1, False, 1)
+            got = JC.conv2d_tc([xm], [False], wm, bias, 1, 1, False, act, res)
+            got.backward(gy)
+        torch.cuda.synchronize()
+    finally:
+        JC.PATCH, JC.PATCH_MIN_TILES, JC.PATCH_DESC_MODE, JC.KSPLIT_SLOTS, JC.PATCH_TILE_ROWS = saved
+    scale = max(z.abs().max().item(), 1e-6)
+    err = (got - ref).abs().max().item()
+    assert err <= 5e-5 * scale, ("forward", case, err, scale)
+    errx = (xm.grad - xr.grad).abs().max().item()
+    assert errx <= 3e-3 * max(xr.grad.abs().max().item(), 1e-6), ("dgrad", case, errx)
+    errw = (wm.grad - wr.grad).abs().max().item()
+    assert errw <= 3e-3 * max(wr.grad.abs().max().item(), 1e-6), ("wgrad", case, errw)
