@@ -112,6 +112,29 @@ class FlatParameters:
             return sl.view(o, h, w, i).permute(0, 3, 1, 2)
         return sl.view(p.shape)
 
+    def permute(self, order, extras=()):
+        """Re-lay the flat buffers so that parameters appear in ``order`` (indices into ``self.params``); ``extras`` are other
+        flat tensors of the same layout (optimizer moments) to permute alike — the new tensors are returned in the same order.
+        Per-parameter views, ``views`` offsets and values are preserved; every cached pointer into the old buffers is stale."""
+        assert sorted(order) == list(range(len(self.params)))
+        new_off, off = [0] * len(self.params), 0
+        for i in order:
+            new_off[i] = off
+            off += self._padded(self.params[i].numel())
+        olds = [self.param, self.grad] + list(extras)
+        news = [torch.zeros_like(t) for t in olds]
+        for i, p in enumerate(self.params):
+            o, n = self.views[i]
+            for a, b in zip(olds, news):
+                b[new_off[i]:new_off[i] + n].copy_(a[o:o + n])
+        for i, p in enumerate(self.params):
+            pv, gv = self._view(news[0], new_off[i], p), self._view(news[1], new_off[i], p)
+            p.data = pv
+            p.grad = gv
+            self.views[i] = (new_off[i], p.numel())
+        self.param, self.grad = news[0], news[1]
+        return news[2:]
+
     def zero_grad(self):
         self.grad.zero_()
         for p, (off, n) in zip(self.params, self.views):   # autograd may have been told to drop .grad
@@ -173,6 +196,126 @@ def build_optimizer(model, optimizer_cfg, grad_clip=None):
                      weight_decay=cfg.get("weight_decay", 0.0), max_norm=max_norm)
 
 
+class GradExchange:
+    """The path's only collective, overlapped with backward: the flat gradient buffer is all-reduced in buckets, each as soon as
+    every gradient in it has been written (the reference gets the same overlap from DDP's buckets, trainer.py:167).
+
+    Step 1 of a multi-rank engine TRACES the order in which backward finishes the parameters' gradients (hook calls from the
+    backward kernels' host code and from autograd's accumulate nodes), exchanges the gradient in one piece, then re-lays the flat
+    buffers in that completion order and cuts them into buckets.  From step 2 on, a bucket's all-reduce is issued (async, on the
+    process group's stream, after the streams that wrote into it) a few hook events after its last gradient was produced; the
+    end of backward issues the rest and makes the caller's stream wait for all of them.  Every rank issues the same buckets in the
+    same order.  Works on NCCL (inside or outside a CUDA graph capture) and on gloo (CPU tests)."""
+
+    LAG = 6   # hook events between "the last gradient of a bucket is about to be written" and the bucket's launch: the writing
+              # launch follows its hook call inside the same autograd function (at most 4 parameters per function), so six events
+              # later it has certainly been issued
+
+    def __init__(self, engine, bucket_bytes=24 << 20, tail_bytes=4 << 20):
+        self.engine = engine
+        self.bucket_bytes, self.tail_bytes = bucket_bytes, tail_bytes
+        self.mode = "trace"
+        self.counter = 0
+        self.last = {}          # id(param) -> last event index (trace)
+        self.buckets = []       # (lo, hi, ready_at)
+        self.bucket_of = {}     # id(param) -> bucket index
+        self.step_streams = []  # per bucket: streams that wrote into it during the current step
+        self.main = None
+        self.next = 0
+        self.works = []
+        self.index = {id(p): i for i, p in enumerate(engine.flat.params)}
+        for p in engine.flat.params:   # gradients that arrive through autograd's accumulate nodes (not written by our kernels directly)
+            p.register_post_accumulate_grad_hook(self._accumulated)
+
+    def _accumulated(self, p):
+        from .. import functional as JF
+        if JF.GRAD_EVENT is not None:
+            JF.GRAD_EVENT(p)
+
+    # ---- hook target
+    def event(self, p):
+        self.counter += 1
+        if self.mode == "trace":
+            self.last[id(p)] = self.counter
+            return
+        if p.is_cuda:   # the streams that write into a bucket are those of THIS step (eager, or the streams of a graph capture)
+            self.step_streams[self.bucket_of[id(p)]].add(torch.cuda.current_stream(p.device))
+        while self.next < len(self.buckets) and self.buckets[self.next][2] + self.LAG <= self.counter:
+            self._launch(self.next)
+            self.next += 1
+
+    def begin(self):
+        self.counter, self.next, self.works = 0, 0, []
+        self.step_streams = [set() for _ in self.buckets]
+        g = self.engine.flat.grad
+        self.main = torch.cuda.current_stream(g.device) if g.is_cuda else None   # zero-fill of the gradient buffer runs here
+
+    def _launch(self, i):
+        lo, hi, _ = self.buckets[i]
+        grad = self.engine.flat.grad
+        if grad.is_cuda:
+            comm = self._comm_stream(grad.device)
+            streams = set(self.step_streams[i])
+            streams.add(self.main)
+            for st in streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                self.works.append(dist.all_reduce(grad[lo:hi], async_op=True))
+        else:
+            self.works.append(dist.all_reduce(grad[lo:hi], async_op=True))
+
+    def _comm_stream(self, device):
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device)
+        return self._comm
+
+    def finish(self):
+        """End of backward: issue the buckets that are still pending, then make the caller's stream wait for all of them."""
+        while self.next < len(self.buckets):
+            self._launch(self.next)
+            self.next += 1
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+    # ---- after the traced step
+    def build(self):
+        eng = self.engine
+        flat = eng.flat
+        last = [self.last.get(id(p), 0) for p in flat.params]            # 0 = never written (unused parameters): first bucket
+        order = sorted(range(len(flat.params)), key=lambda i: (last[i], i))
+        opt = eng.optimizer
+        opt.exp_avg, opt.exp_avg_sq = flat.permute(order, extras=(opt.exp_avg, opt.exp_avg_sq))
+        buckets, members, lo, ready = [], [], None, 0
+        total_bytes = flat.numel * 4
+        for i in order:
+            off, n = flat.views[i]
+            if lo is None:
+                lo = off
+            ready = max(ready, last[i])
+            members.append(i)
+            hi = off + flat._padded(n)
+            size = (hi - lo) * 4
+            limit = self.tail_bytes if (total_bytes - hi * 4) < 2 * self.tail_bytes else self.bucket_bytes   # small buckets at the tail
+            if size >= limit:
+                for m in members:
+                    self.bucket_of[id(flat.params[m])] = len(buckets)
+                buckets.append((lo, hi, ready))
+                lo, members = None, []
+        if lo is not None:
+            for m in members:
+                self.bucket_of[id(flat.params[m])] = len(buckets)
+            buckets.append((lo, flat.numel, ready))
+        self.buckets = buckets
+        self.mode = "run"
+        from .. import conv as JC
+        JC.WT.entries.clear()          # keyed by the weights' (old) addresses
+        JC.WT.table = None
+        eng._graph = None
+
+
 class TrainEngine:
     """One object per process (= per GPU): forward, backward, gradient exchange, optimizer step."""
 
@@ -187,10 +330,17 @@ class TrainEngine:
         self.optimizer = build_optimizer(model, optimizer_cfg or dict(type="Adam", lr=1e-4, weight_decay=0), grad_clip)
         self.flat = model._jpb_flat
         self.rank, self.world = get_dist_info()
+        self.exchange = None
         if self.world > 1:
             # what MMDistributedDataParallel does at construction: every rank starts from rank 0's parameters and buffers
             dist.broadcast(self.flat.param, src=0)
             self.sync_buffers()
+            import os as _os
+            # Overlapped, bucketed exchange: implemented and correct (tests/test_trainer.py on gloo, tests/test_gpu_training.py on
+            # NCCL), but MEASURED SLOWER than the one-piece exchange on 2 and 8 B200s (profiles/r2_scaling_n8.md: 27.29 vs 26.89 ms
+            # per step at N = 8) — the backward kernels already fill the GPU and NCCL's kernels take SMs from them — so it is opt-in.
+            if _os.environ.get("JPB_OVERLAP_ALLREDUCE", "0") not in ("", "0"):
+                self.exchange = GradExchange(self)
         self.last_names = None
         if hasattr(model, "step_counter"):
             model.step_counter = self.optimizer.step_count   # fresh automask noise per step, also under graph replay
@@ -227,8 +377,6 @@ class TrainEngine:
                 cur = torch.cuda.current_stream(self.flat.grad.device)
                 for st in self.model.side_streams():
                     cur.wait_stream(st)
-            if self.flat.grad.is_cuda:
-                JC.join_wgrad_streams(self.flat.grad.device)    # weight gradients launched on companion streams (conv.py)
         finally:
             JF.DIRECT_GRAD = False
             JC.WT.enabled = JC.WT.fresh = False
@@ -237,8 +385,23 @@ class TrainEngine:
     def step(self, data, need_log=True):
         """data: dict of device tensors (see ``change_input_variable``).  Returns the stacked loss tensor
         ``[entries..., total]`` on the device (names in ``self.last_names``)."""
-        names, vals, total = self.forward_backward(data)
-        self.exchange_gradients()
+        from .. import functional as JF
+        ex = self.exchange
+        if ex is None:
+            names, vals, total = self.forward_backward(data)
+            self.exchange_gradients()
+        else:
+            ex.begin()
+            JF.GRAD_EVENT = ex.event
+            try:
+                names, vals, total = self.forward_backward(data)
+            finally:
+                JF.GRAD_EVENT = None
+            if ex.mode == "trace":       # first step: one exchange of the whole buffer, then lay the buffers out in completion order
+                self.exchange_gradients()
+                ex.build()
+            else:
+                ex.finish()
         self.optimizer.step(self.world)
         self.last_names = names + ["loss"]
         if need_log:
@@ -269,6 +432,13 @@ class TrainEngine:
         JF.PROFILE_ON = prof
         torch.cuda.current_stream().wait_stream(side)
         return self
+
+    def release_graph(self):
+        """Drop the captured graph and its output buffers (before tearing down a process group whose collectives it holds, or
+        to return the graph's private memory pool)."""
+        self._graph = None
+        self._static_out = None
+        self._stage = None
 
     def replay(self, data=None):
         """Run the captured step; ``data`` (device or pinned-host tensors) is copied into the static inputs first."""

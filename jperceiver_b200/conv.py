@@ -586,53 +586,10 @@ class _ConvTC(torch.autograd.Function):
         gxs = [None] * len(xs)
         target = direct_grad_target(weight)
         want_dx = any(ctx.needs_input_grad[4:])
-        if ctx.needs_input_grad[1] and want_dx and target is not None and WGRAD_STREAMS and dzp.is_cuda and PRECISION == "tf32":
-            # engine step: the weight gradient goes straight into the flat gradient buffer and nobody reads it before the end of
-            # backward, so it runs on a companion stream, concurrent with the data gradient of this layer and with whatever
-            # follows on this stream.  Its operands are kept alive until the engine has joined the stream (join_wgrad_streams).
-            cur = torch.cuda.current_stream(dzp.device)
-            ws = _wgrad_stream(cur, dzp.device)
-            _WGRAD_USED.add(ws)
-            ws.wait_stream(cur)
-            with torch.cuda.stream(ws):
-                gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=target)
-            _WGRAD_KEEP.append((dzp, xs))
-            if gw is not None:          # packed-K layers return a tensor: autograd must see it on its own stream
-                cur.wait_stream(ws)
-            gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
-            return (None, gw, gb, gr) + tuple(gxs)
         if want_dx:
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
         gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=target) if ctx.needs_input_grad[1] else None
         return (None, gw, gb, gr) + tuple(gxs)
-
-
-# ---- weight gradients on companion streams (engine steps only) ----
-WGRAD_STREAMS = _os.environ.get("JPB_WGRAD_STREAMS", "1") not in ("", "0")
-_WGRAD_STREAM: dict = {}      # (device, home stream handle) -> companion stream
-_WGRAD_KEEP: list = []        # operands of weight-gradient launches in flight on companion streams
-_WGRAD_USED: set = set()      # companion streams with launches since the last join (only these may be waited on: a stream that
-                              # was last used OUTSIDE a graph capture must not be joined from inside one)
-
-
-def _wgrad_stream(cur, device):
-    key = (str(device), cur.cuda_stream)
-    st = _WGRAD_STREAM.get(key)
-    if st is None:
-        st = _WGRAD_STREAM[key] = torch.cuda.Stream(device)
-    return st
-
-
-def join_wgrad_streams(device):
-    """Make the current stream wait for every companion stream, then release the operands kept for them (TrainEngine calls
-    this right after ``backward()``, before the gradient exchange)."""
-    if not _WGRAD_KEEP:
-        return
-    cur = torch.cuda.current_stream(device)
-    for st in _WGRAD_USED:
-        cur.wait_stream(st)
-    _WGRAD_USED.clear()
-    _WGRAD_KEEP.clear()
 
 
 # ---- TMA-patch kernel (csrc/conv_tc.cu: conv_tc_patch_kernel) ----

@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(256) photometric_bwd_kernel(JpbPhotoArgs a, Jp
 
 }  // namespace
 
-static int g_fwd_variant = 2;   // 2: photometric_fwd_kernel (measured, default); 3: v3::photometric_fwd_kernel (packed fp32)
+static int g_fwd_variant = 3;   // 3: v3::photometric_fwd_kernel (packed fp32; measured 24 % faster on B200, profiles/r2_photometric_ab.jsonl); 2: photometric_fwd_kernel
 
 extern "C" int jpb_photometric_set_variant(int fwd_variant) {
   if (fwd_variant != 2 && fwd_variant != 3) return JPB_ERR_ARG;
@@ -900,7 +900,7 @@ extern "C" int jpb_photometric_set_variant(int fwd_variant) {
 extern "C" int jpb_photometric_fwd(const JpbPhotoArgs* a, void* stream) {
   if (!a || a->F < 1 || a->F > JPB_MAX_SRC || a->H < 3 || a->W < 3 || !a->loss_sum) return JPB_ERR_ARG;
   const int nid = a->automask ? a->F : 0;
-  if (a->F <= 2 && g_fwd_variant == 3 && (long long)a->H * a->W * 3 < (1ll << 31)) {   // packed variant (opt-in until measured)
+  if (a->F <= 2 && g_fwd_variant == 3 && (long long)a->H * a->W * 3 < (1ll << 31)) {   // packed variant (default)
     const size_t smem = (size_t)(3 + 6 + (nid ? 6 : 0)) * v3::AN * sizeof(float);
     dim3 grid((a->W + v3::TW - 1) / v3::TW, (a->H + v3::TH - 1) / v3::TH, a->B);
 #ifndef JPB_HOST_EMU

@@ -141,7 +141,9 @@ class _Photometric(torch.autograd.Function):
         return (gdisp, None, None, None, None) + (None,) * F + tuple(gT) + (None,) * n_extra
 
 
-KEEP_WARPED = os.environ.get("JPB_PHOTO_KEEP_WARPED", "0") not in ("", "0")   # opt-in until timed on a B200 (tools/gpu_r2a.sh)
+# The backward stages the warped frames its forward wrote instead of re-projecting the 2-pixel apron: measured -9 % on the backward
+# (profiles/r2_photometric_ab.jsonl); with the drop-in's default outputs (("color", f, s)) those frames exist anyway.
+KEEP_WARPED = os.environ.get("JPB_PHOTO_KEEP_WARPED", "1") not in ("", "0")
 
 
 def photometric_loss(disp, target, sources, Ts, K, invK, *, num_scales=4, automask=True, min_depth=0.1,
@@ -408,6 +410,9 @@ _BN_WS: dict = {}
 DIRECT_GRAD = False
 
 
+GRAD_EVENT = None   # set by TrainEngine (world > 1): called with every parameter whose gradient a backward launch is about to write
+
+
 def direct_grad_target(p):
     """``p.grad`` when the backward kernels may accumulate into it directly (engine step, dense fp32 gradient present)."""
     if not DIRECT_GRAD or p is None:
@@ -415,6 +420,8 @@ def direct_grad_target(p):
     g = p.grad
     if g is None or g.dtype != torch.float32 or g.shape != p.shape or g.stride() != p.stride():
         return None
+    if GRAD_EVENT is not None:
+        GRAD_EVENT(p)
     return g
 
 

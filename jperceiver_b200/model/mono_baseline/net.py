@@ -150,6 +150,8 @@ class Baseline(nn.Module):
         gradients (``TrainEngine``) must wait for these streams after ``backward()``."""
         if self._side is None and device is not None:
             self._side = tuple(torch.cuda.Stream(device) for _ in range(self.N_SIDE))
+        if device is None:
+            return getattr(self, "_side_used", ())      # the streams the last forward actually forked (the ones to join)
         return self._side or ()
 
     def _head_on_streams(self, feat, l4, sfx, car, s_head, s_aux):
@@ -185,12 +187,14 @@ class Baseline(nn.Module):
         x = inputs[("color_aug", 0, 0)]
         main = torch.cuda.current_stream(x.device)
         s_pose, s_road, s_road2, s_car, s_car2 = self.side_streams(x.device)
+        layout = o["type"] != "static_eigen"
+        used = (s_pose, s_road, s_road2, s_car, s_car2) if layout else (s_pose,)   # only forked streams may be joined (graph capture)
         s_pose.wait_stream(main)
-        s_road.wait_stream(main)
+        if layout:
+            s_road.wait_stream(main)
         outputs = {}
         with torch.cuda.stream(s_pose):
             pose_out = self.predict_poses(inputs)
-        layout = o["type"] != "static_eigen"
         occ = o.occ_map_size
         if layout:
             with torch.cuda.stream(s_road):
@@ -220,8 +224,9 @@ class Baseline(nn.Module):
         else:
             bev_done = {}
         outputs.update(self.DepthDecoder(depth_feature))
-        for st in (s_pose, s_road, s_road2, s_car, s_car2):
+        for st in used:
             main.wait_stream(st)
+        self._side_used = used
         if layout:
             outputs.update(lay)
         outputs.update(pose_out)

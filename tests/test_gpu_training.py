@@ -81,6 +81,7 @@ def _nccl_worker(rank, world, port, q):
                automask=True, disp_norm=True, smoothness_weight=1e-3, scale_weight=0.1, dynamic_weight=15.0, static_weight=5.0,
                occ_map_size=64, num_class=2, loss_type="iou", loss_weight=20, loss2_type="boundary", loss2_weight=20,
                type="static_eigen", loss_sum=3, split="odometry")
+    os.environ["JPB_OVERLAP_ALLREDUCE"] = "1"           # exercise the bucketed exchange (opt-in: measured slower than one piece)
     torch.manual_seed(1234 + 17 * rank)                 # DIFFERENT initial weights per rank: the engine must broadcast rank 0's
     model = MONO.module_dict["Baseline"](opt).to(dev).train()
     eng = TrainEngine(model, dict(type="Adam", lr=1e-4, weight_decay=0), dict(max_norm=35, norm_type=2))
@@ -105,7 +106,9 @@ def _nccl_worker(rank, world, port, q):
     den = expect.abs().max().item()
     ok_grad = (got - expect).abs().max().item() <= 1e-6 * max(den, 1e-12)
     eng.optimizer.step(world)
-    eng.step(data)                                      # one full step through the public entry (buckets, overlap and all)
+    for _ in range(3):                                  # full steps through the public entry: the first traces the completion order,
+        eng.step(data)                                  # the next ones all-reduce bucket by bucket during backward
+    assert eng.exchange is not None and eng.exchange.mode == "run" and len(eng.exchange.buckets) >= 4
     params = eng.flat.param.clone()
     allp = [torch.zeros_like(params) for _ in range(world)]
     dist.all_gather(allp, params)

@@ -188,3 +188,55 @@ def test_direct_gradient_accumulation_matches_plain_autograd_gpu():
     xc = torch.randn(2, 32, 4, 4, generator=g).to(dev).contiguous(memory_format=CL)
     Gc = torch.randn(2, 32, 4, 4, generator=g).to(dev)
     check(lambda: (ops.cvp_mlp(xc, fc0, fc2) * Gc).sum(), [fc0.weight, fc0.bias, fc2.weight, fc2.bias])
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import build_emulation as be
+    _lib.use_library(be(), emulated=True)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    engines = []
+    for overlap in ("1", "0"):
+        os.environ["JPB_OVERLAP_ALLREDUCE"] = overlap
+        torch.manual_seed(0)
+        m = Tiny()
+        eng = TrainEngine(m, dict(type="Adam", lr=1e-2, weight_decay=0), dict(max_norm=35, norm_type=2))
+        if eng.exchange is not None:
+            eng.exchange.bucket_bytes, eng.exchange.tail_bytes = 512, 128      # several buckets on a model this small
+        engines.append(eng)
+    for it in range(4):
+        x = torch.randn(4, 3, 8, 8, generator=torch.Generator().manual_seed(100 * it + rank))
+        for eng in engines:
+            eng.step({"x": x})
+    a, b = engines
+    ok_mode = a.exchange is not None and a.exchange.mode == "run" and len(a.exchange.buckets) >= 3 and b.exchange is None
+    # the same parameter values whichever way the gradient travelled (the layouts differ: compare per parameter)
+    ok_same = all(torch.equal(pa, pb) for pa, pb in zip(a.model.parameters(), b.model.parameters()))
+    flat = torch.cat([p.detach().reshape(-1) for p in a.model.parameters()])
+    allp = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(allp, flat)
+    ok_sync = all(torch.equal(allp[0], p) for p in allp)
+    covered = sorted((lo, hi) for lo, hi, _ in a.exchange.buckets)
+    ok_cover = covered[0][0] == 0 and covered[-1][1] == a.flat.numel and all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+    q.put((rank, bool(ok_mode), bool(ok_same), bool(ok_sync), bool(ok_cover)))
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucketed_allreduce_matches_single_exchange_gloo_world2():
+    """GradExchange: step 1 traces the gradient completion order and re-lays the flat buffers; steps 2.. all-reduce bucket by
+    bucket during backward.  Four steps on two gloo ranks must give bit-identical parameters to the one-piece exchange, identical
+    across ranks, and the buckets must tile the flat buffer exactly."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(all(r[1:]) for r in res), res

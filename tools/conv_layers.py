@@ -27,7 +27,7 @@ if args.tf32_peak <= 0:
     args.tf32_peak = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
     del a, b
 print("tf32 cuBLAS peak %.0f TFLOP/s, hbm %.0f GB/s" % (args.tf32_peak, pk["hbm_gbs"]))
-opt = bench.model_options(args.batch)
+opt = bench.model_options(bench.CONFIGS["C2"], args.batch)
 torch.manual_seed(1024)
 model = MONO.module_dict["Baseline"](opt).to(dev).train()
 engine = TrainEngine(model)

@@ -10,7 +10,7 @@ from jperceiver_b200.apis import TrainEngine, change_input_variable
 from jperceiver_b200.model import MONO
 
 dev = torch.device("cuda:0")
-opt = bench.model_options(4)
+opt = bench.model_options(bench.CONFIGS["C2"], 4)
 torch.manual_seed(1024)
 model = MONO.module_dict["Baseline"](opt).to(dev).train()
 engine = TrainEngine(model)
