@@ -111,25 +111,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
-//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): [0,14) start address >> 4 | [16,30) leading byte offset >> 4 |
+// [32,46) stride byte offset >> 4 | [46,48) version = 1 | [49,52) base offset (0: the swizzle follows absolute address bits) |
+// [61,64) layout (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).  Built as 32-bit halves by the issue helpers below.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -224,32 +208,28 @@ __device__ __forceinline__ void umma_tf32_k4(uint32_t tacc, uint32_t a_lo, uint3
       " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
       "}" ::"r"(tacc), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(enable) : "memory");
 }
-// two independent accumulators, instruction-interleaved (acc0 k0, acc1 k0, acc0 k1, ...): the same weight tile, two A tiles
-__device__ __forceinline__ void umma_tf32_k4x2(uint32_t tacc0, uint32_t tacc1, uint32_t a0_lo, uint32_t a1_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t acc_first, uint32_t enable1) {
+// same, with the descriptor advance per MMA as an operand (`step` in 16-byte units: 2 for K-major SW128 operands, 64 for the
+// MN-major operands of the weight-gradient kernel)
+__device__ __forceinline__ void umma_tf32_k4s(uint32_t tacc, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t acc_first, uint32_t step) {
   asm volatile(
       "{\n"
-      " .reg .pred pe, p1, pa, pt, pv;\n"
-      " .reg .b64 da, dc, db;\n"
-      " .reg .b32 al, cl, bl;\n"
+      " .reg .pred pe, pa, pt;\n"
+      " .reg .b64 da, db;\n"
+      " .reg .b32 al, bl;\n"
       " elect.sync _|pe, 0xffffffff;\n"
-      " setp.ne.b32 pv, %9, 0;\n"
-      " and.pred p1, pe, pv;\n"
-      " setp.ne.b32 pa, %8, 0;\n"
-      " setp.eq.b32 pt, %8, %8;\n"
-      " mov.b64 da, {%2, %5};\n mov.b64 dc, {%3, %5};\n mov.b64 db, {%4, %6};\n"
-      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pa;\n"
-      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pa;\n"
-      " add.u32 al, %2, 2;\n add.u32 cl, %3, 2;\n add.u32 bl, %4, 2;\n mov.b64 da, {al, %5};\n mov.b64 dc, {cl, %5};\n mov.b64 db, {bl, %6};\n"
-      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pt;\n"
-      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pt;\n"
-      " add.u32 al, %2, 4;\n add.u32 cl, %3, 4;\n add.u32 bl, %4, 4;\n mov.b64 da, {al, %5};\n mov.b64 dc, {cl, %5};\n mov.b64 db, {bl, %6};\n"
-      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pt;\n"
-      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pt;\n"
-      " add.u32 al, %2, 6;\n add.u32 cl, %3, 6;\n add.u32 bl, %4, 6;\n mov.b64 da, {al, %5};\n mov.b64 dc, {cl, %5};\n mov.b64 db, {bl, %6};\n"
-      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, pt;\n"
-      " @p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], dc, db, %7, pt;\n"
-      "}" ::"r"(tacc0), "r"(tacc1), "r"(a0_lo), "r"(a1_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(enable1) : "memory");
+      " setp.ne.b32 pa, %6, 0;\n"
+      " setp.eq.b32 pt, %6, %6;\n"
+      " mov.b64 da, {%1, %3};\n"
+      " mov.b64 db, {%2, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pa;\n"
+      " add.u32 al, %1, %7;\n add.u32 bl, %2, %7;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
+      " add.u32 al, al, %7;\n add.u32 bl, bl, %7;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
+      " add.u32 al, al, %7;\n add.u32 bl, bl, %7;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, pt;\n"
+      "}" ::"r"(tacc), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(step) : "memory");
 }
 // tcgen05.commit -> mbarrier arrive, issued by one elected lane of a converged warp
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_saddr) {
@@ -593,15 +573,13 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (kb == 0) JPB_STAMP(3);
-      if (lane == 0) {
-        const uint64_t ad = umma_desc_sw128(smem_u32(smem + s * STAGE));
-        const uint64_t bd = umma_desc_sw128(smem_u32(smem + s * STAGE + A_STAGE));
-        for (int k = 0; k < BK / 8; ++k)   // 8 TF32 (32 bytes) per instruction: advance the start address by 2 x 16 B
-          umma_tf32(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-        if (kb == nkb - 1) umma_commit(accum_bar);
+      {   // converged warp, one elected lane issues (see umma_tf32_k4): 8 TF32 (32 bytes) per instruction, start address + 2 x 16 B each
+        const uint32_t sa = smem_u32(smem + s * STAGE);
+        umma_tf32_k4(tmem_base, ((sa >> 4) & 0x3FFFu) | DESC_LO_LBO1, (((sa + A_STAGE) >> 4) & 0x3FFFu) | DESC_LO_LBO1, DESC_HI_SW128(1024),
+                     DESC_HI_SW128(1024), idesc, kb ? 1u : 0u, 1u);
+        umma_commit_elect(smem_u32(&empty_bar[s]));
+        if (kb == nkb - 1) umma_commit_elect(smem_u32(accum_bar));
       }
-      __syncwarp();
     }
     JPB_STAMP(4);
   }
@@ -820,15 +798,13 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
         const uint32_t ph = (uint32_t)(ring / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t ad = umma_desc_sw128(smem_u32(smem + s * STAGE));
-          const uint64_t bd = umma_desc_sw128(smem_u32(smem + s * STAGE + A_STAGE));
-          for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-          if (kb == nkb - 1) umma_commit(&accf_bar[buf]);
+        {
+          const uint32_t sa = smem_u32(smem + s * STAGE);
+          umma_tf32_k4(tacc, ((sa >> 4) & 0x3FFFu) | DESC_LO_LBO1, (((sa + A_STAGE) >> 4) & 0x3FFFu) | DESC_LO_LBO1, DESC_HI_SW128(1024),
+                       DESC_HI_SW128(1024), idesc, kb ? 1u : 0u, 1u);
+          umma_commit_elect(smem_u32(&empty_bar[s]));
+          if (kb == nkb - 1) umma_commit_elect(smem_u32(&accf_bar[buf]));
         }
-        __syncwarp();
       }
       ++it;
     }
@@ -1130,18 +1106,16 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
         for (int i = lane; i < (A_STAGE + B_STAGE) / 4; i += 32) a.dbg[i] = sa[i];
         __syncwarp();
       }
-      if (lane == 0) {
+      {
         // descriptor: leading byte offset = distance between 32-channel MN groups (4096 B), stride byte offset = distance
         // between 4-pixel K groups (512 B), layout type 1 = SWIZZLE_128B_BASE32B; one MMA (K = 8 pixels) spans two K groups
-        const uint64_t hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
-        const uint64_t ad = (uint64_t)((smem_u32(smem + s * STAGE) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | hi;
-        const uint64_t bd = (uint64_t)((smem_u32(smem + s * STAGE + A_STAGE) >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | hi;
-        for (int kk = 0; kk < 4; ++kk)
-          umma_tf32(tmem_base, ad + (uint64_t)(64 * kk), bd + (uint64_t)(64 * kk), idesc, (st | kk) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-        if (st == nsteps - 1) umma_commit(accum_bar);
+        constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);
+        constexpr uint32_t lbo = (4096u >> 4) << 16;
+        const uint32_t sa = smem_u32(smem + s * STAGE);
+        umma_tf32_k4s(tmem_base, ((sa >> 4) & 0x3FFFu) | lbo, (((sa + A_STAGE) >> 4) & 0x3FFFu) | lbo, hi, hi, idesc, st ? 1u : 0u, 64u);
+        umma_commit_elect(smem_u32(&empty_bar[s]));
+        if (st == nsteps - 1) umma_commit_elect(smem_u32(accum_bar));
       }
-      __syncwarp();
     }
   }
   }
