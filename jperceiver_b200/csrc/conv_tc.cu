@@ -254,6 +254,64 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 3) return 1.f / (1.f + __expf(-v));
   return v;
 }
+template <int ACT>
+__device__ __forceinline__ float act_c(float v) {
+  if (ACT == 1) return v > 0.f ? v : 0.f;
+  if (ACT == 2) return v > 0.f ? v : 0.01f * v;
+  if (ACT == 3) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+// ---- epilogue inner loop, shared by the forward kernels ----
+// Per epilogue warp: a padded 32 x 32 staging tile (36-float rows) and a row table of 32 x {output row pointer | atomic flag,
+// residual row pointer}.  One call handles one 32-column pass: 8 lanes cover the 128-byte segment of a row, 4 rows per
+// iteration.  The activation and the residual are TEMPLATE parameters: with a run-time `act` every element went through three
+// compare-and-branch pairs, and those branches (ncu: stall_branch_resolving on the ISETPs), not memory, made the epilogue as
+// long as the main loop (graph-timed: 128 -> 128 channels 51 us with, 28 us without the epilogue).
+constexpr int EPI_WARP_FLOATS = 32 * 36 + 128;          // staging tile + row table (32 x 16 bytes)
+template <int ACT, bool RES>
+__device__ __forceinline__ void epi_rows(uint32_t sbuf, uint32_t rowtab, int r0, int c4, int col, float4 bq, float4& st1, float4& st2) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 4 * i;
+    unsigned long long rp, rr;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(rp), "=l"(rr) : "r"(rowtab + (uint32_t)r * 16u));
+    if (!rp) continue;
+    float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + col;
+    float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
+    o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+    if (RES) {
+      const float4 rq = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>((uintptr_t)rr) + col);
+      o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+    }
+    o.x = act_c<ACT>(o.x); o.y = act_c<ACT>(o.y); o.z = act_c<ACT>(o.z); o.w = act_c<ACT>(o.w);
+    if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+    else *reinterpret_cast<float4*>(op) = o;
+    st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
+    st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
+  }
+}
+__device__ __forceinline__ void epi_rows_dispatch(int act, bool res, uint32_t sbuf, uint32_t rowtab, int r0, int c4, int col, float4 bq, float4& st1,
+                                                  float4& st2) {
+  if (res) {
+    switch (act) {
+      case 1: epi_rows<1, true>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+      case 2: epi_rows<2, true>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+      case 3: epi_rows<3, true>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+      default: epi_rows<0, true>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+    }
+  } else {
+    switch (act) {
+      case 1: epi_rows<1, false>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+      case 2: epi_rows<2, false>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+      case 3: epi_rows<3, false>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+      default: epi_rows<0, false>(sbuf, rowtab, r0, c4, col, bq, st1, st2); break;
+    }
+  }
+}
+__device__ __forceinline__ void sts_row(uint32_t rowtab, int lane, unsigned long long out_ptr_flag, unsigned long long res_ptr) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowtab + (uint32_t)lane * 16u), "l"(out_ptr_flag), "l"(res_ptr) : "memory");
+}
 
 // NT: N tile (UMMA N), multiple of 16 in [16,256].  STAGES: smem pipeline depth.
 template <int NT, int STAGES, int MINB>
@@ -466,10 +524,11 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       // Coalesced epilogue: 32 accumulator columns per pass go TMEM -> registers (lane = row) -> a padded per-warp tile in
       // the (now idle) pipeline memory -> registers (8 lanes = one 128-byte row segment), so every global access of the
       // bias / residual / output covers whole 128-byte lines instead of 32 rows x 16 bytes.
-      const uint32_t sbuf = smem_u32(smem) + (uint32_t)warp * (32 * 36 + 64) * 4u;
+      const uint32_t sbuf = smem_u32(smem) + (uint32_t)warp * EPI_WARP_FLOATS * 4u;
       const uint32_t rowptr = sbuf + 32 * 36 * 4;
-      const uint32_t sstats = smem_u32(smem) + 4u * (32 * 36 + 64) * 4u;   // [4 warps][2][NT] floats, behind the staging tiles
-      sts64(rowptr + (uint32_t)lane * 8u, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull);
+      const uint32_t sstats = smem_u32(smem) + 4u * EPI_WARP_FLOATS * 4u;   // [4 warps][2][NT] floats, behind the staging tiles
+      sts_row(rowptr, lane, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull,
+              (unsigned long long)(uintptr_t)(a.residual ? a.residual + (size_t)(m < M ? m : 0) * a.N + n0 : nullptr));
       __syncwarp();
       const int c4 = (lane & 7) * 4, r0 = lane >> 3;
       for (int j = 0; j < NT; j += 32) {
@@ -483,23 +542,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         if (col < nvalid_all) {
           float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.bias) bq = *reinterpret_cast<const float4*>(a.bias + n0 + col);
-          for (int i = 0; i < 8; ++i) {
-            const int r = r0 + 4 * i;
-            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
-            if (!rp) continue;
-            float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + col;
-            float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
-            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
-            if (a.residual) {
-              const float4 rq = *reinterpret_cast<const float4*>(a.residual + (size_t)(m0 + warp * 32 + r) * a.N + n0 + col);
-              o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
-            }
-            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-            if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-            else *reinterpret_cast<float4*>(op) = o;
-            st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
-            st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
-          }
+          epi_rows_dispatch(a.act, a.residual != nullptr, sbuf, rowptr, r0, c4, col, bq, st1, st2);
         }
         if (a.stats) {
           if (NT >= 32) bn_stats_to_smem(sstats + (uint32_t)(warp * 2 * NT + j) * 4u, NT, lane, st1, st2);
@@ -610,7 +653,6 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
   constexpr int STAGE = A_STAGE + B_STAGE;
   constexpr int ACC_STRIDE = NT < 32 ? 32 : NT;          // TMEM columns per accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
-  constexpr int EPI_WARP_FLOATS = 32 * 36 + 64;          // padded 32x32 tile + 32 row pointers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE);
   constexpr int EPI_STATS_FLOATS = NT <= 64 ? 4 * 2 * NT : 0;   // cross-warp fold of the fused BatchNorm statistics
@@ -849,7 +891,8 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
         }
       }
       if (nvalid > NT) nvalid = NT;
-      sts64(rowptr + (uint32_t)lane * 8u, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull);
+      sts_row(rowptr, lane, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull,
+              (unsigned long long)(uintptr_t)(a.residual ? a.residual + (size_t)(m < M ? m : 0) * a.N + n0 : nullptr));
       mbar_wait(&accf_bar[buf], ((uint32_t)(it >> 1)) & 1u);
       tc_fence_after();
       __syncwarp();
@@ -865,25 +908,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
         __syncwarp();
         float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = make_float4(0.f, 0.f, 0.f, 0.f);   // BatchNorm statistics of this pass
         if (vec_ok) {
-          if (col < nvalid) {
-            for (int i = 0; i < 8; ++i) {
-              const int r = r0 + 4 * i;
-              const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
-              if (!rp) continue;
-              float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + col;
-              float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
-              o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
-              if (a.residual) {
-                const float4 rq = *reinterpret_cast<const float4*>(a.residual + (size_t)(m0 + warp * 32 + r) * a.N + n0 + col);
-                o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
-              }
-              o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-              if (rp & 1ull) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(op), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-              else *reinterpret_cast<float4*>(op) = o;
-              st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
-              st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
-            }
-          }
+          if (col < nvalid) epi_rows_dispatch(a.act, a.residual != nullptr, sbuf, rowptr, r0, c4, col, bq, st1, st2);
           if (a.stats) {
             if (ntiles == 1 && NT <= 64) {       // every tile of this CTA has the same columns: keep running sums
               float* rs = run_stats[(NT <= 64) ? j / 32 : 0];
@@ -896,7 +921,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
         } else {
           // ragged channel counts (destination C % 4 != 0): scalar accesses, lane = column
           for (int r = 0; r < 32; ++r) {
-            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
+            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 16u);
             const int cc = j + lane;
             if (!rp || cc >= nvalid) continue;
             float* op = reinterpret_cast<float*>((uintptr_t)(rp & ~1ull)) + cc;
@@ -1161,7 +1186,6 @@ __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(c
   static_assert(TMEM_COLS <= 512, "TMEM columns");
   constexpr int PATCH_ROWS = 16 * TR + 2;
   constexpr int PATCH_BYTES = PATCH_ROWS * PATCH_PX * 128;
-  constexpr int EPI_WARP_FLOATS = 32 * 36 + 64;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* s_patch = smem;                                   // [PSTAGES][PATCH_BYTES]
   unsigned char* s_b = smem + PSTAGES * PATCH_BYTES;               // [BSTAGES][B_STAGE]
@@ -1312,8 +1336,9 @@ __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(c
       const bool rowok = oy < H;
       const long long pix = ((long long)b_ * H + oy) * W + ox;
       __syncwarp();
-      // pixel index (+1, 0 = row outside the image) of every tile row: output and residual share it
-      sts64(rowptr + (uint32_t)lane * 8u, rowok ? (unsigned long long)pix + 1ull : 0ull);
+      // output / residual row pointers of every tile row (0 = row outside the image)
+      sts_row(rowptr, lane, rowok ? (unsigned long long)(uintptr_t)(a.out + (size_t)pix * a.N + n0) : 0ull,
+              (unsigned long long)(uintptr_t)(a.residual ? a.residual + (size_t)(rowok ? pix : 0) * a.N + n0 : nullptr));
       __syncwarp();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((buf * TR + r) * ACC_STRIDE);
       for (int j = 0; j < NT && j < nvalid; j += 32) {
@@ -1326,24 +1351,7 @@ __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(c
           sts128(sbuf + (uint32_t)(lane * 36 + q) * 4u, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
         __syncwarp();
         float4 st1 = make_float4(0.f, 0.f, 0.f, 0.f), st2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col < nvalid) {
-          for (int i = 0; i < 8; ++i) {
-            const int r = r0 + 4 * i;
-            const unsigned long long rp = lds64(rowptr + (uint32_t)r * 8u);
-            if (!rp) continue;
-            const size_t off = (size_t)(rp - 1ull) * a.N + n0 + col;
-            float4 o = lds128(sbuf + (uint32_t)(r * 36 + c4) * 4u);
-            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
-            if (a.residual) {
-              const float4 rq = *reinterpret_cast<const float4*>(a.residual + off);
-              o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
-            }
-            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act); o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-            *reinterpret_cast<float4*>(a.out + off) = o;
-            st1.x += o.x; st1.y += o.y; st1.z += o.z; st1.w += o.w;
-            st2.x += o.x * o.x; st2.y += o.y * o.y; st2.z += o.z * o.z; st2.w += o.w * o.w;
-          }
-        }
+        if (col < nvalid) epi_rows_dispatch(a.act, a.residual != nullptr, sbuf, rowptr, r0, c4, col, bq, st1, st2);
         if (a.stats) {
           if (run_ok) {
 #pragma unroll
@@ -1409,7 +1417,7 @@ EncodeTiledFn get_encode() {
 
 template <int NT, int STAGES, int MINB>
 int launch_fwd2(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
-  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 4 * (32 * 36 + 64) * 4 + (NT <= 64 ? 4 * 2 * NT * 4 : 0) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 4 * EPI_WARP_FLOATS * 4 + (NT <= 64 ? 4 * 2 * NT * 4 : 0) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
   static int configured = 0;
   if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
   if (smem > configured) {
@@ -1453,7 +1461,7 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
 
 template <int NT, int TR, int PSTAGES, int BSTAGES>
 int launch_patch(const JpbConvArgs* a, const CUtensorMap& xmap, const CUtensorMap& wmap, cudaStream_t st) {
-  constexpr int smem = PSTAGES * (16 * TR + 2) * PATCH_PX * 128 + BSTAGES * NT * BK * 4 + 4 * (32 * 36 + 64) * 4 + 1024 + 256;
+  constexpr int smem = PSTAGES * (16 * TR + 2) * PATCH_PX * 128 + BSTAGES * NT * BK * 4 + 4 * EPI_WARP_FLOATS * 4 + 1024 + 256;
   static_assert(smem <= 227 * 1024, "patch kernel shared memory");
   static bool configured = false;
   if (!configured) {

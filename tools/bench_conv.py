@@ -34,13 +34,26 @@ LAYERS = [
 
 
 def bench(fn, iters=10):
+    """Device time per call: `iters` calls captured into ONE CUDA graph and replayed (host launch overhead — ctypes, tensor-map
+    encoding, allocation: ~50 us per call — would otherwise floor every layer below ~55 us)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters

@@ -11,4 +11,9 @@ try:
 except Exception as e:
     print("bench unreadable", e); print(open("gpurun_out/bench_l.err").read()[-1500:])
 PY
-timeout 200 python tools/bench_conv.py "iconv1" 10 2>&1 | cut -c1-330; timeout 200 python tools/bench_conv.py "merge1" 10 2>&1 | cut -c1-330; timeout 200 python tools/bench_conv.py "crp1" 10 2>&1 | cut -c1-330
+timeout 600 python tools/bench_conv.py "" 10 2>&1 | tee gpurun_out/conv_microbench_graph.jsonl | python -c "
+import sys,json
+for l in sys.stdin:
+    try: r=json.loads(l)
+    except Exception: print(l.strip()[:200]); continue
+    print('%-42s fwd %7.1f us %5.0f TF | dgrad %7.1f us %5.0f | wgrad %7.1f us %5.0f'%(r['layer'][:42], r['fwd_ms']*1e3, r['fwd_tflops'], r.get('dgrad_ms',0)*1e3, r.get('dgrad_tflops',0), r['wgrad_ms']*1e3, r['wgrad_tflops']))"
