@@ -198,6 +198,10 @@ typedef struct JpbConvArgs {
   int patch;                            /* != 0 (1 = one or two tiles per CTA chosen by the library, 2 / 3 = forced to one / two): 3x3 / stride 1 / zero pad 1 over ONE dense source with C % 32 == 0 and W % 8 == 0: the A operand is
                                            read as 18 x 16 pixel TMA patches (one per 32-channel block and 16 x 8 output tile) shared by all nine
                                            taps instead of the per-tap gather; weight columns must be tap-major (tap * C + c); table / kcol unused */
+  int patch_ntaps;                      /* patch mode: number of taps (9 for 3x3; 8 for the space-to-depth form of the 7x7 / stride-2 stems) */
+  int patch_halo;                       /* patch rows beyond the 16 tile rows (2 for 3x3, 3 for the stems) */
+  int patch_org_y, patch_org_x;         /* the patch starts at (tile row - org_y, tile pixel - org_x) (1, 1 for 3x3 / pad 1) */
+  int patch_tapoff[16];                 /* per tap: (dy * 2048 + dx * 128) / 16 — start-address offset of the tap inside the patch */
   int patch_desc_mode;                  /* debug: 2 = set the UMMA matrix-descriptor base offset for the shifted patch start addresses (WRONG on
                                            B200: the swizzle follows absolute address bits; kept to reproduce the measurement) */
 } JpbConvArgs;
@@ -242,6 +246,11 @@ int jpb_conv3x3_smalln_bwd(const float* x, const float* w, const float* dz, floa
  * torch.backends.cudnn.allow_tf32 = False): x [rows][C] -> out [rows][2*Cp], Cp = C rounded up to 4; columns [0,Cp) hold
  * hi = x rounded to TF32 (nearest even), [Cp,2Cp) hold lo = x - hi; padding columns are zero.                    */
 int jpb_tf32_split(const float* x, float* out, long long rows, int C, void* stream);
+
+/* ---- space-to-depth form of the stem input for the TMA-patch convolution: x [B,H,W,Cp] (Cp = 4 | 8, H and W even) ->
+ * x3 [B,H/2,W/2+1,8*Cp], channel ((dy*4 + dx)*Cp + c) of position (oy, p) = x[b, 2*oy+dy, 2*(p-1)+dx, c] (dy < 2, dx < 4, zero
+ * outside the image).                                                                                                        */
+int jpb_stem_s2d(const float* x, float* x3, int B, int H, int W, int Cp, void* stream);
 
 /* ---- backward of the convolution epilogue: dz = dy * act'(y) (act as in JpbConvArgs, from the OUTPUT y) and
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */

@@ -81,7 +81,8 @@ class ConvArgs(C.Structure):
         ("dst", C.c_void_p * 3), ("dst_C", C.c_int * 3), ("dst_H", C.c_int * 3), ("dst_W", C.c_int * 3), ("dst_up", C.c_int * 3),
         ("ndst", C.c_int), ("fold_pad", C.c_int), ("fold_reflect", C.c_int), ("fold_H", C.c_int), ("fold_W", C.c_int),
         ("ntaps", C.c_int), ("kw", C.c_int), ("ksplit", C.c_int), ("kcol", C.c_void_p), ("l1_gather", C.c_int),
-        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p), ("acc_scale", C.c_float), ("patch", C.c_int), ("patch_desc_mode", C.c_int),
+        ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p), ("acc_scale", C.c_float), ("patch", C.c_int), ("patch_ntaps", C.c_int), ("patch_halo", C.c_int), ("patch_org_y", C.c_int),
+        ("patch_org_x", C.c_int), ("patch_tapoff", C.c_int * 16), ("patch_desc_mode", C.c_int),
     ]
 
 
@@ -175,6 +176,7 @@ class _Signatures:
     jpb_act_bwd = [P, P, P, C.c_longlong, I, I, P, V]
     jpb_bias_act = [P, P, P, C.c_longlong, I, I, V]
     jpb_tf32_split = [P, P, C.c_longlong, I, V]
+    jpb_stem_s2d = [P, P, I, I, I, I, V]
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]

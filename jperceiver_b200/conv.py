@@ -364,6 +364,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
         a.out = ptr(grads[0])
         if (not three) and wcols == kh * kw * Nc and _patch_ok(Nc, Cin, H, W, B, kh, kw, stride, pad, False, 1, False, ks) and a.pad == 1:
             a.patch, a.patch_desc_mode = 1 + PATCH_TILE_ROWS, PATCH_DESC_MODE
+            _patch_taps(a, TAPS_3X3, 2, (1, 1))
     else:
         a.scatter = 1
         a.ndst = len(xs)
@@ -496,6 +497,12 @@ class _ConvTC(torch.autograd.Function):
             ctx.cfg = cfg
             ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)
             return out
+        if residual is None and _stem_ok(weight, xs, ups, stride, pad, reflect, 1):
+            out = stem_forward(xs[0], weight, bias, act, cfg.get("bn_stats"))
+            ctx.cfg = cfg
+            ctx.has = (bias is not None, False)
+            ctx.save_for_backward(weight, bias, residual, out if act != "none" else None, *xs)
+            return out
         B = xs[0].shape[0]
         Hin = xs[0].shape[2] * (2 if ups[0] else 1)
         Win = xs[0].shape[3] * (2 if ups[0] else 1)
@@ -554,6 +561,7 @@ class _ConvTC(torch.autograd.Function):
         a.dbg_skip = DBG_SKIP
         if src_C == w_C and wcols == kh * kw * Cin and _patch_ok(Cin, N, Hin, Win, B, kh, kw, stride, pad, reflect, len(xs), ups[0], ks):
             a.patch, a.patch_desc_mode = 1 + PATCH_TILE_ROWS, PATCH_DESC_MODE
+            _patch_taps(a, TAPS_3X3, 2, (1, 1))
         tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
         check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd")
         if finish:
@@ -612,6 +620,86 @@ def _patch_ok(C, N, H, W, B, kh, kw, stride, pad, reflect, nsrc, up, ks):
     while nt < N and nt < 256:
         nt *= 2
     return ((N + nt - 1) // nt) * B * ((H + 15) // 16) * (W // 8) >= PATCH_MIN_TILES
+
+
+def _patch_taps(a, taps, halo, org):
+    """Fill the tap geometry of a patch-mode launch: ``taps`` = [(dy, dx)] offsets inside the patch (rows, pixels)."""
+    a.patch_ntaps, a.patch_halo, a.patch_org_y, a.patch_org_x = len(taps), halo, org[0], org[1]
+    for t, (dy, dx) in enumerate(taps):
+        a.patch_tapoff[t] = (dy * 2048 + dx * 128) >> 4
+
+
+TAPS_3X3 = [(ky, kx) for ky in range(3) for kx in range(3)]
+# the 7x7 / stride-2 / pad-3 stems in space-to-depth form (csrc/elementwise.cu: stem_s2d_kernel): 4 row taps (oy-2 .. oy+1) x 2
+# position taps (ox-1, ox+1 in x3's shifted coordinates), patch origin (tile row - 2, tile pixel - 1)
+TAPS_STEM = [(ai, bi) for ai in range(4) for bi in (0, 2)]
+STEM_PATCH = int(_os.environ.get("JPB_CONV_STEM_PATCH", "1"))
+_STEM_INDEX: dict = {}
+
+
+def _stem_ok(weight, xs, ups, stride, pad, reflect, ks):
+    N, Cin, kh, kw = weight.shape
+    if not (STEM_PATCH and PATCH and PRECISION == "tf32" and kh == 7 and kw == 7 and stride == 2 and pad == 3 and not reflect and len(xs) == 1 and not ups[0]):
+        return False
+    B, Cp, H, W = xs[0].shape
+    return Cp in (4, 8) and Cin <= Cp and H % 2 == 0 and W % 2 == 0 and (W // 2) % 8 == 0 and N % 16 == 0
+
+
+def stem_weight(weight, Cp):
+    """[N, 8 taps * 8*Cp] GEMM operand of the space-to-depth stem: column (t, dy, dx, c) = w[n, c, 2a+dy+3, 2b+dx+3] for tap
+    t = (a, b), a in -2..1, b in {-2, 0}; zero where the 7x7 window has no such element or c is a padding channel."""
+    N, Cin, kh, kw = weight.shape
+    key = (Cin, Cp, str(weight.device))
+    idx = _STEM_INDEX.get(key)
+    if idx is None:
+        cols = []
+        zero = Cin * 49                     # index of an appended zero column
+        for a_ in (-2, -1, 0, 1):
+            for b_ in (-2, 0):
+                for dy in range(2):
+                    for dx in range(4):
+                        ky, kx = 2 * a_ + dy + 3, 2 * b_ + dx + 3
+                        for c in range(Cp):
+                            cols.append((c * 49 + ky * 7 + kx) if (0 <= ky < 7 and 0 <= kx < 7 and c < Cin) else zero)
+        idx = _STEM_INDEX[key] = torch.tensor(cols, dtype=torch.long, device=weight.device)
+    w = torch.cat([weight.detach().reshape(N, Cin * 49), torch.zeros(N, 1, dtype=weight.dtype, device=weight.device)], 1)
+    return w.index_select(1, idx).contiguous()
+
+
+def stem_forward(x, weight, bias, act, bn_stats):
+    """7x7 / stride-2 / pad-3 stem as an 8-tap patch convolution over the space-to-depth input (no gather)."""
+    x = _cl(x)
+    B, Cp, H, W = x.shape
+    N = weight.shape[0]
+    Ho, Wo = H // 2, W // 2
+    dev = x.device
+    x3 = torch.empty((B, 8 * Cp, Ho, Wo + 1), dtype=torch.float32, device=dev, memory_format=CL)
+    check(_launch("stem_s2d", x, lambda: _lib.lib().jpb_stem_s2d(ptr(x), ptr(x3), B, H, W, Cp, stream_of(x))), "jpb_stem_s2d")
+    wmat = stem_weight(weight, Cp)
+    out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=dev, memory_format=CL)
+    a = _lib.ConvArgs()
+    a.acc_scale = _acc_scale()
+    _fill_sources(a, [x3], [False])
+    a.B, a.Hin, a.Win, a.Ho, a.Wo, a.N = B, Ho, Wo, Ho, Wo, N
+    a.stride, a.pad, a.reflect = 1, 0, 0
+    a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wmat.shape[1]
+    table = chunk_table([8 * Cp], 1, 1, dev)          # unused by the patch kernel (argument check only)
+    a.table, a.nkb = ptr(table), table.shape[0] // 8
+    a.ntaps, a.kw = len(TAPS_STEM), 2
+    a.bias = ptr(bias.detach()) if bias is not None else None
+    a.act = ACT[act]
+    a.out = ptr(out)
+    STATS_FUSED[0] = False
+    if bn_stats and N % 4 == 0:
+        from .functional import bn_stats_pointer
+        a.stats = bn_stats_pointer(N, dev)
+        STATS_FUSED[0] = True
+    a.patch, a.patch_desc_mode = 1 + PATCH_TILE_ROWS, PATCH_DESC_MODE
+    _patch_taps(a, TAPS_STEM, 3, (2, 1))
+    a.dbg_skip = DBG_SKIP
+    tag = (B * Ho * Wo, N, weight.shape[1] * 49, 7, 2, (Cp,), (0,), 0, 1)
+    check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd(stem)")
+    return out
 
 
 STATS_FUSED = [False]   # set by the last forward launch: its epilogue accumulated the BatchNorm statistics of its output

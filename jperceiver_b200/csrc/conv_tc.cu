@@ -1184,8 +1184,9 @@ __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(c
   constexpr int ACC_STRIDE = NT < 32 ? 32 : NT;
   constexpr uint32_t TMEM_COLS = 2 * TR * ACC_STRIDE;
   static_assert(TMEM_COLS <= 512, "TMEM columns");
-  constexpr int PATCH_ROWS = 16 * TR + 2;
-  constexpr int PATCH_BYTES = PATCH_ROWS * PATCH_PX * 128;
+  constexpr int PATCH_BYTES = (16 * TR + 3) * PATCH_PX * 128;     // buffer size: up to three halo rows (the stem's 4 x 2 taps)
+  const int ntaps = a.patch_ntaps;
+  const uint32_t patch_tx = (uint32_t)((16 * TR + a.patch_halo) * PATCH_PX * 128);   // bytes of one TMA box
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* s_patch = smem;                                   // [PSTAGES][PATCH_BYTES]
   unsigned char* s_b = smem + PSTAGES * PATCH_BYTES;               // [BSTAGES][B_STAGE]
@@ -1245,10 +1246,10 @@ __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(c
           mbar_wait(&pempty[ps], (((uint32_t)(pring / PSTAGES)) & 1u) ^ 1u);
           if (a.dbg_skip & 1) mbar_arrive(&pfull[ps]);            // timing experiment (wrong results): no patch traffic
           else {
-            mbar_expect_tx(&pfull[ps], (uint32_t)PATCH_BYTES);
-            tma_load_4d(smem_u32(s_patch + ps * PATCH_BYTES), &xmap, &pfull[ps], cb * 32, ox0 - 1, oy0 - 1, b_);
+            mbar_expect_tx(&pfull[ps], patch_tx);
+            tma_load_4d(smem_u32(s_patch + ps * PATCH_BYTES), &xmap, &pfull[ps], cb * 32, ox0 - a.patch_org_x, oy0 - a.patch_org_y, b_);
           }
-          for (int tap = 0; tap < 9; ++tap, ++bring) {
+          for (int tap = 0; tap < ntaps; ++tap, ++bring) {
             if (a.dbg_skip & 8) continue;                          // timing experiment: no per-tap weight hand-shake at all
             const int s = bring % BSTAGES;
             mbar_wait(&bempty[s], (((uint32_t)(bring / BSTAGES)) & 1u) ^ 1u);
@@ -1280,22 +1281,22 @@ __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(c
         mbar_wait(&pfull[ps], pph);
         tc_fence_after();
         const uint32_t a_lo0 = (((patch0 + (uint32_t)(ps * PATCH_BYTES)) >> 4) & 0x3FFFu) | DESC_LO_LBO1;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < ntaps; ++tap) {
           const bool nosync = (a.dbg_skip & 8) != 0;
           if (!nosync) {
             mbar_wait(&bfull[bs], bph);
             tc_fence_after();
           }
-          // tap (ky, kx): the same patch, start address moved by ky rows (2048 B) and kx pixels (128 B).  The swizzle follows
-          // the ABSOLUTE shared-memory address bits (measured: tests/test_conv.py patch cases), so the base-offset field stays 0.
-          const uint32_t a_lo = a_lo0 + (uint32_t)(((tap / 3) * 2048 + (tap % 3) * 128) >> 4);
+          // tap (dy, dx): the same patch, start address moved by dy rows (2048 B) and dx pixels (128 B) — patch_tapoff, in 16-byte
+          // units.  The swizzle follows the ABSOLUTE shared-memory address bits (measured: tests/test_conv.py patch cases), so the
+          // descriptor's base-offset field stays 0.
+          const uint32_t a_lo = a_lo0 + (uint32_t)a.patch_tapoff[tap];
           const uint32_t b_lo = (((b0addr + (uint32_t)(bs * B_STAGE)) >> 4) & 0x3FFFu) | DESC_LO_LBO1;
           const uint32_t first = (cb | tap) ? 1u : 0u;
           umma_tf32_k4(tacc + (uint32_t)(mr * ACC_STRIDE), a_lo + (uint32_t)((mr * 16 * 2048) >> 4), b_lo, a_hi, b_hi, idesc, first,
                        mr == 0 ? 1u : lower_ok);
           if (!nosync) umma_commit_elect(bempty0 + (uint32_t)bs * 8u);
-          if (tap == 8) {
+          if (tap == ntaps - 1) {
             umma_commit_elect(pempty0 + (uint32_t)ps * 8u);
             if (cb == ncb - 1) umma_commit_elect(accf0 + (uint32_t)buf * 8u);
           }
@@ -1461,7 +1462,7 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
 
 template <int NT, int TR, int PSTAGES, int BSTAGES>
 int launch_patch(const JpbConvArgs* a, const CUtensorMap& xmap, const CUtensorMap& wmap, cudaStream_t st) {
-  constexpr int smem = PSTAGES * (16 * TR + 2) * PATCH_PX * 128 + BSTAGES * NT * BK * 4 + 4 * EPI_WARP_FLOATS * 4 + 1024 + 256;
+  constexpr int smem = PSTAGES * (16 * TR + 3) * PATCH_PX * 128 + BSTAGES * NT * BK * 4 + 4 * EPI_WARP_FLOATS * 4 + 1024 + 256;
   static_assert(smem <= 227 * 1024, "patch kernel shared memory");
   static bool configured = false;
   if (!configured) {
@@ -1479,9 +1480,14 @@ int launch_patch(const JpbConvArgs* a, const CUtensorMap& xmap, const CUtensorMa
 
 // 3x3 / stride 1 / zero pad 1 / one dense source with C % 32 == 0 / W % 8 == 0: the TMA-patch kernel
 int conv2d_patch(const JpbConvArgs* a, cudaStream_t st) {
-  if (a->nsrc != 1 || a->src_up[0] || a->stride != 1 || a->pad != 1 || a->reflect || a->ntaps != 9 || a->kw != 3 || a->in_div || a->scatter ||
-      a->ksplit > 1 || (a->src_C[0] & 31) || (a->Wo & 7) || a->Ho != a->src_H[0] || a->Wo != a->src_W[0] || (a->N & 15) || a->w_cols != 9 * a->src_C[0])
+  if (a->nsrc != 1 || a->src_up[0] || a->reflect || a->in_div || a->scatter || a->ksplit > 1 || (a->src_C[0] & 31) || (a->Wo & 7) ||
+      a->Ho != a->src_H[0] || a->Wo > a->src_W[0] || (a->N & 15) || a->patch_ntaps < 1 || a->patch_ntaps > 16 ||
+      a->w_cols != a->patch_ntaps * a->src_C[0] || a->patch_halo < 0 || a->patch_halo > 3)
     return JPB_ERR_ARG;
+  for (int t = 0; t < a->patch_ntaps; ++t) {        // every tap must stay inside the 16-pixel x (16 + halo)-row patch
+    const int dy = (a->patch_tapoff[t] * 16) / 2048, dx = ((a->patch_tapoff[t] * 16) % 2048) / 128;
+    if (a->patch_tapoff[t] < 0 || ((a->patch_tapoff[t] * 16) % 128) || dy > a->patch_halo || dx + 8 > PATCH_PX) return JPB_ERR_ARG;
+  }
   if ((reinterpret_cast<uintptr_t>(a->src[0]) & 15) || (reinterpret_cast<uintptr_t>(a->weight) & 15) || (a->w_row & 3)) return JPB_ERR_ARG;
   EncodeTiledFn enc = get_encode();
   if (!enc) return JPB_ERR_UNSUPPORTED;
@@ -1503,7 +1509,7 @@ int conv2d_patch(const JpbConvArgs* a, cudaStream_t st) {
   {
     const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a->B};
     const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    const cuuint32_t box[4] = {32, (cuuint32_t)PATCH_PX, (cuuint32_t)(16 * tr + 2), 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)PATCH_PX, (cuuint32_t)(16 * tr + a->patch_halo), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->src[0]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -107,6 +107,31 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float* x, float* 
   }
 }
 
+
+// Space-to-depth form of the stem input (7x7 / stride-2 convolutions, ResnetEncoder.py / resnet.py conv1): x [B,H,W,Cp] (Cp = 4 or
+// 8: the 3 / 6 image channels zero-padded) -> x3 [B, H/2, W/2 + 1, 8*Cp]: position (oy, p) holds the 2 x 4 input pixels of rows
+// 2*oy + dy (dy < 2) and columns 2*(p - 1) + dx (dx < 4), channel ((dy*4 + dx)*Cp + c), zero outside the image.  The 4-wide column
+// windows overlap (stride 2) and the one at p = 0 reaches the valid columns 0 and 1 — hence the extra leading position.  The
+// stride-2 7x7 window of output (oy, ox) becomes 4 x 2 stride-1 taps over x3: rows oy-2 .. oy+1, positions ox - 1 and ox + 1,
+// which the TMA-patch convolution reads without any gather.
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* x, float* x3, int B, int H, int W, int Cp) {
+  const int H2 = H >> 1, W3 = (W >> 1) + 1, v4 = Cp >> 2;       // float4 per (dy, dx) group
+  const long long n = (long long)B * H2 * W3 * 8 * v4;
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n; i += (long long)gridDim.x * JPB_NT) {
+    const int q = (int)(i % v4);
+    long long r = i / v4;
+    const int g = (int)(r % 8); r /= 8;
+    const int p = (int)(r % W3); r /= W3;
+    const int oy = (int)(r % H2);
+    const int b = (int)(r / H2);
+    const int dy = g >> 2, dx = g & 3;
+    const int iy = 2 * oy + dy, ix = 2 * (p - 1) + dx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ix >= 0 && ix < W) v = *reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * Cp + q * 4);
+    *reinterpret_cast<float4*>(x3 + i * 4) = v;
+  }
+}
+
 }  // namespace
 
 extern "C" int jpb_bias_act(float* z, const float* bias, const float* residual, long long rows, int C, int act, void* stream) {
@@ -132,5 +157,14 @@ extern "C" int jpb_tf32_split(const float* x, float* out, long long rows, int C,
   long long blocks = (rows * Cp + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   JPB_LAUNCH(tf32_split_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, out, rows, C, Cp);
+  return jpb_status();
+}
+
+extern "C" int jpb_stem_s2d(const float* x, float* x3, int B, int H, int W, int Cp, void* stream) {
+  if (!x || !x3 || B < 1 || H < 2 || W < 4 || (H & 1) || (W & 1) || (Cp != 4 && Cp != 8)) return JPB_ERR_ARG;
+  const long long n = (long long)B * (H / 2) * (W / 2 + 1) * 8 * (Cp / 4);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  JPB_LAUNCH(stem_s2d_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, x3, B, H, W, Cp);
   return jpb_status();
 }
