@@ -50,6 +50,11 @@ typedef struct JpbPhotoArgs {
   unsigned char* winner;           /* [B,H,W] same argmin as a byte (kept for backward) or NULL    */
   float* warped[JPB_MAX_SRC];      /* [B,3,H,W] outputs[("color",f,s)] or NULL.  Forward: written.  Backward: when non-NULL, the
                                       frames the forward of this scale wrote are staged instead of being re-projected          */
+  float* ident_err;                /* [B,H,W,2] identity-candidate errors (frame 0, frame 1) WITHOUT the tie-breaking noise, or NULL.
+                                      They compare the target with the un-warped sources (net.py:159-166) and do not depend on the
+                                      scale: one launch of a step computes them, the others read them                          */
+  int ident_mode;                  /* 0: compute, do not store (default); 1: compute and store to ident_err; 2: read ident_err
+                                      (forward schedule 3 with automask only; the backward ignores both fields)                */
 } JpbPhotoArgs;
 
 typedef struct JpbPhotoGrad {
@@ -64,7 +69,11 @@ int jpb_photometric_fwd(const JpbPhotoArgs* args, void* stream);
 /* Forward schedule: 2 = one value per instruction (default, the measured one); 3 = the two source frames of a snippet packed
  * into FADD2/FMUL2/FFMA2 pairs (same results within fp32 rounding).  Process-wide; not thread-safe against running launches. */
 int jpb_photometric_set_variant(int fwd_variant);
+int jpb_photometric_get_variant(void);   /* the forward schedule in force (ident_mode needs schedule 3) */
 int jpb_photometric_bwd(const JpbPhotoArgs* args, const JpbPhotoGrad* grad, void* stream);
+/* Backward schedule: 4 = register-resident kernel specialised on F <= 2 (default; F > 2 always takes schedule 1); 1 = the
+ * generic kernel.  Same gradients within fp32 summation order.  Process-wide; not thread-safe against running launches.       */
+int jpb_photometric_set_bwd_variant(int bwd_variant);
 
 /* ---- area-downsampled target pyramid -----------------------------------------------------------
  * level[s] = F.interpolate(img, (H/2^(s+1), W/2^(s+1)), mode="area")  (net.py:762), all levels in one

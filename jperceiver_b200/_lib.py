@@ -32,7 +32,7 @@ class PhotoArgs(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hs", C.c_int), ("ws", C.c_int), ("F", C.c_int),
         ("automask", C.c_int), ("min_disp", C.c_float), ("max_disp", C.c_float), ("noise_scale", C.c_float),
         ("seed", C.c_uint64), ("stream", C.c_uint64), ("step", C.c_void_p), ("loss_sum", C.c_void_p), ("min_index", C.c_void_p),
-        ("winner", C.c_void_p), ("warped", C.c_void_p * MAX_SRC),
+        ("winner", C.c_void_p), ("warped", C.c_void_p * MAX_SRC), ("ident_err", C.c_void_p), ("ident_mode", C.c_int),
     ]
 
 
@@ -147,6 +147,8 @@ class _Signatures:
     jpb_photometric_fwd = [C.POINTER(PhotoArgs), V]
     jpb_photometric_bwd = [C.POINTER(PhotoArgs), C.POINTER(PhotoGrad), V]
     jpb_photometric_set_variant = [I]
+    jpb_photometric_get_variant = []
+    jpb_photometric_set_bwd_variant = [I]
     jpb_finalize = [P, P, F, P, I, V]
     jpb_weight_flipT = [P, I, I, V]
     jpb_cct_select_fwd = [P] * 10 + [I, I, I, I, V]
@@ -209,6 +211,11 @@ def lib():
         if v:
             check(_handle.jpb_photometric_set_variant(int(v)), "jpb_photometric_set_variant(JPB_PHOTO_FWD=%s)" % v)
     return _handle
+
+
+def photo_fwd_variant():
+    """Forward schedule of the photometric kernel in force (``jpb_photometric_set_variant``)."""
+    return int(lib().jpb_photometric_get_variant())
 
 
 def use_library(path, emulated=False):

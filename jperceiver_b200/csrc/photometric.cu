@@ -526,13 +526,18 @@ __device__ __forceinline__ void pair_row(PairState& S, const float2 xa, const fl
   S.h1a = S.h1b; S.h1b = h1; S.h2a = S.h2b; S.h2b = h2; S.h3a = S.h3b; S.h3b = h3; S.xbp = xb;
 }
 
-__global__ void __launch_bounds__(256, 2) photometric_fwd_kernel(JpbPhotoArgs a) {
+// IDENT: 0 = no identity candidates (automask off); 1 = computed here (and stored to a.ident_err when a.ident_mode == 1);
+// 2 = read from a.ident_err (computed by another scale's launch of the same step: the identity terms compare the target with
+// the un-warped full-resolution sources, net.py:159-166, and do not depend on the scale).  Modes 0 / 2 stage and evaluate only
+// the warped pair: fewer instructions, no identity tile in shared memory, three resident CTAs per SM instead of two.
+template <int IDENT>
+__global__ void __launch_bounds__(256, IDENT == 1 ? 2 : 3) photometric_fwd_kernel(JpbPhotoArgs a) {
   JPB_DYN_SMEM(float, sm);
   __shared__ SrcGeom geom[2];
   __shared__ double red[32];
   const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int F = a.F, H = a.H, W = a.W;
-  const bool ident = a.automask != 0;
+  constexpr bool ident = IDENT == 1;
   const int pl = H * W;
   float* s_tgt = sm;                                                  // [3][AN]
   float2* s_wp = reinterpret_cast<float2*>(sm + 3 * AN);              // [3][AN] warped (f0, f1)
@@ -649,8 +654,10 @@ __global__ void __launch_bounds__(256, 2) photometric_fwd_kernel(JpbPhotoArgs a)
       float best = 3.0e38f;
       int besti = 0;
       int nid = 0;
-      if (ident) {
+      if (IDENT != 0) {
         nid = F;
+        if (IDENT == 2) errI[r] = __ldg(reinterpret_cast<const float2*>(a.ident_err) + po);
+        else if (a.ident_mode == 1) reinterpret_cast<float2*>(a.ident_err)[po] = errI[r];
         float nz0 = 0.f, nz1 = 0.f;
         if (!a.noise[0] && a.noise_scale != 0.f) {
           randn2(a.seed, a.stream + (a.step ? 64ull * (uint64_t)a.step[0] : 0ull), (uint64_t)po, nz0, nz1);
@@ -887,9 +894,318 @@ __global__ void __launch_bounds__(256) photometric_bwd_kernel(JpbPhotoArgs a, Jp
   }
 }
 
+
+// ------------------------------------------------------------------------------------ backward, F <= 2 (every reference configuration)
+// Same mathematics as photometric_bwd_kernel, re-organised around its ncu capture (profiles/r2_ncu_photo_bwd.csv: 108 M warp
+// instructions per launch at 17 of 32 lanes active, pose accumulators in local memory, 48 block barriers for the 24 pose sums,
+// shared-memory float atomics that serialise 16-fold on the coarse scales):
+//  * F is a template parameter: every per-frame array lives in registers and the frame loops unroll;
+//  * the two warped frames are staged interleaved as float2, the window coefficients (alpha, beta, gamma) of a window's
+//    winning frame as one float4 per channel (w of channel 0 = the winning frame or -1): phase C reads 3 LDS.128 per window;
+//  * the transposed bilinear up-sampling of the disparity gradient is separable and gather-based — per-pixel d(loss)/d(D)
+//    goes to shared memory, then (row, texel column) sums, then (texel row, texel column) sums: no shared-memory atomics and one
+//    global atomic per texel of the tile's footprint;
+//  * the 12 F pose sums are reduced with warp shuffles and ONE shared-memory transposition (two barriers in all).
+namespace v4 {
+constexpr int TW = 32, TH = 16;
+constexpr int W2 = TW + 4, H2 = TH + 4, N2 = W2 * H2;   // tile + 2-pixel apron: staged pixels
+constexpr int W1 = TW + 2, H1 = TH + 2, N1 = W1 * H1;   // tile + 1-pixel apron: SSIM windows
+constexpr int FJ = TW + 2, FI = TH + 2;                 // largest disparity footprint of a tile (up-sampling factor >= 1)
+constexpr int NWARP_MAX = 8;
+constexpr int SMEM_FLOATS = 4 * 3 * N1 + 3 * N2 + 2 * 3 * N2 + TW * TH + TH * FJ + NWARP_MAX * 24 + 24;
+
+// weight with which pixel coordinate `p` of the up-sampled axis reads texel `t` (both taps may coincide at the far border)
+__device__ __forceinline__ float up_weight(int p, float scale, int in_size, int t) {
+  int i0, i1;
+  float l1;
+  up_axis(p, scale, in_size, i0, i1, l1);
+  return (i0 == t ? 1.f - l1 : 0.f) + (i1 == t ? l1 : 0.f);
+}
+
+template <int F>
+__global__ void __launch_bounds__(256, 3) photometric_bwd_kernel(JpbPhotoArgs a, JpbPhotoGrad g) {
+  JPB_DYN_SMEM(float, sm);
+  __shared__ SrcGeom geom[2];
+  const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int H = a.H, W = a.W, hs = a.hs, ws = a.ws;
+  const int nid = a.automask ? F : 0;
+  float4* s_cf = reinterpret_cast<float4*>(sm);                 // [3][N1] (alpha, beta, gamma, sel) of the window's winning frame
+  float* s_tgt = sm + 4 * 3 * N1;                               // [3][N2]
+  float2* s_wp = reinterpret_cast<float2*>(s_tgt + 3 * N2);     // [3][N2] warped (f0, f1)
+  float* s_gd = s_tgt + 3 * N2 + 2 * 3 * N2;                    // [TH][TW] d(loss)/d(up-sampled disparity)
+  float* s_h = s_gd + TW * TH;                                  // [TH][FJ] horizontally gathered
+  float* s_red = s_h + TH * FJ;                                 // [NWARP_MAX][24] + [24]
+  const int pl = H * W;
+  const float gpix = g.grad_out[0] * g.inv_count;
+
+  for (int f = JPB_TID; f < F; f += JPB_NT) make_geom(a.K + b * 16, a.T[f] + b * 16, geom[f]);
+  const float* disp = a.disp + (size_t)b * hs * ws;
+  const float sy = (float)hs / (float)H, sx = (float)ws / (float)W;
+  const float* tg0 = a.target + (size_t)b * 3 * pl;
+  const float* sp0 = a.src[0] + (size_t)b * 3 * pl;
+  const float* sp1 = a.src[F > 1 ? 1 : 0] + (size_t)b * 3 * pl;
+  const float* wk0 = a.warped[0] ? a.warped[0] + (size_t)b * 3 * pl : nullptr;
+  const float* wk1 = (F > 1 && a.warped[1]) ? a.warped[1] + (size_t)b * 3 * pl : nullptr;
+  const bool kept = wk0 != nullptr && (F == 1 || wk1 != nullptr);
+  if (!kept) __syncthreads();   // geom is read in phase A only when the apron is re-projected
+
+  // ---- phase A: target + warped frames on the 2-pixel apron
+  for (int e = JPB_TID; e < N2; e += JPB_NT) {
+    const int hy = e / W2, hx = e - hy * W2;
+    const int y = jpb_reflect(jpb_clampi(y0 + hy - 2, -(H - 1), H), H), x = jpb_reflect(jpb_clampi(x0 + hx - 2, -(W - 1), W), W);
+    const int o = y * W + x;
+    s_tgt[e] = __ldg(tg0 + o); s_tgt[N2 + e] = __ldg(tg0 + pl + o); s_tgt[2 * N2 + e] = __ldg(tg0 + 2 * pl + o);
+    float v0[3], v1[3];
+    if (kept) {   // the forward launch of this scale kept its warped frames (outputs[("color",f,s)]): stage them as they are
+      v0[0] = __ldg(wk0 + o); v0[1] = __ldg(wk0 + pl + o); v0[2] = __ldg(wk0 + 2 * pl + o);
+      if (F > 1) { v1[0] = __ldg(wk1 + o); v1[1] = __ldg(wk1 + pl + o); v1[2] = __ldg(wk1 + 2 * pl + o); }
+    } else {
+      DispTap tp;
+      const float D = disp_upsample(disp, hs, ws, sy, sx, y, x, tp);
+      const float z = 1.f / (a.min_disp + (a.max_disp - a.min_disp) * D);
+      float rc[3];
+      pixel_ray(a.invK + b * 16, x, y, rc);
+      Sample s;
+      project(geom[0], z, rc, W, H, s);
+      gather3(sp0, H, W, s, v0);
+      if (F > 1) {
+        project(geom[1], z, rc, W, H, s);
+        gather3(sp1, H, W, s, v1);
+      }
+    }
+    if (F == 1) { v1[0] = v0[0]; v1[1] = v0[1]; v1[2] = v0[2]; }
+    s_wp[e] = make_float2(v0[0], v1[0]); s_wp[N2 + e] = make_float2(v0[1], v1[1]); s_wp[2 * N2 + e] = make_float2(v0[2], v1[2]);
+  }
+  __syncthreads();
+
+  // ---- phase B: per SSIM window q (tile + 1 apron), for its winning warped frame: d(err_q)/d(x_i) = alpha + beta*x_i + gamma*y_i
+  for (int e = JPB_TID; e < N1; e += JPB_NT) {
+    const int hy = e / W1, hx = e - hy * W1;
+    const int y = y0 + hy - 1, x = x0 + hx - 1;
+    int sel = -1;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const int w = (int)g.winner[(size_t)b * pl + (size_t)y * W + x];
+      if (w >= nid && w - nid < F) sel = w - nid;
+    }
+    if (sel < 0) {
+      s_cf[e] = make_float4(0.f, 0.f, 0.f, -1.f);
+      s_cf[N1 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s_cf[2 * N1 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const int ctr = (hy + 1) * W2 + hx + 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float2* xp = s_wp + c * N2 + ctr;
+      const float* yp = s_tgt + c * N2 + ctr;
+      float sxv = 0.f, syv = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const float2 xw = xp[dy * W2 + dx];
+          const float xv = sel ? xw.y : xw.x, yv = yp[dy * W2 + dx];
+          sxv += xv; syv += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
+        }
+      const float ma = sxv * (1.f / 9.f), mb = syv * (1.f / 9.f);
+      const float va = sxx * (1.f / 9.f) - ma * ma, vb = syy * (1.f / 9.f) - mb * mb, vab = sxy * (1.f / 9.f) - ma * mb;
+      const float n1 = 2.f * ma * mb + SSIM_C1, n2 = 2.f * vab + SSIM_C2;
+      const float d1 = ma * ma + mb * mb + SSIM_C1, d2 = va + vb + SSIM_C2;
+      const float inv = 1.f / (d1 * d2);
+      const float S = (1.f - n1 * n2 * inv) * 0.5f;
+      float al = 0.f, be = 0.f, ga = 0.f;
+      if (S >= 0.f && S <= 1.f) {
+        // dS/dx_i = -(1/2) * (2/9) * [ (mb*n2 + n1*(y_i-mb))*inv - n1*n2*inv^2*(ma*d2 + d1*(x_i-ma)) ]
+        const float k = -(1.f / 9.f) * (0.85f / 3.f) * gpix;
+        const float q = n1 * n2 * inv * inv;
+        al = k * ((mb * n2 - n1 * mb) * inv - q * (ma * d2 - d1 * ma));
+        be = k * (-q * d1);
+        ga = k * (n1 * inv);
+      }
+      s_cf[c * N1 + e] = make_float4(al, be, ga, c == 0 ? (float)sel : 0.f);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: window contributions per pixel, back through grid_sample / projection / disparity
+  float G[F][12];
+#pragma unroll
+  for (int f = 0; f < F; ++f)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) G[f][i] = 0.f;
+  const float l1k = (0.15f / 3.f) * gpix;
+  const float drange = a.max_disp - a.min_disp;
+  for (int e = JPB_TID; e < TW * TH; e += JPB_NT) {
+    const int ty = e / TW, tx = e - ty * TW;
+    const int y = y0 + ty, x = x0 + tx;
+    float gD = 0.f;
+    if (y < H && x < W) {
+      const int c1 = (ty + 1) * W1 + tx + 1, c2 = (ty + 2) * W2 + tx + 2;
+      const float2 xw0 = s_wp[c2], xw1 = s_wp[N2 + c2], xw2 = s_wp[2 * N2 + c2];
+      const float yv0 = s_tgt[c2], yv1 = s_tgt[N2 + c2], yv2 = s_tgt[2 * N2 + c2];
+      float gw[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int qy = y + dy;
+        if (qy < 0 || qy >= H) continue;
+        const float mrow = ((qy == 0 && y == 1) || (qy == H - 1 && y == H - 2)) ? 2.f : 1.f;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int qx = x + dx;
+          if (qx < 0 || qx >= W) continue;
+          const int qe = c1 + dy * W1 + dx;
+          const float4 k0 = s_cf[qe];
+          if (k0.w < 0.f) continue;
+          const float4 k1 = s_cf[N1 + qe], k2 = s_cf[2 * N1 + qe];
+          const bool second = k0.w > 0.5f;
+          const float m = mrow * (((qx == 0 && x == 1) || (qx == W - 1 && x == W - 2)) ? 2.f : 1.f);
+          const float t0 = m * (k0.x + k0.y * (second ? xw0.y : xw0.x) + k0.z * yv0);
+          const float t1 = m * (k1.x + k1.y * (second ? xw1.y : xw1.x) + k1.z * yv1);
+          const float t2 = m * (k2.x + k2.y * (second ? xw2.y : xw2.x) + k2.z * yv2);
+          if (second) { gw[1][0] += t0; gw[1][1] += t1; gw[1][2] += t2; }
+          else { gw[0][0] += t0; gw[0][1] += t1; gw[0][2] += t2; }
+        }
+      }
+      {
+        const float selp = s_cf[c1].w;
+        if (selp >= 0.f) {
+          const bool second = selp > 0.5f;
+          const float d0 = (second ? xw0.y : xw0.x) - yv0, d1 = (second ? xw1.y : xw1.x) - yv1, d2 = (second ? xw2.y : xw2.x) - yv2;
+          const float a0 = l1k * d0 / sqrtf(d0 * d0 + 1e-6f), a1 = l1k * d1 / sqrtf(d1 * d1 + 1e-6f), a2 = l1k * d2 / sqrtf(d2 * d2 + 1e-6f);
+          if (second) { gw[1][0] += a0; gw[1][1] += a1; gw[1][2] += a2; }
+          else { gw[0][0] += a0; gw[0][1] += a1; gw[0][2] += a2; }
+        }
+      }
+      bool any = false;
+#pragma unroll
+      for (int f = 0; f < F; ++f) any = any || gw[f][0] != 0.f || gw[f][1] != 0.f || gw[f][2] != 0.f;
+      if (any) {
+        DispTap tp;
+        const float D = disp_upsample(disp, hs, ws, sy, sx, y, x, tp);
+        const float z = 1.f / (a.min_disp + drange * D);
+        float gz = 0.f;
+        float rc[3];
+        pixel_ray(a.invK + b * 16, x, y, rc);
+        const float X0 = z * rc[0], X1 = z * rc[1], X2 = z * rc[2];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          if (gw[f][0] == 0.f && gw[f][1] == 0.f && gw[f][2] == 0.f) continue;
+          Sample s;
+          project(geom[f], z, rc, W, H, s);
+          const float* img = f ? sp1 : sp0;
+          const int x1 = s.x0 + 1, y1 = s.y0 + 1;
+          const bool xin = x1 < W, yin = y1 < H;
+          const int o00 = s.y0 * W + s.x0;
+          float gix = 0.f, giy = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* p = img + c * pl;
+            const float nw = __ldg(p + o00), ne = xin ? __ldg(p + o00 + 1) : 0.f, sw = yin ? __ldg(p + o00 + W) : 0.f,
+                        se = (xin && yin) ? __ldg(p + o00 + W + 1) : 0.f;
+            gix += gw[f][c] * ((ne - nw) * (1.f - s.ty) + (se - sw) * s.ty);
+            giy += gw[f][c] * ((sw - nw) * (1.f - s.tx) + (se - ne) * s.tx);
+          }
+          // ix = u*W/(W-1) - 0.5  (clip mask mx), u = px/(pz+eps)
+          const float gu = gix * s.mx * ((float)W / (float)(W - 1)), gv = giy * s.my * ((float)H / (float)(H - 1));
+          const float iden = 1.f / (s.p[2] + 1e-7f);
+          const float gp0 = gu * iden, gp1 = gv * iden;
+          const float gp2 = -(gu * s.p[0] + gv * s.p[1]) * iden * iden;
+          const float* P = geom[f].P;
+          gz += gp0 * (P[0] * rc[0] + P[1] * rc[1] + P[2] * rc[2]) + gp1 * (P[4] * rc[0] + P[5] * rc[1] + P[6] * rc[2]) +
+                gp2 * (P[8] * rc[0] + P[9] * rc[1] + P[10] * rc[2]);
+          // G[i][j] += gp_i * Xh_j with Xh = (z*rc, 1)
+          G[f][0] += gp0 * X0; G[f][1] += gp0 * X1; G[f][2] += gp0 * X2; G[f][3] += gp0;
+          G[f][4] += gp1 * X0; G[f][5] += gp1 * X1; G[f][6] += gp1 * X2; G[f][7] += gp1;
+          G[f][8] += gp2 * X0; G[f][9] += gp2 * X1; G[f][10] += gp2 * X2; G[f][11] += gp2;
+        }
+        gD = gz * (-drange * z * z);
+      }
+    }
+    s_gd[e] = gD;
+  }
+  __syncthreads();
+
+  // ---- phase D: transposed bilinear up-sampling of gD, separable, gather form.  Footprint of the tile in disp_s:
+  int fy0, fx0, fy1, fx1, tmp;
+  float tl;
+  up_axis(min(y0, H - 1), sy, hs, fy0, tmp, tl);
+  up_axis(min(x0, W - 1), sx, ws, fx0, tmp, tl);
+  up_axis(min(y0 + TH - 1, H - 1), sy, hs, tmp, fy1, tl);
+  up_axis(min(x0 + TW - 1, W - 1), sx, ws, tmp, fx1, tl);
+  const int nj = min(fx1 - fx0 + 1, FJ), ni = min(fy1 - fy0 + 1, FI);
+  const float rx = (float)W / (float)ws, ry = (float)H / (float)hs;
+  const int xe = min(TW, W - x0), ye = min(TH, H - y0);          // valid pixels of the tile
+  for (int e = JPB_TID; e < TH * nj; e += JPB_NT) {
+    const int ty = e / nj, j = e - ty * nj, t = fx0 + j;
+    // pixels whose taps can touch texel t: source coordinate in [t - 1, t + 1)  ->  x + 0.5 in [(t - 0.5) rx, (t + 1.5) rx)
+    const int lo = max((int)floorf(((float)t - 0.5f) * rx - 0.5f) - 1 - x0, 0);
+    const int hi = min((int)ceilf(((float)t + 1.5f) * rx - 0.5f) + 1 - x0, xe - 1);
+    float acc = 0.f;
+    if (ty < ye)
+      for (int px = (t == 0 ? 0 : lo); px <= (t == ws - 1 ? xe - 1 : hi); ++px) acc += up_weight(x0 + px, sx, ws, t) * s_gd[ty * TW + px];
+    s_h[ty * FJ + j] = acc;
+  }
+  __syncthreads();
+  float* gd = g.grad_disp + (size_t)b * hs * ws;
+  for (int e = JPB_TID; e < ni * nj; e += JPB_NT) {
+    const int i = e / nj, j = e - i * nj, t = fy0 + i;
+    const int lo = max((int)floorf(((float)t - 0.5f) * ry - 0.5f) - 1 - y0, 0);
+    const int hi = min((int)ceilf(((float)t + 1.5f) * ry - 0.5f) + 1 - y0, ye - 1);
+    float acc = 0.f;
+    for (int py = (t == 0 ? 0 : lo); py <= (t == hs - 1 ? ye - 1 : hi); ++py) acc += up_weight(y0 + py, sy, hs, t) * s_h[py * FJ + j];
+    if (acc != 0.f) atomicAdd(&gd[t * ws + fx0 + j], acc);
+  }
+
+  // ---- phase E: pose gradient, dT[k][j] = sum_i K[i][k] * G[i][j]: warp shuffles, one shared-memory transposition
+  float* s_tot = s_red + NWARP_MAX * 24;
+#if defined(JPB_HOST_EMU) && !defined(JPB_HOST_EMU_MT)
+  for (int f = 0; f < F; ++f)
+    for (int i = 0; i < 12; ++i) s_tot[f * 12 + i] = G[f][i];
+#else
+  {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        float v = G[f][i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[wid * 24 + f * 12 + i] = v;
+      }
+    __syncthreads();
+    if ((int)threadIdx.x < 12 * F) {
+      float v = 0.f;
+      for (int w = 0; w < nw; ++w) v += s_red[w * 24 + threadIdx.x];
+      s_tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+#endif
+  for (int e = JPB_TID; e < 16 * F; e += JPB_NT) {
+    const int f = e >> 4, k = (e >> 2) & 3, j = e & 3;
+    if (!g.grad_T[f]) continue;
+    const float* K = a.K + b * 16;
+    const float* tot = s_tot + f * 12;
+    const float v = K[0 * 4 + k] * tot[0 * 4 + j] + K[1 * 4 + k] * tot[1 * 4 + j] + K[2 * 4 + k] * tot[2 * 4 + j];
+    if (v != 0.f) atomicAdd(&g.grad_T[f][b * 16 + k * 4 + j], v);
+  }
+}
+}  // namespace v4
+
 }  // namespace
 
 static int g_fwd_variant = 3;   // 3: v3::photometric_fwd_kernel (packed fp32; measured 24 % faster on B200, profiles/r2_photometric_ab.jsonl); 2: photometric_fwd_kernel
+
+static int g_bwd_variant = 4;   // 4: v4::photometric_bwd_kernel<F> (F <= 2); 1: photometric_bwd_kernel (any F)
+
+extern "C" int jpb_photometric_set_bwd_variant(int bwd_variant) {
+  if (bwd_variant != 1 && bwd_variant != 4) return JPB_ERR_ARG;
+  g_bwd_variant = bwd_variant;
+  return JPB_OK;
+}
+
+extern "C" int jpb_photometric_get_variant(void) { return g_fwd_variant; }
 
 extern "C" int jpb_photometric_set_variant(int fwd_variant) {
   if (fwd_variant != 2 && fwd_variant != 3) return JPB_ERR_ARG;
@@ -900,19 +1216,28 @@ extern "C" int jpb_photometric_set_variant(int fwd_variant) {
 extern "C" int jpb_photometric_fwd(const JpbPhotoArgs* a, void* stream) {
   if (!a || a->F < 1 || a->F > JPB_MAX_SRC || a->H < 3 || a->W < 3 || !a->loss_sum) return JPB_ERR_ARG;
   const int nid = a->automask ? a->F : 0;
+  if (a->ident_mode < 0 || a->ident_mode > 2 || (a->ident_mode && (!a->ident_err || !nid))) return JPB_ERR_ARG;
   if (a->F <= 2 && g_fwd_variant == 3 && (long long)a->H * a->W * 3 < (1ll << 31)) {   // packed variant (default)
-    const size_t smem = (size_t)(3 + 6 + (nid ? 6 : 0)) * v3::AN * sizeof(float);
+    const int mode = !nid ? 0 : (a->ident_mode == 2 ? 2 : 1);
+    const size_t smem = (size_t)(3 + 6 + (mode == 1 ? 6 : 0)) * v3::AN * sizeof(float);
     dim3 grid((a->W + v3::TW - 1) / v3::TW, (a->H + v3::TH - 1) / v3::TH, a->B);
 #ifndef JPB_HOST_EMU
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      if (cudaFuncSetAttribute(v3::photometric_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
-      configured = smem;
+    static bool configured = false;
+    if (!configured) {
+      const int big = (int)((3 + 6 + 6) * v3::AN * sizeof(float)), lean = (int)((3 + 6) * v3::AN * sizeof(float));
+      if (cudaFuncSetAttribute(v3::photometric_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+          cudaFuncSetAttribute(v3::photometric_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean) != cudaSuccess ||
+          cudaFuncSetAttribute(v3::photometric_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lean) != cudaSuccess)
+        return JPB_ERR_UNSUPPORTED;
+      configured = true;
     }
 #endif
-    JPB_LAUNCH(v3::photometric_fwd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+    if (mode == 0) JPB_LAUNCH(v3::photometric_fwd_kernel<0>, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+    else if (mode == 1) JPB_LAUNCH(v3::photometric_fwd_kernel<1>, grid, dim3(256), smem, (cudaStream_t)stream, *a);
+    else JPB_LAUNCH(v3::photometric_fwd_kernel<2>, grid, dim3(256), smem, (cudaStream_t)stream, *a);
     return jpb_status();
   }
+  if (a->ident_mode) return JPB_ERR_UNSUPPORTED;   // the shared identity terms exist in the packed schedule only
   if (a->F <= 2) {   // fast path: 32x32 tiles, separable window sums (every reference configuration: F <= 2)
     const size_t smem = (size_t)(3 + 3 * a->F) * Q1_N * sizeof(float);
     dim3 grid((a->W + QT_W - 1) / QT_W, (a->H + QT_H - 1) / QT_H, a->B);
@@ -942,6 +1267,22 @@ extern "C" int jpb_photometric_fwd(const JpbPhotoArgs* a, void* stream) {
 extern "C" int jpb_photometric_bwd(const JpbPhotoArgs* a, const JpbPhotoGrad* g, void* stream) {
   if (!a || !g || a->F < 1 || a->F > JPB_MAX_SRC || !g->winner || !g->grad_disp || !g->grad_out) return JPB_ERR_ARG;
   if (a->hs > a->H || a->ws > a->W) return JPB_ERR_UNSUPPORTED;  // footprint buffer assumes up-sampling
+  if (a->F <= 2 && g_bwd_variant == 4 && (long long)a->H * a->W * 3 < (1ll << 31)) {   // register-resident schedule (default)
+    const size_t smem4 = (size_t)v4::SMEM_FLOATS * sizeof(float);
+    dim3 grid4((a->W + v4::TW - 1) / v4::TW, (a->H + v4::TH - 1) / v4::TH, a->B);
+#ifndef JPB_HOST_EMU
+    static bool configured4 = false;
+    if (!configured4) {
+      if (cudaFuncSetAttribute(v4::photometric_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess ||
+          cudaFuncSetAttribute(v4::photometric_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess)
+        return JPB_ERR_UNSUPPORTED;
+      configured4 = true;
+    }
+#endif
+    if (a->F == 1) JPB_LAUNCH(v4::photometric_bwd_kernel<1>, grid4, dim3(256), smem4, (cudaStream_t)stream, *a, *g);
+    else JPB_LAUNCH(v4::photometric_bwd_kernel<2>, grid4, dim3(256), smem4, (cudaStream_t)stream, *a, *g);
+    return jpb_status();
+  }
   const size_t smem = (size_t)(3 + 3 * a->F) * P2_N * sizeof(float) + (size_t)9 * P1_N * sizeof(float) + (size_t)P1_N * sizeof(int);
   dim3 grid((a->W + PT_W - 1) / PT_W, (a->H + PT_H - 1) / PT_H, a->B);
 #ifndef JPB_HOST_EMU

@@ -16,11 +16,22 @@ from ._lib import PhotoArgs, PhotoGrad, check, ptr, stream_of
 PROFILE_ON = False
 PROFILE: dict = {}
 PROFILE_DETAIL: dict = {}     # (name, tag) -> events; tag = the caller's shape description (per-layer tables, tools/conv_layers.py)
+# An eager step is host-bound (~40 us of Python / ctypes / tensor-map encoding per launch against 5-50 us kernels): with an idle
+# GPU the first event of a pair is stamped when the host reaches it and the pair measures the host's launch latency, not the
+# kernel.  PROFILE_BACKPRESSURE > 0 queues a device spin of that many SM cycles every PROFILE_EVERY launches so that the GPU
+# always runs behind the host and each event pair brackets device time only.
+PROFILE_BACKPRESSURE = 0
+PROFILE_EVERY = 48
+_profile_count = [0]
 
 
 def _launch(name, tensor, call, tag=None):
     """Run one C-ABI launch; when profiling, bracket it with CUDA events on the tensor's current stream."""
     if PROFILE_ON and tensor.is_cuda:
+        if PROFILE_BACKPRESSURE:
+            if _profile_count[0] % PROFILE_EVERY == 0:
+                torch.cuda._sleep(int(PROFILE_BACKPRESSURE))
+            _profile_count[0] += 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         status = call()
@@ -103,6 +114,17 @@ class _Photometric(torch.autograd.Function):
                 w = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
                 warped.append(w)
                 a.warped[i] = ptr(w)
+        cache = cfg.get("ident_cache")
+        if cache is not None and cfg["automask"] and F <= 2 and _lib.photo_fwd_variant() == 3:
+            # the identity candidates do not depend on the scale (net.py:159-166): the first launch of a step stores their
+            # un-noised errors, the other scales' launches read them instead of evaluating two more SSIM candidates
+            key = (target.data_ptr(), tuple(s.data_ptr() for s in sources), B, H, W)
+            if cache.get("key") == key and cache.get("err") is not None:
+                a.ident_err, a.ident_mode = ptr(cache["err"]), 2
+            else:
+                cache["err"] = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev)
+                cache["key"] = key
+                a.ident_err, a.ident_mode = ptr(cache["err"]), 1
         check(_launch("photometric_fwd", target, lambda: _lib.lib().jpb_photometric_fwd(C.byref(a), stream_of(target))),
               "jpb_photometric_fwd")
         loss = finalize(acc, 1.0 / (B * H * W * cfg["num_scales"])).reshape(())
@@ -148,15 +170,17 @@ KEEP_WARPED = os.environ.get("JPB_PHOTO_KEEP_WARPED", "1") not in ("", "0")
 
 def photometric_loss(disp, target, sources, Ts, K, invK, *, num_scales=4, automask=True, min_depth=0.1,
                      max_depth=100.0, noise=None, noise_scale=1e-5, seed=0, stream=0, step=None, debug_outputs=False,
-                     keep_warped=None):
+                     keep_warped=None, ident_cache=None):
     """``loss_dict[("min_reconstruct_loss", s)]`` of one scale (already divided by ``num_scales``).
 
     Returns ``(loss, winner_u8, min_index|None, [warped...])``.  ``noise``: list of B×H×W tensors for the
-    identity terms (tests) or None for the in-kernel Philox draw scaled by ``noise_scale``.
+    identity terms (tests) or None for the in-kernel Philox draw scaled by ``noise_scale``.  ``ident_cache``: a dict shared by
+    the per-scale calls of ONE step over the same target / sources — the first call stores the (scale-independent) identity
+    errors in it, the others read them (``JpbPhotoArgs.ident_mode``).
     """
     cfg = dict(F=len(sources), num_scales=num_scales, automask=automask, min_depth=min_depth, max_depth=max_depth,
                noise_scale=noise_scale, seed=seed, stream=stream, step=step, debug_outputs=debug_outputs,
-               keep_warped=KEEP_WARPED if keep_warped is None else bool(keep_warped))
+               keep_warped=KEEP_WARPED if keep_warped is None else bool(keep_warped), ident_cache=ident_cache)
     rest = list(sources) + list(Ts) + (list(noise) if noise is not None else [])
     out = _Photometric.apply(disp, K, invK, target, cfg, *rest)
     loss, winner = out[0], out[1]

@@ -353,13 +353,15 @@ class Baseline(nn.Module):
         sources = [inputs[("color", f, 0)] for f in fids]
         poses = [outputs[("cam_T_cam", 0, f)] for f in fids]
         pyramid = JF.area_pyramid(target, max(scales) + 1)
+        ident_cache = {}      # identity-candidate errors: computed by the first scale's launch, read by the others
         for s in scales:
             disp = outputs[("disp", 0, s)]
             noise = self.noise_override[s] if self.noise_override is not None else None
             loss, winner, min_index, warped = JF.photometric_loss(
                 disp, target, sources, poses, inputs[("K", 0)], inputs[("inv_K", 0)], num_scales=nsc, automask=o.automask,
                 min_depth=o.min_depth, max_depth=o.max_depth, noise=noise, noise_scale=self.noise_scale,
-                seed=int(o.get("seed", 1024)), stream=4 * s, step=self.step_counter, debug_outputs=self.debug_outputs)
+                seed=int(o.get("seed", 1024)), stream=4 * s, step=self.step_counter, debug_outputs=self.debug_outputs,
+                ident_cache=ident_cache)
             L[("min_reconstruct_loss", s)] = loss
             if self.debug_outputs:
                 lo, hi = 1.0 / o.max_depth, 1.0 / o.min_depth

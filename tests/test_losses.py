@@ -147,6 +147,65 @@ def test_photometric_variants_agree(dev):
     assert _lib.lib().jpb_photometric_set_variant(7) != 0        # unknown schedule: argument error, nothing changes
 
 
+@pytest.mark.parametrize("s,H,W,F,keep", [(0, 24, 40, 2, False), (1, 36, 72, 2, True), (3, 64, 96, 2, True), (2, 48, 80, 1, False), (0, 17, 33, 2, True)])
+def test_photometric_backward_schedules_agree(dev, s, H, W, F, keep):
+    """jpb_photometric_set_bwd_variant: the register-resident kernel (4, default for F <= 2) against the generic one (1) — disparity
+    and pose gradients equal within fp32 summation order, with re-projected and with kept warped frames, at every scale's
+    up-sampling factor (the separable transposed up-sampling replaces the shared-memory atomics of schedule 1)."""
+    target, sources, disp, K, invK, Ts = _photo_case(B=2, H=H, W=W, s=s, F=F, seed=5)
+    grads = {}
+    try:
+        for v in (1, 4):
+            _lib.check(_lib.lib().jpb_photometric_set_bwd_variant(v), "jpb_photometric_set_bwd_variant")
+            d = D(disp.clone(), dev).requires_grad_(True)
+            T = [D(t.clone(), dev).requires_grad_(True) for t in Ts]
+            loss = JF.photometric_loss(d, D(target, dev), D(sources, dev), T, D(K, dev), D(invK, dev), num_scales=4, noise_scale=0.0,
+                                       keep_warped=keep)[0]
+            loss.backward()
+            grads[v] = (d.grad.cpu(), [t.grad.cpu() for t in T])
+    finally:
+        _lib.check(_lib.lib().jpb_photometric_set_bwd_variant(4), "jpb_photometric_set_bwd_variant")
+    scale = grads[1][0].abs().max().item()
+    # same formulas, different FMA contraction of the cancelling window statistics on the GPU: 1e-4 of the largest entry
+    assert scale > 0 and (grads[1][0] - grads[4][0]).abs().max().item() <= 1e-4 * scale
+    for a, b in zip(grads[1][1], grads[4][1]):
+        assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item() + 1e-12
+    assert _lib.lib().jpb_photometric_set_bwd_variant(3) != 0      # unknown schedule: argument error
+
+
+@pytest.mark.parametrize("F,explicit_noise", [(2, True), (1, False)])
+def test_photometric_identity_terms_shared_across_scales(dev, F, explicit_noise):
+    """JpbPhotoArgs.ident_mode: the identity candidates (target vs un-warped sources, net.py:159-166) do not depend on the
+    scale, so the first launch of a step stores their errors and the other scales' launches read them.  Every scale's loss,
+    arg-min and gradients equal those of the launches that evaluate the identity terms themselves."""
+    H, W = 48, 80
+    target, sources, _, K, invK, Ts = _photo_case(B=2, H=H, W=W, s=0, F=F, seed=9)
+    g = torch.Generator().manual_seed(3)
+    disps = [0.05 + 0.9 * torch.rand(2, 1, H >> (s + 1), W >> (s + 1), generator=g) for s in range(4)]
+    noises = [[1e-5 * torch.randn(2, H, W, generator=g) for _ in sources] for _ in range(4)] if explicit_noise else [None] * 4
+    _lib.check(_lib.lib().jpb_photometric_set_variant(3), "jpb_photometric_set_variant")
+    try:
+        res = {}
+        for shared in (False, True):
+            cache = {} if shared else None
+            out = []
+            for s in range(4):
+                d = D(disps[s].clone(), dev).requires_grad_(True)
+                loss, winner, idx, _ = JF.photometric_loss(d, D(target, dev), D(sources, dev), D(Ts, dev), D(K, dev), D(invK, dev), num_scales=4,
+                                                           noise=D(noises[s], dev) if noises[s] is not None else None, noise_scale=0.0,
+                                                           debug_outputs=True, ident_cache=cache)
+                loss.backward()
+                out.append((loss.item(), idx.cpu(), d.grad.cpu()))
+            res[shared] = out
+            if shared:
+                assert cache["err"].shape == (2, H, W, 2)
+    finally:
+        _lib.check(_lib.lib().jpb_photometric_set_variant(3), "jpb_photometric_set_variant")     # the library default
+    for (l0, i0, g0), (l1, i1, g1) in zip(res[False], res[True]):
+        assert l0 == l1 and (i0 != i1).sum().item() == 0
+        assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()      # fp32 atomics: arrival order
+
+
 def test_area_pyramid_and_smoothness_kat4(dev):
     kat = np.load(os.path.join(GOLDEN, "kat.npz"))
     img = pat((1, 3, 8, 12), 2)
@@ -313,6 +372,45 @@ def test_photometric_full_size_vs_oracle_and_properties():
     lb = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=7, stream=1)[0].item()
     lc = JF.photometric_loss(disps[0], target, sources, Ts, K, invK, seed=8, stream=1)[0].item()
     assert la == lb and abs(la - loss.item()) < 1e-4 and abs(lc - loss.item()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_photometric_backward_schedules_agree_full_size(s):
+    """BASELINE frame size (320x1024, F=2), every scale, with the warped frames the forward kept (the drop-in default): both
+    backward schedules against the oracle's autograd evaluated in float64.  The window statistics cancel (variance = E[x^2] -
+    E[x]^2 of smooth frames), so two fp32 evaluations with different FMA contraction differ by ~1e-3 of the largest gradient and
+    the fp32 oracle itself is 2e-2 away from the float64 one (arg-min flips at ties); the default schedule has to be as close to
+    float64 as the generic one, in the L2 norm, and the two have to agree entry-wise within that fp32 noise."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bench_photometric import make_case
+    _lib._handle, _lib._emulated = None, False
+    dev = torch.device("cuda:0")
+    target, sources, disps, K, invK, Ts = make_case(2, 320, 1024, 2, dev)
+    dd = torch.float64
+    d64 = disps[s].detach().cpu().to(dd).requires_grad_(True)
+    T64 = [t.detach().cpu().to(dd).requires_grad_(True) for t in Ts]
+    m, _, _ = O.photometric_scale(d64, target.cpu().to(dd), [x.cpu().to(dd) for x in sources], T64, K.cpu().to(dd), invK.cpu().to(dd),
+                                  automask=True, noise=None)
+    (m / 4).backward()
+    grads = {}
+    try:
+        for v in (1, 4):
+            _lib.check(_lib.lib().jpb_photometric_set_bwd_variant(v), "jpb_photometric_set_bwd_variant")
+            d = disps[s].detach().clone().requires_grad_(True)
+            T = [t.detach().clone().requires_grad_(True) for t in Ts]
+            JF.photometric_loss(d, target, sources, T, K, invK, num_scales=4, noise_scale=0.0, debug_outputs=True)[0].backward()
+            grads[v] = (d.grad.cpu().to(dd), [t.grad.cpu().to(dd) for t in T])
+    finally:
+        _lib.check(_lib.lib().jpb_photometric_set_bwd_variant(4), "jpb_photometric_set_bwd_variant")
+    ref = d64.grad
+    e1 = ((grads[1][0] - ref).norm() / ref.norm()).item()
+    e4 = ((grads[4][0] - ref).norm() / ref.norm()).item()
+    assert e4 <= max(1.25 * e1, 2e-3), (e1, e4)
+    assert e4 < 5e-2, (e1, e4)
+    assert (grads[1][0] - grads[4][0]).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    for a, b, r in zip(grads[1][1], grads[4][1], T64):
+        assert (b - r.grad).abs().max().item() <= max(1.25 * (a - r.grad).abs().max().item(), 2e-3 * r.grad.abs().max().item())
 
 
 @pytest.mark.parametrize("k,s,p,H,W,C", [(5, 1, 2, 12, 20, 8), (3, 2, 1, 16, 24, 16), (2, 2, 0, 8, 8, 128), (3, 2, 1, 15, 21, 4)])

@@ -28,9 +28,11 @@ def test_photometric_backward_from_kept_warped_frames(dev, s, H, W, automask):
     (l0, gd0, gT0), (l1, gd1, gT1) = grads
     assert abs(l0 - l1) <= 1e-6 * abs(l0)
     scale = gd0.abs().max().item()
-    assert scale > 0 and (gd0 - gd1).abs().max().item() <= 1e-5 * scale   # fp32 atomics: arrival order
+    # fp32 atomics' arrival order, and on the GPU the forward's fast reciprocal in the kept frames vs the exact division of the
+    # re-projection: 1e-4 of the largest entry
+    assert scale > 0 and (gd0 - gd1).abs().max().item() <= 1e-4 * scale
     for a, b in zip(gT0, gT1):
-        assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12)
+        assert (a - b).abs().max().item() <= 1e-4 * max(a.abs().max().item(), 1e-12)
     # and against the oracle's autograd
     d0 = disp.detach().clone().requires_grad_(True)
     T0 = [t.detach().clone().requires_grad_(True) for t in Ts]

@@ -36,6 +36,7 @@ for _ in range(3):
     engine.step(data, need_log=False)
 torch.cuda.synchronize()
 JF.PROFILE.clear(); JF.PROFILE_DETAIL.clear(); JF.PROFILE_ON = True
+JF.PROFILE_BACKPRESSURE = 16_000_000   # keep the GPU behind the host: event pairs bracket device time (see functional.py)
 steps = 2
 for _ in range(steps):
     engine.step(data, need_log=False)
