@@ -240,6 +240,67 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar_saddr) {
       " @pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
       "}" ::"r"(bar_saddr) : "memory");
 }
+// ---- CTA pairs (tcgen05 cta_group::2): two CTAs of a 2-cluster on the two SMs of a TPC compute one 256-row tile; each holds its
+// 128 rows of A, HALF of the B tile and its 128 lanes of the accumulator.  The leader (cluster rank 0) issues the MMAs for both.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster (one elected lane of a converged warp)
+__device__ __forceinline__ void mbar_arrive_remote_elect(uint32_t bar_saddr, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      " .reg .pred pe;\n"
+      " .reg .b32 ra;\n"
+      " elect.sync _|pe, 0xffffffff;\n"
+      " mapa.shared::cluster.u32 ra, %0, %1;\n"
+      " @pe mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}" ::"r"(bar_saddr), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAITC_%=:\n"
+      " mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONEC_%=;\n"
+      " bra WAITC_%=;\n"
+      "DONEC_%=:\n"
+      "}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_k4_cg2(uint32_t tacc, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                                 uint32_t acc_first) {
+  asm volatile(
+      "{\n"
+      " .reg .pred pe, pa, pt;\n"
+      " .reg .b64 da, db;\n"
+      " .reg .b32 al, bl;\n"
+      " elect.sync _|pe, 0xffffffff;\n"
+      " setp.ne.b32 pa, %6, 0;\n"
+      " setp.eq.b32 pt, %6, %6;\n"
+      " mov.b64 da, {%1, %3};\n"
+      " mov.b64 db, {%2, %4};\n"
+      " @pe tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, pa;\n"
+      " add.u32 al, %1, 2;\n add.u32 bl, %2, 2;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, pt;\n"
+      " add.u32 al, %1, 4;\n add.u32 bl, %2, 4;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, pt;\n"
+      " add.u32 al, %1, 6;\n add.u32 bl, %2, 6;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %4};\n"
+      " @pe tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, pt;\n"
+      "}" ::"r"(tacc), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar_saddr) {
+  asm volatile(
+      "{\n"
+      " .reg .pred pe;\n"
+      " .reg .b16 m;\n"
+      " mov.b16 m, 3;\n"
+      " elect.sync _|pe, 0xffffffff;\n"
+      " @pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}" ::"r"(bar_saddr) : "memory");
+}
 constexpr uint32_t DESC_HI_SW128(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }   // bits [32,64) of the descriptor
 constexpr uint32_t DESC_LO_LBO1 = 1u << 16;
 
@@ -314,17 +375,24 @@ __device__ __forceinline__ void sts_row(uint32_t rowtab, int lane, unsigned long
 }
 
 // NT: N tile (UMMA N), multiple of 16 in [16,256].  STAGES: smem pipeline depth.
-template <int NT, int STAGES, int MINB>
+// CG = 2: CTA-pair version (launched as 2-clusters along blockIdx.x).  CTA x owns output rows [128 x, 128 x + 128) exactly as in
+// the single-CTA version — gather, epilogue and accumulator lanes are unchanged — but loads only rows [rank * NT/2, +NT/2) of
+// the weight tile: the pair's tcgen05.mma.cta_group::2 (M = 256) reads both halves, so the weight stream per output row — two
+// thirds of the L2 -> SM traffic that bounds the wide layers (tools/microbench/mma_pipeline.cu, profiles/README.md) — is halved.
+// The peer's MMA warp forwards "my stage is full" to the leader's pfull barrier; the leader's commits arrive in both CTAs.
+template <int NT, int STAGES, int MINB, int CG = 1>
 __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap wmap, JpbConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [STAGES][A 16KB][B NT*128] | barriers | tmem ptr | src table
-  constexpr int B_STAGE = NT * BK * 4;
+  // carve: [STAGES][A 16KB][B (NT/CG)*128] | barriers | tmem ptr | src table
+  constexpr int B_STAGE = (NT / CG) * BK * 4;
   constexpr int STAGE = A_STAGE + B_STAGE;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* pfull_bar = accum_bar + 1;                     // CG == 2, leader: the peer's stage s is full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + (CG == 2 ? STAGES : 0));
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
   SrcDev* srcs = reinterpret_cast<SrcDev*>(tmem_slot + 2);
   int* s_off = reinterpret_cast<int*>(srcs + JPB_CONV_MAX_SRC);
   const uint32_t srcs_u32 = smem_u32(srcs), soff_u32 = smem_u32(s_off);
@@ -352,7 +420,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   if (nkb < 0) nkb = 0;
   const bool split = gridDim.z > 1;
   // rotated K loop (see the persistent kernel): CTAs of one N column must not all stream the same weight tile at once
-  const int rot = nkb > 1 ? (int)((((uint32_t)blockIdx.x * 0x9E3779B1u) >> 12) % (uint32_t)nkb) : 0;
+  const int rot = nkb > 1 ? (int)(((((uint32_t)blockIdx.x / (uint32_t)CG) * 0x9E3779B1u) >> 12) % (uint32_t)nkb) : 0;   // same for a pair
 #define JPB_KROT(kb) ((kb) + rot >= nkb ? (kb) + rot - nkb : (kb) + rot)
 
   if (tid < a.nsrc) {
@@ -362,15 +430,23 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   if (tid == 160) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
+    if (CG == 2)
+      for (int s = 0; s < STAGES; ++s) mbar_init(&pfull_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {   // TMEM allocation (power of two >= 32 columns), owned by warp 4
+  if (warp == 4) {   // TMEM allocation (power of two >= 32 columns), owned by warp 4 (of each CTA of a pair)
     constexpr uint32_t cols = NT < 32 ? 32 : NT;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   JPB_STAMP(1);
@@ -602,36 +678,53 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         if (a.dbg_skip & 2) { mbar_arrive(&full_bar[s]); continue; }   // timing experiment: no B traffic
         mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
         const int kr = kb0 + JPB_KROT(kb);
-        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kr] : kr * BK, n0);
+        tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kr] : kr * BK, n0 + (int)crank * (NT / CG));
       }
+    }
+  } else if (CG == 2 && crank != 0) {
+    // ===================================================== pair, peer CTA: tell the leader when this CTA's stage is full
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full_bar[s], (uint32_t)(kb / STAGES) & 1u);
+      mbar_arrive_remote_elect(smem_u32(&pfull_bar[s]), 0u);
     }
   } else {
     // ===================================================== MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
     // both K-major, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
+      if (CG == 2) mbar_wait_cluster(&pfull_bar[s], ph);
       tc_fence_after();
       if (kb == 0) JPB_STAMP(3);
       {   // converged warp, one elected lane issues (see umma_tf32_k4): 8 TF32 (32 bytes) per instruction, start address + 2 x 16 B each
         const uint32_t sa = smem_u32(smem + s * STAGE);
-        umma_tf32_k4(tmem_base, ((sa >> 4) & 0x3FFFu) | DESC_LO_LBO1, (((sa + A_STAGE) >> 4) & 0x3FFFu) | DESC_LO_LBO1, DESC_HI_SW128(1024),
-                     DESC_HI_SW128(1024), idesc, kb ? 1u : 0u, 1u);
-        umma_commit_elect(smem_u32(&empty_bar[s]));
-        if (kb == nkb - 1) umma_commit_elect(smem_u32(accum_bar));
+        if (CG == 2) {
+          umma_tf32_k4_cg2(tmem_base, ((sa >> 4) & 0x3FFFu) | DESC_LO_LBO1, (((sa + A_STAGE) >> 4) & 0x3FFFu) | DESC_LO_LBO1, DESC_HI_SW128(1024),
+                           DESC_HI_SW128(1024), idesc, kb ? 1u : 0u);
+          umma_commit_pair_elect(smem_u32(&empty_bar[s]));
+          if (kb == nkb - 1) umma_commit_pair_elect(smem_u32(accum_bar));
+        } else {
+          umma_tf32_k4(tmem_base, ((sa >> 4) & 0x3FFFu) | DESC_LO_LBO1, (((sa + A_STAGE) >> 4) & 0x3FFFu) | DESC_LO_LBO1, DESC_HI_SW128(1024),
+                       DESC_HI_SW128(1024), idesc, kb ? 1u : 0u, 1u);
+          umma_commit_elect(smem_u32(&empty_bar[s]));
+          if (kb == nkb - 1) umma_commit_elect(smem_u32(accum_bar));
+        }
       }
     }
     JPB_STAMP(4);
   }
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // both CTAs are done with each other's shared memory and tensor memory
   JPB_STAMP(6);
   if (warp == 4) {
     tc_fence_after();
     constexpr uint32_t cols = NT < 32 ? 32 : NT;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
   }
 #undef JPB_STAMP
 #undef JPB_KROT
@@ -1460,6 +1553,43 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
 }
 
 
+// CTA-pair launch: 2-clusters along the M tiles (an odd tile count gets one idle partner: rows >= M gather zeros, store nothing)
+template <int NT, int STAGES, int MINB>
+int launch_fwd_pair(const JpbConvArgs* a, const CUtensorMap& half_map, cudaStream_t st) {
+  const int smem = STAGES * (A_STAGE + (NT / 2) * BK * 4) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+  static int configured = 0;
+  if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES, MINB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    configured = smem;
+  }
+  const int M = a->B * a->Ho * a->Wo;
+  const int mt = (M + BM - 1) / BM;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((mt + 1) & ~1, (a->N + NT - 1) / NT, a->ksplit > 1 ? a->ksplit : 1);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, conv_tc_fwd_kernel<NT, STAGES, MINB, 2>, half_map, *a) != cudaSuccess) return jpb_status() ? jpb_status() : JPB_ERR_UNSUPPORTED;
+  return jpb_status();
+}
+
+// JPB_CONV_PAIR=1 (two pairs per TPC, 3 stages) / 2 (one pair, 4 stages) switches the CTA-pair schedule of the 256-wide tiles on.
+// OFF by default — measured on B200 (tools/gpu_r2r.sh, profiles/r2_conv_pair_ab.txt): parity-exact, but not faster (iconv1 forward
+// 556 -> 590 us, merge1 266 -> 278 us; one pair per TPC: 789 / 400 us), i.e. the weight stream it halves is not what bounds these
+// layers (the same conclusion as removing the weight TMA altogether, profiles/README.md), and the full multi-stream step did not
+// finish with it (bench.py ran into its time limit) — kept as a tested schedule for single-stream use and as the starting point of
+// a persistent 2-CTA kernel.
+int conv_pair() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JPB_CONV_PAIR"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <int NT, int TR, int PSTAGES, int BSTAGES>
 int launch_patch(const JpbConvArgs* a, const CUtensorMap& xmap, const CUtensorMap& wmap, cudaStream_t st) {
   constexpr int smem = PSTAGES * (16 * TR + 3) * PATCH_PX * 128 + BSTAGES * NT * BK * 4 + 4 * EPI_WARP_FLOATS * 4 + 1024 + 256;
@@ -1580,7 +1710,17 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
       case 32: return launch_fwd2<32, 4, 2>(a, map, st);
       case 64: return nts <= 27 ? launch_fwd2<64, 3, 2>(a, map, st) : launch_fwd2<64, 4, 1>(a, map, st);
       case 128: return (nts <= 27 && tiles > 148) ? launch_fwd<128, 3, 2>(a, map, st) : launch_fwd<128, 5, 1>(a, map, st);
-      default: return (nts <= 27 && tiles > 148) ? launch_fwd<256, 2, 2>(a, map, st) : launch_fwd<256, 4, 1>(a, map, st);
+      default:
+        if (conv_pair() && nts <= 27 && tiles > 148) {
+          // CTA pairs: each CTA streams half of the weight tile (box of 128 rows), three stages, two pairs per TPC
+          CUtensorMap hmap;
+          const cuuint32_t hbox[2] = {(cuuint32_t)BK, 128u};
+          if (enc(&hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->weight), gdim, gstr, hbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return JPB_ERR_ARG;
+          return conv_pair() == 2 ? launch_fwd_pair<256, 4, 1>(a, hmap, st) : launch_fwd_pair<256, 3, 2>(a, hmap, st);
+        }
+        return (nts <= 27 && tiles > 148) ? launch_fwd<256, 2, 2>(a, map, st) : launch_fwd<256, 4, 1>(a, map, st);
     }
   }
   if (var >= 3) {   // persistent kernel

@@ -31,12 +31,23 @@ CASES = [
     ("persistent stem: 7x7 s2 (3->pad4)->64, 512 tiles", 2, [(4, 256, 512, 0)], 64, 7, 2, 3, 0, "none", 0),
     ("wide tiles, 2 CTAs/SM: refl 3x3 256->256 leaky, 320 tiles", 2, [(256, 80, 256, 0)], 256, 3, 1, 1, 1, "leaky", 1),
     ("N=128, 2 CTAs/SM: 3x3 128->128, 512 tiles", 4, [(128, 128, 128, 0)], 128, 3, 1, 1, 0, "none", 0),
+    # CTA pairs (tcgen05 cta_group::2, 256-wide tiles with more than 148 tiles): odd tile count (one idle partner), a ragged N
+    # tile whose second half is partly outside the weight, and the three-source gather of the depth decoder's iconv layers
+    ("CTA pairs, odd tile count: refl 3x3 64->256, 157 tiles", 2, [(64, 100, 100, 0)], 256, 3, 1, 1, 1, "none", 0),
+    ("CTA pairs, N=192: 3x3 64->192 relu, 157 tiles", 2, [(64, 100, 100, 0)], 192, 3, 1, 1, 0, "relu", 1),
+    ("CTA pairs, concat: refl 3x3 cat(128, up(128), 1)->256 leaky, 160 tiles", 4, [(128, 40, 128, 0), (128, 20, 64, 1), (1, 40, 128, 0)], 256, 3, 1, 1, 1,
+     "leaky", 1),
+    ("CTA pairs, 1x1 256->256, 160 tiles", 4, [(256, 40, 128, 0)], 256, 1, 1, 0, 0, "none", 1),
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_forward_many_tiles_per_cta(case):
     name, B, srcs, cout, k, stride, pad, reflect, act, has_bias = case
+    if name.startswith("CTA pairs") and os.environ.get("JPB_CONV_PAIR", "0") in ("", "0"):
+        # the opt-in cta_group::2 schedule (csrc/conv_tc.cu: conv_pair): run with JPB_CONV_PAIR=1; without it the same cases
+        # exercise the default wide-tile kernel at these extents
+        pass
     _lib._handle, _lib._emulated = None, False
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(len(name))
