@@ -238,6 +238,14 @@ typedef struct JpbConvWgradArgs {
   float acc_scale;           /* as JpbConvArgs.acc_scale */
   int dy_pitch;              /* floats between consecutive pixels of dy; 0 = N (dense).  The 3xTF32 mode passes the hi or lo
                                 half of a split gradient tensor (jpb_tf32_split): pitch = 2 * N */
+  int rows;                  /* != 0: the im2col^T operand arrives by TMA (stride 1, Ho x Wo == Hin x Win, Wo % 32 == 0, no up-sampled
+                                source): every group of 8 table rows with gflags != 0 is ONE (source, tap, 32-channel block) and is
+                                read as a {32 channels, 32 pixels} box of the source; other groups are gathered.  2 = one deep CTA
+                                per SM for the 256-wide tiles (default: two shallow ones)                                        */
+  const unsigned char* gflags; /* rows != 0: [nchunks / 8] 1 = regular group                                                      */
+  int dz3;                   /* set by the library (ignored on input): dZ is fetched as one 3-D box per step              */
+  const int* chunk_col;      /* rows != 0: [nchunks] column of dw that the first K position of each table row accumulates into,
+                                -1 for padding rows (the table order is then free)                                              */
 } JpbConvWgradArgs;
 int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
 
@@ -260,6 +268,12 @@ int jpb_tf32_split(const float* x, float* out, long long rows, int C, void* stre
  * x3 [B,H/2,W/2+1,8*Cp], channel ((dy*4 + dx)*Cp + c) of position (oy, p) = x[b, 2*oy+dy, 2*(p-1)+dx, c] (dy < 2, dx < 4, zero
  * outside the image).                                                                                                        */
 int jpb_stem_s2d(const float* x, float* x3, int B, int H, int W, int Cp, void* stream);
+
+/* ---- nearest 2x up-sampling, NHWC: x [B,H,W,C] (C % 4 == 0) -> y [B,2H,2W,C]  (layers.py:16-19) */
+int jpb_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);
+
+/* ---- zero-padded channel copy: x [rows][C] -> y [rows][Cp], Cp % 4 == 0, Cp >= C */
+int jpb_pad_channels(const float* x, float* y, long long rows, int C, int Cp, void* stream);
 
 /* ---- backward of the convolution epilogue: dz = dy * act'(y) (act as in JpbConvArgs, from the OUTPUT y) and
  * dbias[c] += sum over rows of dz.  dz may be NULL (bias gradient only), dbias may be NULL.                  */

@@ -93,6 +93,7 @@ class ConvWgradArgs(C.Structure):
         ("stride", C.c_int), ("pad", C.c_int), ("reflect", C.c_int), ("table", C.c_void_p), ("nchunks", C.c_int),
         ("dy", C.c_void_p), ("dw", C.c_void_p), ("w_row", C.c_longlong), ("w_cols", C.c_int), ("splits", C.c_int),
         ("dbg", C.c_void_p), ("accumulate", C.c_int), ("acc_scale", C.c_float), ("dy_pitch", C.c_int),
+        ("rows", C.c_int), ("gflags", C.c_void_p), ("dz3", C.c_int), ("chunk_col", C.c_void_p),
     ]
 
 
@@ -179,6 +180,8 @@ class _Signatures:
     jpb_bias_act = [P, P, P, C.c_longlong, I, I, V]
     jpb_tf32_split = [P, P, C.c_longlong, I, V]
     jpb_stem_s2d = [P, P, I, I, I, I, V]
+    jpb_upsample2x = [P, P, I, I, I, I, V]
+    jpb_pad_channels = [P, P, C.c_longlong, I, I, V]
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]

@@ -386,6 +386,79 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     return grads
 
 
+WGRAD_ROWS = int(_os.environ.get("JPB_WGRAD_ROWS", "1"))     # 0: always the gathered operand (A/B measurements); 2: deep CTAs for N tile 256
+_ROW_TABLES: dict = {}
+
+
+def upsample2x(x):
+    """Nearest 2x up-sampling of a channels-last map (csrc/elementwise.cu: upsample2x_kernel)."""
+    x = _cl(x)
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=CL)
+    check(_launch("upsample2x", x, lambda: _lib.lib().jpb_upsample2x(ptr(x), ptr(y), B, H, W, Cc, stream_of(x))), "jpb_upsample2x")
+    return y
+
+
+def pad_channels(x, Cp):
+    """Zero-padded channel copy of a channels-last map (csrc/elementwise.cu: pad_channels_kernel)."""
+    x = _cl(x)
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cp, H, W), dtype=torch.float32, device=x.device, memory_format=CL)
+    check(_launch("pad_channels", x, lambda: _lib.lib().jpb_pad_channels(ptr(x), ptr(y), B * H * W, Cc, Cp, stream_of(x))), "jpb_pad_channels")
+    return y
+
+
+def _wgrad_rows_ok(src_C, ups, kh, kw, stride, pad, Hin, Win, Ho, Wo, reflect):
+    return (WGRAD_ROWS and PRECISION == "tf32" and stride == 1 and kh == kw and kh in (1, 3) and pad == (kh - 1) // 2 and Ho == Hin and Wo == Win
+            and Wo % 32 == 0 and (not reflect or Win >= 64) and src_C[0] % 32 == 0
+            and all(c % 32 == 0 or (c < 32 and not u) for c, u in zip(src_C, ups)))
+
+
+def row_table(src_C, kh, kw, device, tma_C=None):
+    """(table, gflags, chunk_col) of the TMA-row weight gradient: first one group of 8 table rows per (tap, source with C % 32 == 0,
+    32-channel block) — read as one tensor box —, then the 16-byte chunks of the remaining sources (gathered), in the table format
+    of ``chunk_table``.  ``chunk_col``: column of each row's first K position in the packed weight layout [kh, kw, sum(pad4(C))].
+    ``tma_C``: channels of the tensors handed to the kernel when a narrow source was zero-padded to a 32-channel block
+    (``src_C`` keeps the real counts: the padding channels have no column)."""
+    tma_C = list(tma_C) if tma_C is not None else list(src_C)
+    key = (tuple(src_C), tuple(tma_C), kh, kw, str(device))
+    r = _ROW_TABLES.get(key)
+    if r is None:
+        nsrc = len(src_C)
+        cpad = [_pad4(c) for c in src_C]
+        soff = [sum(cpad[:i]) for i in range(nsrc)]
+        ctot = sum(cpad)
+        rows, cols, flags = [], [], []
+        for ky in range(kh):
+            for kx in range(kw):
+                tap = ky * kw + kx
+                for si, c in enumerate(tma_C):
+                    if c % 32:
+                        continue
+                    for cb in range(0, c, 32):
+                        for coff in range(cb, cb + 32, 4):
+                            rows.append((si | ((tap * nsrc + si) << 8), (ky << 16) | (kx & 0xFFFF), coff, 16))
+                            cols.append(tap * ctot + soff[si] + coff if coff < cpad[si] else -1)
+                        flags.append(1)
+        for ky in range(kh):
+            for kx in range(kw):
+                tap = ky * kw + kx
+                for si, c in enumerate(tma_C):
+                    if c % 32 == 0:
+                        continue
+                    for coff in range(0, c, 4):
+                        rows.append((si | ((tap * nsrc + si) << 8), (ky << 16) | (kx & 0xFFFF), coff, min(16, (c - coff) * 4)))
+                        cols.append(tap * ctot + soff[si] + coff)
+        while len(rows) % 8:
+            rows.append((-1, 0, 0, 0))
+            cols.append(-1)
+        flags += [0] * (len(rows) // 8 - len(flags))
+        r = _ROW_TABLES[key] = (torch.tensor(rows, dtype=torch.int32, device=device).contiguous(),
+                                torch.tensor(flags, dtype=torch.uint8, device=device).contiguous(),
+                                torch.tensor(cols, dtype=torch.int32, device=device).contiguous())
+    return r
+
+
 def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None):
     """``target``: the weight's channels-last gradient view; when given (and the K layout needs no padding) the kernel adds
     into it and None is returned."""
@@ -412,6 +485,14 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None)
     a.stride, a.pad, a.reflect = stride, pad, int(reflect)
     a.table, a.nchunks = ptr(table), table.shape[0]
     a.dy, a.dw, a.w_row, a.w_cols = ptr(dz), ptr(dw), wcols, wcols
+    if dbg is None and _wgrad_rows_ok(src_C, ups, kh, kw, stride, pad, a.Hin, a.Win, Ho, Wo, reflect):
+        # TMA-row operand: dense full-resolution sources (an up-sampled source is materialised), group-major table
+        # (and a narrow one — the 1-channel disparity of the iconv layers — zero-padded to one 32-channel block: no gathered group)
+        xs_d = [upsample2x(x) if u else (pad_channels(x, 32) if x.shape[1] % 32 else _cl(x)) for x, u in zip(xs, ups)]
+        _fill_sources(a, xs_d, [False] * len(xs_d))
+        table, gflags, ccol = row_table(src_C, kh, kw, dev, [x.shape[1] for x in xs_d])
+        a.table, a.nchunks = ptr(table), table.shape[0]
+        a.rows, a.gflags, a.chunk_col = WGRAD_ROWS, ptr(gflags), ptr(ccol)
     nt = 32
     while nt < Nc and nt < 256:
         nt *= 2
@@ -522,8 +603,13 @@ class _ConvTC(torch.autograd.Function):
             table, kcol = ordered_table([_pad4(c) for c in src_C], kh, kw, dev, split3=True)
             wmat, wcols = gemm_weight3(weight.detach(), src_C, w_C)
         else:
-            table, kcol = ordered_table(src_C, kh, kw, dev)
-            wmat, wcols = gemm_weight(weight.detach(), src_C, w_C)
+            if len(xs) > 1 and any(c % 4 for c in src_C):
+                # a source with a ragged channel count (the 1-channel disparity of the iconv layers) is zero-padded to whole 16-byte
+                # chunks: its K blocks then take the asynchronous copy path instead of eight dependent scalar loads per thread
+                xs_k = [pad_channels(x, _pad4(x.shape[1])) if x.shape[1] % 4 else x for x in xs]
+            src_k = [x.shape[1] for x in xs_k]
+            table, kcol = ordered_table(src_k, kh, kw, dev)
+            wmat, wcols = gemm_weight(weight.detach(), src_k, w_C)
         nkb = table.shape[0] // 8
         ks = _ksplit(B * Ho * Wo, N, nkb)
         has_epi = bias is not None or residual is not None or act != "none"

@@ -111,6 +111,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): [0,14) start address >> 4 | [16,30) leading byte offset >> 4 |
 // [32,46) stride byte offset >> 4 | [46,48) version = 1 | [49,52) base offset (0: the swizzle follows absolute address bits) |
 // [61,64) layout (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).  Built as 32-bit halves by the issue helpers below.
@@ -1071,8 +1080,22 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
 //   M tile = 128 consecutive K positions (32 chunks of the table), N tile = NT output channels,
 //   each pipeline stage = 32 pixels = 4 tcgen05.mma (K = 8 pixels each).
 // The pixel range is split over gridDim.z CTAs; partial tiles are accumulated with red.global.add.
-template <int NT, int STAGES, int MINB>
-__global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, JpbConvWgradArgs a) {
+// ROWS (the default for stride-1 "same" convolutions whose row length is a multiple of 32): the im2col^T operand arrives by TMA.
+// A pipeline step is 32 consecutive pixels of ONE image row, so for a (source, tap, 32-channel block) — one MN group of the A
+// tile — the 32 x 32 operand block is a 4-D box {32 channels, 32 pixels, 1 row, 1 image} of the NHWC source at the tap's offset:
+// zero padding is the box's out-of-bounds fill; reflection padding mirrors the row coordinate and, at the two row ends, splits the
+// box into a 31-pixel box plus the mirrored single pixel (disjoint shared-memory destinations, same barrier).  One thread issues
+// at most 8 bulk tensor copies per step in place of 1024 16-byte cp.async gathers issued by 128 threads: measured with the
+// tensor pipe in the loop (tools/microbench/mma_tma_gather.cu, profiles/r2_mma_tma_gather.txt) the operand path then sustains
+// 650-680 cycles per K block and SM against ~1650 with the gather.  Groups that are not a whole 32-channel block of one source
+// (the 1-channel disparity of the iconv layers) keep the gather, in the CTAs that own them.
+struct WgradRowMaps {
+  CUtensorMap m[JPB_CONV_MAX_SRC][3];   // per source: boxes of 32, 31 and 1 pixels
+};
+
+template <int NT, int STAGES, int MINB, bool ROWS = false>
+__global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ WgradRowMaps xmaps,
+                                                                  JpbConvWgradArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int B_STAGE = NT * BK * 4;
   constexpr int STAGE = A_STAGE + B_STAGE;
@@ -1094,10 +1117,30 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
   if (nsteps > steps_per) nsteps = steps_per;
   if (nsteps < 0) nsteps = 0;
 
+  // ROWS: MN group g of this K tile (chunks 8g .. 8g+7 of the table) is `regular` (one TMA box per step), gathered, or dead
+  // (beyond the table: stays zero).  The classification is the same for every step of the CTA.
+  int grp_regular = 0, grp_live = 0;
+  if (ROWS) {
+    for (int g = 0; g < 4; ++g) {
+      const int gq = mt * 32 + 8 * g;
+      if (gq < a.nchunks && __ldg(a.table + (size_t)gq * 4) >= 0) {
+        grp_live |= 1 << g;
+        if (a.gflags[gq >> 3]) grp_regular |= 1 << g;
+      }
+    }
+  }
+  const bool gather_on = !ROWS || (grp_live & ~grp_regular) != 0;
   if (tid == 160) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], gather_on ? NPROD + 1 : 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (ROWS && !gather_on && grp_live != 0xF) {     // dead groups are never written: zero them once in every stage
+    for (int i = tid; i < STAGES * (A_STAGE / 16); i += 192) {
+      const int st_ = i / (A_STAGE / 16), o = i % (A_STAGE / 16);
+      if (!((grp_live >> (o / 256)) & 1)) sts128(smem_u32(smem + st_ * STAGE) + (uint32_t)o * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    fence_async_proxy();
   }
   if (warp == 4) {
     if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&dymap)) : "memory");
@@ -1114,6 +1157,8 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
   if (warp < 4) {
     // ------------------------------------------------ im2col^T gather: thread owns chunk q of the K tile, 8 pixel slots
     const int q = tid & 31, prow = tid >> 5;
+    const bool my_copy = !ROWS || !((grp_regular >> (q >> 3)) & 1);     // ROWS: regular groups arrive by TMA
+    if (gather_on) {
     const int gq = mt * 32 + q;
     int4 e = make_int4(-1, 0, 0, 0);
     if (gq < a.nchunks) e = __ldg(reinterpret_cast<const int4*>(a.table) + gq);
@@ -1147,6 +1192,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
         const int s = issued % STAGES;
         const uint32_t abase = smem_u32(smem + s * STAGE);
         for (int i = 0; i < 8; ++i) {
+          if (!my_copy) break;
           const int slot = prow + 4 * i;            // pixel slot 0..31 of this step
           // MN group (q>>3) of 4096 B = 8 K-groups of 4 pixels (512 B); row = slot&3; 32-byte chunk ((q&7)>>1) ^ row, 16-byte half q&1
           const uint32_t dst = abase + (uint32_t)((q >> 3) * 4096 + (slot >> 2) * 512 + (slot & 3) * 128 +
@@ -1179,10 +1225,15 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
         ++published;
       }
     }
+    }   // gather_on
     // ------------------------------------------------ epilogue: dW[n0 + j][k] (+)= D[k, j]
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int k = mt * 128 + warp * 32 + lane;
+    int k = mt * 128 + warp * 32 + lane;
+    if (ROWS) {      // column of K position k in dw: the chunk's column (chunk_col, -1 = padding) + the channel inside the chunk
+      const int cc = (k >> 2) < a.nchunks ? __ldg(a.chunk_col + (k >> 2)) : -1;
+      k = cc < 0 ? a.w_cols : cc + (k & 3);
+    }
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool use_atomic = gridDim.z > 1 || a.accumulate;
     for (int j = 0; j < NT; j += 16) {
@@ -1200,15 +1251,67 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_c
     }
     tc_fence_before();
   } else if (warp == 4) {
-    if (lane == 0) {
-      for (int st = 0; st < nsteps; ++st) {
-        const int s = st % STAGES;
-        const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
-        const int p0 = (step0 + st) * 32;
-        for (int h = 0; h < NT / 32; ++h)     // one {32 channels x 32 pixels} box per MN group: lands as 8 atoms of 4 pixels
-          tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE + h * 4096), &dymap, &full_bar[s], n0 + 32 * h, p0);
+    if (!ROWS) {
+      if (lane == 0) {
+        for (int st = 0; st < nsteps; ++st) {
+          const int s = st % STAGES;
+          const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)B_STAGE);
+          const int p0 = (step0 + st) * 32;
+          for (int h = 0; h < NT / 32; ++h)     // one {32 channels x 32 pixels} box per MN group: lands as 8 atoms of 4 pixels
+            tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE + h * 4096), &dymap, &full_bar[s], n0 + 32 * h, p0);
+        }
+      }
+    } else {
+      // ROWS: lane g < 4 issues the box(es) of MN group g, lane 4 the dZ tile — as ONE 3-D box {32 channels, 32 pixels, NT/32
+      // channel blocks} when N % 32 == 0 (a.dz3), which lands block-major exactly like NT/32 separate boxes.  A single thread
+      // issuing 12 copies per step (with their address arithmetic) was itself the bottleneck of the first version.
+      const int g = lane;
+      const bool mine = g < 4 && ((grp_regular >> g) & 1);
+      int si = 0, dy = 0, dx = 0, coff = 0;
+      if (mine) {
+        const int4 e = __ldg(reinterpret_cast<const int4*>(a.table) + (mt * 32 + 8 * g));
+        si = e.x & 0xff; dy = e.y >> 16; dx = (int)(short)(e.y & 0xffff); coff = e.z;
+      }
+      const CUtensorMap* m32 = &xmaps.m[si][0];
+      const CUtensorMap* m31 = &xmaps.m[si][1];
+      const CUtensorMap* m1 = &xmaps.m[si][2];
+      const int nreg = __popc(grp_regular);
+      // this step's pixels: row `ry` of image `rb`, pixels rx .. rx + 31 (Wo % 32 == 0: a step never leaves its row)
+      const int p00 = step0 * 32;
+      int rb = p00 / (a.Ho * a.Wo);
+      int ry = (p00 - rb * (a.Ho * a.Wo)) / a.Wo;
+      int rx = p00 - (rb * a.Ho + ry) * a.Wo;
+      if (lane <= 4) {
+        for (int st = 0; st < nsteps; ++st) {
+          const int s = st % STAGES;
+          const uint32_t ph = (uint32_t)(st / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (lane == 4) {
+            mbar_expect_tx(&full_bar[s], (uint32_t)(B_STAGE + nreg * 4096));
+            const int p0 = (step0 + st) * 32;
+            if (a.dz3) tma_load_3d(smem_u32(smem + s * STAGE + A_STAGE), &dymap, &full_bar[s], 0, p0, n0 >> 5);
+            else
+              for (int h = 0; h < NT / 32; ++h) tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE + h * 4096), &dymap, &full_bar[s], n0 + 32 * h, p0);
+          } else if (mine) {
+            int ys = ry + dy - a.pad;
+            const int xs = rx + dx - a.pad;
+            if (a.reflect) ys = jpb_reflect(ys, a.Hin);
+            const uint32_t dst = smem_u32(smem + s * STAGE) + (uint32_t)g * 4096u;
+            if (a.reflect && xs < 0) {                       // pixel -1 mirrors to pixel 1
+              tma_load_4d(dst + 128u, m31, &full_bar[s], coff, 0, ys, rb);
+              tma_load_4d(dst, m1, &full_bar[s], coff, 1, ys, rb);
+            } else if (a.reflect && xs + 32 > a.Win) {       // pixel W mirrors to pixel W - 2
+              tma_load_4d(dst, m31, &full_bar[s], coff, xs, ys, rb);
+              tma_load_4d(dst + 31u * 128u, m1, &full_bar[s], coff, a.Win - 2, ys, rb);
+            } else {
+              tma_load_4d(dst, m32, &full_bar[s], coff, xs, ys, rb);   // out-of-range rows / pixels: zero fill = zero padding
+            }
+          }
+          rx += 32;
+          if (rx >= a.Wo) { rx = 0; if (++ry >= a.Ho) { ry = 0; ++rb; } }
+        }
       }
     }
   } else {
@@ -1264,10 +1367,6 @@ constexpr int PATCH_PX = 16;
 // 16*TR + 2 rows and ONE weight tile per (channel block, tap) feed TR accumulators — the weight stream, which dominated the L2 -> SM
 // traffic of the one-tile version (ncu: 302 of 378 MB for 128 -> 128 channels), is halved per output for TR = 2.
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 
 template <int NT, int TR, int PSTAGES, int BSTAGES>
 __global__ void __launch_bounds__(192 + 32 * (TR - 1), 1) conv_tc_patch_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
@@ -1762,17 +1861,43 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
 }
 
 namespace {
-template <int NT, int STAGES, int MINB>
-int launch_wgrad(const JpbConvWgradArgs* a, const CUtensorMap& map, cudaStream_t st) {
+template <int NT, int STAGES, int MINB, bool ROWS = false>
+int launch_wgrad(const JpbConvWgradArgs* a, const CUtensorMap& map, cudaStream_t st, const WgradRowMaps* xmaps = nullptr) {
   constexpr int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<NT, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<NT, STAGES, MINB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
     configured = true;
   }
+  static const WgradRowMaps no_maps = {};
   dim3 grid((a->nchunks + 31) / 32, (a->N + NT - 1) / NT, a->splits);
-  conv_tc_wgrad_kernel<NT, STAGES, MINB><<<grid, 192, smem, st>>>(map, *a);
+  conv_tc_wgrad_kernel<NT, STAGES, MINB, ROWS><<<grid, 192, smem, st>>>(map, xmaps ? *xmaps : no_maps, *a);
   return jpb_status();
+}
+
+// tensor maps of the TMA-row weight gradient: every source as [C, W, H, B] with boxes of 32 channels x {32, 31, 1} pixels
+int wgrad_row_maps(const JpbConvWgradArgs* a, EncodeTiledFn enc, WgradRowMaps* out) {
+  static const cuuint32_t px[3] = {32, 31, 1};
+  for (int si = 0; si < a->nsrc; ++si) {
+    const int C = a->src_C[si], H = a->src_H[si], W = a->src_W[si];
+    if (a->src_up[si] || H != a->Hin || W != a->Win) return JPB_ERR_ARG;
+    if (C & 31) {                        // gathered source: its maps are never used (placeholder: the first TMA source's)
+      if (si == 0) return JPB_ERR_ARG;   // the host lists a TMA source first
+      for (int v = 0; v < 3; ++v) out->m[si][v] = out->m[0][v];
+      continue;
+    }
+    if (reinterpret_cast<uintptr_t>(a->src[si]) & 15) return JPB_ERR_ARG;
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a->B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int v = 0; v < 3; ++v) {
+      const cuuint32_t box[4] = {32, px[v], 1, 1};
+      if (enc(&out->m[si][v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->src[si]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return JPB_ERR_ARG;
+    }
+  }
+  return JPB_OK;
 }
 }  // namespace
 
@@ -1791,11 +1916,37 @@ extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
   const cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
   const cuuint32_t box[2] = {32, 32};
   const cuuint32_t estr[2] = {1, 1};
-  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  JpbConvWgradArgs local = *a;
+  local.dz3 = 0;
+  if (a->rows && !(a->N & 31)) {
+    // dZ as [32 channels, P pixels, N / 32 channel blocks]: one box per step lands all MN groups of the B tile
+    const cuuint64_t gdim3[3] = {32, (cuuint64_t)P, (cuuint64_t)(a->N / 32)};
+    const cuuint64_t gstr3[2] = {(cuuint64_t)pitch * 4, 128};
+    const cuuint32_t box3[3] = {32, 32, (cuuint32_t)(nt / 32)};
+    const cuuint32_t estr3[3] = {1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a->dy), gdim3, gstr3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return JPB_ERR_ARG;
+    local.dz3 = 1;
+  } else if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return JPB_ERR_ARG;
+  a = &local;
   cudaStream_t st = (cudaStream_t)stream;
   const int var = conv_variant();
+  if (a->rows) {
+    // TMA-row operand: stride-1 "same" convolution over dense full-resolution sources, rows of a multiple of 32 pixels
+    if (a->stride != 1 || a->Ho != a->Hin || a->Wo != a->Win || (a->Wo & 31) || !a->gflags || !a->chunk_col || (a->reflect && a->Win < 33)) return JPB_ERR_ARG;
+    WgradRowMaps xm;
+    const int rc = wgrad_row_maps(a, enc, &xm);
+    if (rc != JPB_OK) return rc;
+    switch (nt) {
+      case 32: return launch_wgrad<32, 4, 2, true>(a, map, st, &xm);
+      case 64: return launch_wgrad<64, 4, 2, true>(a, map, st, &xm);
+      case 128: return launch_wgrad<128, 3, 2, true>(a, map, st, &xm);
+      default: return a->rows == 2 ? launch_wgrad<256, 4, 1, true>(a, map, st, &xm) : launch_wgrad<256, 2, 2, true>(a, map, st, &xm);
+    }
+  }
   if (var == 0) {
     switch (nt) {
       case 32: return launch_wgrad<32, 6, 1>(a, map, st);

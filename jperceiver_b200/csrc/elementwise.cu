@@ -132,7 +132,54 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* x, float* x3
   }
 }
 
+// nearest 2x up-sampling of an NHWC map (layers.py:16-19 upsample = F.interpolate(scale_factor=2, mode="nearest")), materialised
+// for the TMA-row weight gradient, whose operand boxes need a dense full-resolution source (the other convolution kernels read
+// up-sampled sources through their gather)
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float4* x, float4* y, int B, int H, int W, int C4) {
+  const long long n = (long long)B * (2 * H) * (2 * W) * C4;
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n; i += (long long)gridDim.x * JPB_NT) {
+    const int c = (int)(i % C4);
+    long long r = i / C4;
+    const int ox = (int)(r % (2 * W)); r /= 2 * W;
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    y[i] = x[(((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * C4 + c];
+  }
+}
+
+// zero-padded channel copy of an NHWC map, C -> Cp (Cp % 4 == 0): the 1-channel disparity that the iconv layers concatenate becomes
+// a source of whole 16-byte chunks (forward / data gradient gather: cp.async instead of synchronous scalar loads) or of a whole
+// 32-channel block (TMA-row weight gradient)
+__global__ void __launch_bounds__(256) pad_channels_kernel(const float* x, float4* y, long long rows, int C, int Cp4) {
+  const long long n = rows * Cp4;
+  for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n; i += (long long)gridDim.x * JPB_NT) {
+    const long long r = i / Cp4;
+    const int c = (int)(i - r * Cp4) * 4;
+    const float* px = x + r * C;
+    y[i] = make_float4(c < C ? px[c] : 0.f, c + 1 < C ? px[c + 1] : 0.f, c + 2 < C ? px[c + 2] : 0.f, c + 3 < C ? px[c + 3] : 0.f);
+  }
+}
+
 }  // namespace
+
+extern "C" int jpb_pad_channels(const float* x, float* y, long long rows, int C, int Cp, void* stream) {
+  if (!x || !y || rows < 1 || C < 1 || Cp < C || (Cp & 3) || ((uintptr_t)y & 15)) return JPB_ERR_ARG;
+  const long long n = rows * (Cp / 4);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  JPB_LAUNCH(pad_channels_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, reinterpret_cast<float4*>(y), rows, C, Cp / 4);
+  return jpb_status();
+}
+
+extern "C" int jpb_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 4 || (C & 3) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return JPB_ERR_ARG;
+  const long long n = (long long)B * 4 * H * W * (C / 4);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  JPB_LAUNCH(upsample2x_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(x),
+             reinterpret_cast<float4*>(y), B, H, W, C / 4);
+  return jpb_status();
+}
 
 extern "C" int jpb_bias_act(float* z, const float* bias, const float* residual, long long rows, int C, int act, void* stream) {
   if (!z || rows < 1 || C < 4 || (C & 3)) return JPB_ERR_ARG;

@@ -270,3 +270,51 @@ def test_conv_patch_kernel_forward_and_dgrad(case, desc_mode, tile_rows):
     assert errx <= 3e-3 * max(xr.grad.abs().max().item(), 1e-6), ("dgrad", case, errx)
     errw = (wm.grad - wr.grad).abs().max().item()
     assert errw <= 3e-3 * max(wr.grad.abs().max().item(), 1e-6), ("wgrad", case, errw)
+
+
+ROW_CASES = [
+    # name, B, sources [(C, H, W, up)], Cout, k, reflect
+    ("zero pad 3x3 64->64 @64x64", 2, [(64, 64, 64, 0)], 64, 3, 0),
+    ("reflect 3x3 128->256 @24x128 (row-end boxes 31 + 1)", 2, [(128, 24, 128, 0)], 256, 3, 1),
+    ("reflect 3x3 cat(64, up(64), 1)->128 @32x64 (gathered 1-channel source)", 2, [(64, 32, 64, 0), (64, 16, 32, 1), (1, 32, 64, 0)], 128, 3, 1),
+    ("1x1 128->256 @32x32", 3, [(128, 32, 32, 0)], 256, 1, 0),
+    ("zero pad 3x3 32->16 @16x96 (one group + dead groups)", 2, [(32, 16, 96, 0)], 16, 3, 0),
+]
+
+
+@pytest.mark.parametrize("case", ROW_CASES, ids=[c[0] for c in ROW_CASES])
+def test_conv_wgrad_tma_rows_matches_gather_and_library(case):
+    """Weight gradient with the im2col^T operand fetched by TMA boxes (csrc/conv_tc.cu: conv_tc_wgrad_kernel<.., ROWS>, the default
+    for stride-1 same-size convolutions with rows of a multiple of 32 pixels) against the gathered operand and against fp32
+    autograd of the library convolution; TF32-representable operands, so only the summation order differs."""
+    name, B, srcs, cout, k, reflect = case
+    _lib._handle, _lib._emulated = None, False
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(len(name))
+    xs = [tf32(torch.randn(B, c, h, w, generator=g)).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
+    ups = [bool(up) for *_, up in srcs]
+    cin = sum(c for c, *_ in srcs)
+    pad = (k - 1) // 2
+    weight = tf32(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev).contiguous(memory_format=CL)
+    H, W = srcs[0][1], srcs[0][2]
+    dz = tf32(torch.randn(B, cout, H, W, generator=g)).to(dev).contiguous(memory_format=CL)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        wr = weight.clone().requires_grad_(True)
+        torch_conv(xs, ups, wr, None, 1, pad, reflect, "none", None).backward(dz)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    got = {}
+    saved = JC.WGRAD_ROWS
+    try:
+        for rows in (0, 1):
+            JC.WGRAD_ROWS = rows
+            with JC.trunc_comp(1.0):
+                got[rows] = JC.conv_wgrad(dz, weight, xs, ups, 1, pad, reflect).contiguous()
+            torch.cuda.synchronize()
+    finally:
+        JC.WGRAD_ROWS = saved
+    scale = wr.grad.abs().max().item()
+    assert (got[0] - wr.grad).abs().max().item() <= 1e-4 * scale, (name, "gather vs library")
+    assert (got[1] - wr.grad).abs().max().item() <= 1e-4 * scale, (name, "rows vs library")
