@@ -213,6 +213,11 @@ typedef struct JpbConvArgs {
   int patch_tapoff[16];                 /* per tap: (dy * 2048 + dx * 128) / 16 — start-address offset of the tap inside the patch */
   int patch_desc_mode;                  /* debug: 2 = set the UMMA matrix-descriptor base offset for the shifted patch start addresses (WRONG on
                                            B200: the swizzle follows absolute address bits; kept to reproduce the measurement) */
+  int rows;                             /* != 0: the A operand arrives by TMA boxes of 32 pixels x 32 channels instead of the gather: stride 1,
+                                           every source dense (no up-sampling) with C % 32 == 0, N tile >= 64, reflect only for pad 1 with
+                                           Wo == Win.  2 = one deep CTA per SM for the 256-wide tiles                                         */
+  int rows_wv;                          /* rows != 0: row length of the tile raster, a multiple of 32 and >= Wo; pixels Wo .. rows_wv - 1 of a
+                                           row are computed and dropped (data gradient of reflection-padded layers: Wo = W + 2)              */
 } JpbConvArgs;
 #define JPB_TF32_TRUNC_COMP 1.00067702f  /* 1 + 2 * 2^-11 * ln 2 */
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);

@@ -381,6 +381,12 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
             nt = 0
         assert nt == 0 or nt >= 16
         a.nt = nt
+    if (FWD_ROWS and not three and not a.patch and stride == 1 and Nc % 32 == 0 and Cin > 32 and (a.nt == 0 or a.nt >= 64)):
+        # TMA-row operand (dz is one dense source): the tile raster's row length is the gradient domain's, rounded up to 32 pixels
+        # (reflection-padded layers: W + 2 -> the surplus pixels are computed and dropped) when that costs at most a quarter more
+        wv = (a.Wo + 31) // 32 * 32
+        if wv * 4 <= a.Wo * 5:
+            a.rows, a.rows_wv = FWD_ROWS, wv
     tag = (B * a.Ho * a.Wo, Cin, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
     check(_launch("conv_dgrad", dz, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_fwd(dgrad)")
     return grads
@@ -397,6 +403,16 @@ def upsample2x(x):
     y = torch.empty((B, Cc, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=CL)
     check(_launch("upsample2x", x, lambda: _lib.lib().jpb_upsample2x(ptr(x), ptr(y), B, H, W, Cc, stream_of(x))), "jpb_upsample2x")
     return y
+
+
+FWD_ROWS = int(_os.environ.get("JPB_FWD_ROWS", "1"))         # 0: gathered A operand in the forward / data-gradient kernels (A/B measurements)
+
+
+def _fwd_rows_ok(src_C, ups, N, kh, kw, stride, pad, reflect, Hin, Win, Ho, Wo):
+    """TMA-row A operand of conv_tc_fwd_kernel (JpbConvArgs.rows): stride-1 same-size convolutions with rows of a multiple of 32
+    pixels; every source becomes a dense tensor of whole 32-channel blocks (up-sampled ones are materialised, a narrow one padded)."""
+    return (FWD_ROWS and PRECISION == "tf32" and stride == 1 and kh == kw and pad == (kh - 1) // 2 and Ho == Hin and Wo == Win and Wo % 32 == 0
+            and N > 32 and (not reflect or (pad == 1 and Win >= 64)) and all(c % 32 == 0 or (c < 32 and not u) for c, u in zip(src_C, ups)))
 
 
 def pad_channels(x, Cp):
@@ -603,7 +619,13 @@ class _ConvTC(torch.autograd.Function):
             table, kcol = ordered_table([_pad4(c) for c in src_C], kh, kw, dev, split3=True)
             wmat, wcols = gemm_weight3(weight.detach(), src_C, w_C)
         else:
-            if len(xs) > 1 and any(c % 4 for c in src_C):
+            patchable = src_C == w_C and _patch_ok(Cin, N, Hin, Win, B, kh, kw, stride, pad, reflect, len(xs), ups[0], 1)
+            use_rows = (not patchable) and len(src_C) == len(w_C) and _fwd_rows_ok(src_C, ups, N, kh, kw, stride, pad, reflect, Hin, Win, Ho, Wo)
+            if use_rows:
+                # TMA-row operand: dense full-resolution sources of whole 32-channel blocks
+                xs_k = [upsample2x(x) if u else (pad_channels(x, 32) if x.shape[1] % 32 else x) for x, u in zip(xs, ups)]
+                ups = [False] * len(xs_k)
+            elif len(xs) > 1 and any(c % 4 for c in src_C):
                 # a source with a ragged channel count (the 1-channel disparity of the iconv layers) is zero-padded to whole 16-byte
                 # chunks: its K blocks then take the asynchronous copy path instead of eight dependent scalar loads per thread
                 xs_k = [pad_channels(x, _pad4(x.shape[1])) if x.shape[1] % 4 else x for x in xs]
@@ -648,7 +670,9 @@ class _ConvTC(torch.autograd.Function):
         if src_C == w_C and wcols == kh * kw * Cin and _patch_ok(Cin, N, Hin, Win, B, kh, kw, stride, pad, reflect, len(xs), ups[0], ks):
             a.patch, a.patch_desc_mode = 1 + PATCH_TILE_ROWS, PATCH_DESC_MODE
             _patch_taps(a, TAPS_3X3, 2, (1, 1))
-        tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
+        elif PRECISION == "tf32" and use_rows:
+            a.rows, a.rows_wv = FWD_ROWS, Wo
+        tag = (B * Ho * Wo, N, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in cfg["ups"]), int(bool(reflect)), ks)
         check(_launch("conv_fwd", out, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(out)), tag), "jpb_conv2d_fwd")
         if finish:
             check(_launch("conv_bias_act", out, lambda: _lib.lib().jpb_bias_act(

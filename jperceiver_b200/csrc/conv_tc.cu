@@ -383,14 +383,26 @@ __device__ __forceinline__ void sts_row(uint32_t rowtab, int lane, unsigned long
   asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowtab + (uint32_t)lane * 16u), "l"(out_ptr_flag), "l"(res_ptr) : "memory");
 }
 
+struct WgradRowMaps {
+  CUtensorMap m[JPB_CONV_MAX_SRC][3];   // per source: boxes of 32 channels x {32, 31, 1} pixels
+};
+
 // NT: N tile (UMMA N), multiple of 16 in [16,256].  STAGES: smem pipeline depth.
 // CG = 2: CTA-pair version (launched as 2-clusters along blockIdx.x).  CTA x owns output rows [128 x, 128 x + 128) exactly as in
 // the single-CTA version — gather, epilogue and accumulator lanes are unchanged — but loads only rows [rank * NT/2, +NT/2) of
 // the weight tile: the pair's tcgen05.mma.cta_group::2 (M = 256) reads both halves, so the weight stream per output row — two
 // thirds of the L2 -> SM traffic that bounds the wide layers (tools/microbench/mma_pipeline.cu, profiles/README.md) — is halved.
 // The peer's MMA warp forwards "my stage is full" to the leader's pfull barrier; the leader's commits arrive in both CTAs.
-template <int NT, int STAGES, int MINB, int CG = 1>
-__global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap wmap, JpbConvArgs a) {
+// ROWS: the A operand arrives by TMA (JpbConvArgs.rows; stride 1, dense sources of whole 32-channel blocks).  The tile's 128 rows are
+// four 32-pixel segments of image rows (the output raster has a row length `rows_wv` that is a multiple of 32 — for the data
+// gradient of a reflection-padded layer the padded width rounded up, whose surplus pixels are computed and dropped); per K block
+// (one source, one tap, 32 channels) lanes 0-3 of the copy warp issue one {32 channels, 32 pixels} box each — out-of-range rows,
+// pixels and images are the box's zero fill, reflection mirrors the row coordinate and splits the box at the row ends into
+// 31 + 1 pixels — and lane 4 the weight tile.  No thread gathers: measured (tools/microbench/mma_tma_gather.cu) the operand
+// path then sustains 650-680 cycles per K block and SM against ~1650 with 1024 cp.async per block.
+template <int NT, int STAGES, int MINB, int CG = 1, bool ROWS = false>
+__global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ WgradRowMaps xmaps,
+                                                                JpbConvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [STAGES][A 16KB][B (NT/CG)*128] | barriers | tmem ptr | src table
   constexpr int B_STAGE = (NT / CG) * BK * 4;
@@ -407,7 +419,8 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   const uint32_t srcs_u32 = smem_u32(srcs), soff_u32 = smem_u32(s_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = a.B * a.Ho * a.Wo;
+  const int Wv = ROWS ? a.rows_wv : a.Wo;               // row length of the tile raster (ROWS: a multiple of 32, >= Wo)
+  const int M = a.B * a.Ho * Wv;
   const float acc_scale = a.acc_scale != 0.f ? a.acc_scale : 1.f;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT;
   // debug timeline (tools/conv_timeline.py): stamps[cta][warp][slot] = globaltimer ns at fixed points of each role
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     srcs[tid].C = a.src_C[tid]; srcs[tid].H = a.src_H[tid]; srcs[tid].W = a.src_W[tid]; srcs[tid].up = a.src_up[tid];
   }
   if (tid == 160) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], ROWS ? 1 : NPROD + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     if (CG == 2)
       for (int s = 0; s < STAGES; ++s) mbar_init(&pfull_bar[s], 1);
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   // filter tap `tap` in source `src` (padding / reflection / up-sampling / stride folded), or -1.  Thread = tile row: three
   // integer divisions per row, then the taps are walked with counters (the per-entry form with six divisions per entry cost
   // 2.2 us of every tile's 4.7 us set-up).
-  if (tid < BM) {
+  if (!ROWS && tid < BM) {
     const int m = m0 + tid;
     const bool rowok = m < M;
     const int HoWo = a.Ho * a.Wo;
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     // L1 is carved down to almost nothing by the pipeline stages) was the largest single stall of the producer warps
     int4 e_next = make_int4(-1, 0, 0, 0);
     if (nkb > 0) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(0)) * 8 + c);
-    while (published < nkb) {
+    while (!ROWS && published < nkb) {
       bool can = false;
       if (issued < nkb && issued - published < MAXFLY) {
         const int s = issued % STAGES;
@@ -578,7 +591,13 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     tc_fence_after();
     JPB_STAMP(4);
     const int row = warp * 32 + lane;
-    const int m = m0 + row;
+    int m = m0 + row;
+    bool mok = m < M;
+    if (ROWS && Wv != a.Wo) {                 // tile raster with a padded row length: back to the dense output index
+      const int b_ = m / (a.Ho * Wv), rem_ = m - b_ * (a.Ho * Wv), oy_ = rem_ / Wv, ox_ = rem_ - oy_ * Wv;
+      mok = mok && ox_ < a.Wo;
+      m = mok ? (b_ * a.Ho + oy_) * a.Wo + ox_ : 0;
+    }
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     float* out = nullptr;
     const float* res = nullptr;
@@ -594,7 +613,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       while (j + 1 < a.ndst && n0 >= cbase + a.dst_C[j]) { cbase += a.dst_C[j]; ++j; }
       vec_ok = (a.dst_C[j] & 3) == 0;
       nvalid = cbase + a.dst_C[j] - n0;
-      if (m < M) {
+      if (mok) {
         const int b = m / (a.Ho * a.Wo), rem = m - b * (a.Ho * a.Wo);
         int ty = rem / a.Wo - a.fold_pad, tx = rem % a.Wo - a.fold_pad;
         if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
@@ -612,8 +631,8 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
       const uint32_t sbuf = smem_u32(smem) + (uint32_t)warp * EPI_WARP_FLOATS * 4u;
       const uint32_t rowptr = sbuf + 32 * 36 * 4;
       const uint32_t sstats = smem_u32(smem) + 4u * EPI_WARP_FLOATS * 4u;   // [4 warps][2][NT] floats, behind the staging tiles
-      sts_row(rowptr, lane, (m < M) ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull,
-              (unsigned long long)(uintptr_t)(a.residual ? a.residual + (size_t)(m < M ? m : 0) * a.N + n0 : nullptr));
+      sts_row(rowptr, lane, mok ? (unsigned long long)(uintptr_t)out | (atomic ? 1ull : 0ull) : 0ull,
+              (unsigned long long)(uintptr_t)(a.residual ? a.residual + (size_t)(mok ? m : 0) * a.N + n0 : nullptr));
       __syncwarp();
       const int c4 = (lane & 7) * 4, r0 = lane >> 3;
       for (int j = 0; j < NT; j += 32) {
@@ -651,7 +670,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     for (int j = 0; j < NT; j += 16) {
       float v[16];
       tmem_ld16(taddr + (uint32_t)j, v, acc_scale);   // warp-collective: every lane executes it, even for rows >= M
-      if (m < M) {
+      if (mok) {
         const int nleft = nvalid - j;
         if (nleft >= 16 && vec_ok) {
           for (int q = 0; q < 16; q += 4) {
@@ -679,6 +698,46 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
     tc_fence_before();
   } else if (warp == 4) {
     // ===================================================== weight TMA producer
+    if (ROWS) {
+      if (lane <= 4) {
+        // lane j < 4: segment j of the tile = 32 consecutive pixels (ox0 ..) of output row oy of image b (b >= B: past the end,
+        // the box is all zero fill)
+        const int ms = m0 + 32 * lane;
+        const int sb = ms / (a.Ho * Wv), srem = ms - sb * (a.Ho * Wv), soy = srem / Wv, sox = srem - soy * Wv;
+        const uint32_t seg_off = (uint32_t)lane * 4096u;
+        int4 e_next = make_int4(-1, 0, 0, 0);
+        if (nkb > 0 && lane < 4) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(0)) * 8);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+          const int4 e = e_next;
+          if (kb + 1 < nkb && lane < 4) e_next = __ldg(reinterpret_cast<const int4*>(a.table) + (size_t)(kb0 + JPB_KROT(kb + 1)) * 8);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (lane == 4) {
+            mbar_expect_tx(&full_bar[s], (uint32_t)(B_STAGE + A_STAGE));
+            const int kr = kb0 + JPB_KROT(kb);
+            tma_load_2d(smem_u32(smem + s * STAGE + A_STAGE), &wmap, &full_bar[s], a.kcol ? a.kcol[kr] : kr * BK, n0 + (int)crank * (NT / CG));
+          } else {
+            const int si = e.x < 0 ? 0 : (e.x & 0xff), tap = e.x < 0 ? 0 : (e.x >> 8) / a.nsrc;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            int iy = soy - a.pad + ky;
+            const int ix = sox - a.pad + kx;
+            int bb = e.x < 0 ? a.B : sb;                      // padding K block: all zero
+            if (a.reflect) iy = jpb_reflect(iy, a.Hin);
+            const uint32_t dst = smem_u32(smem + s * STAGE) + seg_off;
+            if (a.reflect && ix < 0) {                       // pixel -1 mirrors to pixel 1
+              tma_load_4d(dst + 128u, &xmaps.m[si][1], &full_bar[s], e.z, 0, iy, bb);
+              tma_load_4d(dst, &xmaps.m[si][2], &full_bar[s], e.z, 1, iy, bb);
+            } else if (a.reflect && ix + 32 > a.Win) {       // pixel W mirrors to pixel W - 2
+              tma_load_4d(dst, &xmaps.m[si][1], &full_bar[s], e.z, ix, iy, bb);
+              tma_load_4d(dst + 31u * 128u, &xmaps.m[si][2], &full_bar[s], e.z, a.Win - 2, iy, bb);
+            } else {
+              tma_load_4d(dst, &xmaps.m[si][0], &full_bar[s], e.z, ix, iy, bb);
+            }
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
@@ -1089,9 +1148,6 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
 // tensor pipe in the loop (tools/microbench/mma_tma_gather.cu, profiles/r2_mma_tma_gather.txt) the operand path then sustains
 // 650-680 cycles per K block and SM against ~1650 with the gather.  Groups that are not a whole 32-channel block of one source
 // (the 1-channel disparity of the iconv layers) keep the gather, in the CTAs that own them.
-struct WgradRowMaps {
-  CUtensorMap m[JPB_CONV_MAX_SRC][3];   // per source: boxes of 32, 31 and 1 pixels
-};
 
 template <int NT, int STAGES, int MINB, bool ROWS = false>
 __global__ void __launch_bounds__(192, MINB) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ WgradRowMaps xmaps,
@@ -1636,18 +1692,23 @@ int conv_variant() {
   return v;
 }
 
-template <int NT, int STAGES, int MINB>
-int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st) {
-  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+const WgradRowMaps& no_row_maps() {
+  static const WgradRowMaps m = {};
+  return m;
+}
+
+template <int NT, int STAGES, int MINB, bool ROWS = false>
+int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st, const WgradRowMaps* xmaps = nullptr) {
+  const int smem = STAGES * (A_STAGE + NT * BK * 4) + 1024 + 256 + (ROWS ? 0 : a->ntaps * a->nsrc * BM * 4);
   static int configured = 0;
   if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES, MINB, 1, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
     configured = smem;
   }
-  const int M = a->B * a->Ho * a->Wo;
+  const int M = a->B * a->Ho * (ROWS ? a->rows_wv : a->Wo);
   dim3 grid((M + BM - 1) / BM, (a->N + NT - 1) / NT, a->ksplit > 1 ? a->ksplit : 1);
-  conv_tc_fwd_kernel<NT, STAGES, MINB><<<grid, 192, smem, st>>>(map, *a);
+  conv_tc_fwd_kernel<NT, STAGES, MINB, 1, ROWS><<<grid, 192, smem, st>>>(map, xmaps ? *xmaps : no_row_maps(), *a);
   return jpb_status();
 }
 
@@ -1673,7 +1734,7 @@ int launch_fwd_pair(const JpbConvArgs* a, const CUtensorMap& half_map, cudaStrea
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, conv_tc_fwd_kernel<NT, STAGES, MINB, 2>, half_map, *a) != cudaSuccess) return jpb_status() ? jpb_status() : JPB_ERR_UNSUPPORTED;
+  if (cudaLaunchKernelEx(&cfg, conv_tc_fwd_kernel<NT, STAGES, MINB, 2>, half_map, no_row_maps(), *a) != cudaSuccess) return jpb_status() ? jpb_status() : JPB_ERR_UNSUPPORTED;
   return jpb_status();
 }
 
@@ -1773,6 +1834,28 @@ int conv2d_patch(const JpbConvArgs* a, cudaStream_t st) {
 
 }  // namespace
 
+namespace {
+// tensor maps of the TMA-row forward / data-gradient kernel: every source as [C, W, H, B], boxes of 32 channels x {32, 31, 1} pixels,
+// 128-byte swizzle (K-major operand rows)
+int fwd_row_maps(const JpbConvArgs* a, EncodeTiledFn enc, WgradRowMaps* out) {
+  static const cuuint32_t px[3] = {32, 31, 1};
+  for (int si = 0; si < a->nsrc; ++si) {
+    const int C = a->src_C[si], H = a->src_H[si], W = a->src_W[si];
+    if (a->src_up[si] || H != a->Hin || W != a->Win || (C & 31) || (reinterpret_cast<uintptr_t>(a->src[si]) & 15)) return JPB_ERR_ARG;
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)a->B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int v = 0; v < 3; ++v) {
+      const cuuint32_t box[4] = {32, px[v], 1, 1};
+      if (enc(&out->m[si][v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a->src[si]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return JPB_ERR_ARG;
+    }
+  }
+  return JPB_OK;
+}
+}  // namespace
+
 extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   if (!a || !a->weight || !a->table || (!a->out && !a->scatter) || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nkb < 1) return JPB_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(a->weight) & 15) || (a->w_row & 3)) return JPB_ERR_ARG;   // TMA: 16-byte aligned base and row pitch
@@ -1800,6 +1883,21 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
   // allocation) and epilogue (TMEM -> registers -> global) with the other tiles' main loops
   const int nts = a->ntaps * a->nsrc;
   const int var = conv_variant();
+  if (a->rows) {
+    // TMA-row operand (see conv_tc_fwd_kernel): stride 1, dense sources of whole 32-channel blocks, tile raster of 32-pixel segments
+    if (a->stride != 1 || a->in_div || a->patch || (a->rows_wv & 31) || a->rows_wv < a->Wo || (a->reflect && (a->Wo != a->Win || a->pad != 1 || a->Win < 33)) ||
+        nt < 64)
+      return JPB_ERR_ARG;
+    WgradRowMaps xm;
+    const int rc = fwd_row_maps(a, enc, &xm);
+    if (rc != JPB_OK) return rc;
+    const long long tiles = (long long)((a->B * a->Ho * a->rows_wv + BM - 1) / BM) * ((a->N + nt - 1) / nt) * (a->ksplit > 1 ? a->ksplit : 1);
+    switch (nt) {
+      case 64: return launch_fwd<64, 4, 2, true>(a, map, st, &xm);
+      case 128: return tiles > 148 ? launch_fwd<128, 3, 2, true>(a, map, st, &xm) : launch_fwd<128, 5, 1, true>(a, map, st, &xm);
+      default: return (tiles > 148 && a->rows != 2) ? launch_fwd<256, 2, 2, true>(a, map, st, &xm) : launch_fwd<256, 4, 1, true>(a, map, st, &xm);
+    }
+  }
   if (var == 5) {
     // measured best per N tile (tools/bench_conv.py, B200): narrow tiles -> persistent kernel, two CTAs per SM; wide tiles ->
     // one tile per CTA, two shallow CTAs per SM when there are enough tiles to fill them, else one deep CTA
