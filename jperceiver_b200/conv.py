@@ -475,9 +475,10 @@ def row_table(src_C, kh, kw, device, tma_C=None):
     return r
 
 
-def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None):
+def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None, dense=None):
     """``target``: the weight's channels-last gradient view; when given (and the K layout needs no padding) the kernel adds
-    into it and None is returned."""
+    into it and None is returned.  ``dense``: the sources as the TMA-row forward already materialised them (up-sampled /
+    channel-padded), if it did."""
     N, Cin, kh, kw = weight.shape
     B, Nc, Ho, Wo = dz.shape
     dev = dz.device
@@ -504,7 +505,7 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None)
     if dbg is None and _wgrad_rows_ok(src_C, ups, kh, kw, stride, pad, a.Hin, a.Win, Ho, Wo, reflect):
         # TMA-row operand: dense full-resolution sources (an up-sampled source is materialised), group-major table
         # (and a narrow one — the 1-channel disparity of the iconv layers — zero-padded to one 32-channel block: no gathered group)
-        xs_d = [upsample2x(x) if u else (pad_channels(x, 32) if x.shape[1] % 32 else _cl(x)) for x, u in zip(xs, ups)]
+        xs_d = dense if dense is not None else [upsample2x(x) if u else (pad_channels(x, 32) if x.shape[1] % 32 else _cl(x)) for x, u in zip(xs, ups)]
         _fill_sources(a, xs_d, [False] * len(xs_d))
         table, gflags, ccol = row_table(src_C, kh, kw, dev, [x.shape[1] for x in xs_d])
         a.table, a.nchunks = ptr(table), table.shape[0]
@@ -625,6 +626,7 @@ class _ConvTC(torch.autograd.Function):
                 # TMA-row operand: dense full-resolution sources of whole 32-channel blocks
                 xs_k = [upsample2x(x) if u else (pad_channels(x, 32) if x.shape[1] % 32 else x) for x, u in zip(xs, ups)]
                 ups = [False] * len(xs_k)
+                ctx.dense_sources = xs_k          # the weight gradient reads the same materialised sources
             elif len(xs) > 1 and any(c % 4 for c in src_C):
                 # a source with a ragged channel count (the 1-channel disparity of the iconv layers) is zero-padded to whole 16-byte
                 # chunks: its K blocks then take the asynchronous copy path instead of eight dependent scalar loads per thread
@@ -706,7 +708,7 @@ class _ConvTC(torch.autograd.Function):
         want_dx = any(ctx.needs_input_grad[4:])
         if want_dx:
             gxs = conv_dgrad(dzp, weight, xs, ups, stride, pad, reflect, ctx.needs_input_grad[4:])
-        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=target) if ctx.needs_input_grad[1] else None
+        gw = conv_wgrad(dzp, weight, xs, ups, stride, pad, reflect, target=target, dense=getattr(ctx, "dense_sources", None)) if ctx.needs_input_grad[1] else None
         return (None, gw, gb, gr) + tuple(gxs)
 
 

@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
   if (nkb < 0) nkb = 0;
   const bool split = gridDim.z > 1;
   // rotated K loop (see the persistent kernel): CTAs of one N column must not all stream the same weight tile at once
-  const int rot = nkb > 1 ? (int)(((((uint32_t)blockIdx.x / (uint32_t)CG) * 0x9E3779B1u) >> 12) % (uint32_t)nkb) : 0;   // same for a pair
+  // (timing experiment JPB_CONV_SKIP=16: no rotation)
+  const int rot = (nkb > 1 && !(a.dbg_skip & 16)) ? (int)(((((uint32_t)blockIdx.x / (uint32_t)CG) * 0x9E3779B1u) >> 12) % (uint32_t)nkb) : 0;   // same for a pair
 #define JPB_KROT(kb) ((kb) + rot >= nkb ? (kb) + rot - nkb : (kb) + rot)
 
   if (tid < a.nsrc) {

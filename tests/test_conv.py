@@ -50,7 +50,7 @@ CASES = [
     ("odd extent 3x3 64->64 (M not a multiple of 128)", [(64, 13, 19, 0)], 64, 3, 1, 1, 1, "none", 1, 0),
     # TMA-row A operand (JpbConvArgs.rows: rows of a multiple of 32 pixels): reflection at the row ends (31 + 1 pixel boxes), the data
     # gradient on the padded raster 258 -> 288, materialised up-sampled / padded sources, several zero-padded sources, a ragged tile
-    ("rows: refl 3x3 128->256 leaky @24x256", [(128, 24, 256, 0)], 256, 3, 1, 1, 1, "leaky", 1, 0),
+    ("rows: refl 3x3 128->128 leaky @24x256", [(128, 24, 256, 0)], 128, 3, 1, 1, 1, "leaky", 1, 0),
     ("rows: refl 3x3 cat(64, up64, 1)->128 leaky @16x256", [(64, 16, 256, 0), (64, 8, 128, 1), (1, 16, 256, 0)], 128, 3, 1, 1, 1, "leaky", 1, 0),
     ("rows: 1x1 64->128 + residual @15x96", [(64, 15, 96, 0)], 128, 1, 1, 0, 0, "none", 0, 1),
     ("rows: 3x3 cat(64, 64)->64 relu @16x64", [(64, 16, 64, 0), (64, 16, 64, 0)], 64, 3, 1, 1, 0, "relu", 1, 0),
