@@ -1715,16 +1715,16 @@ int launch_fwd(const JpbConvArgs* a, const CUtensorMap& map, cudaStream_t st, co
 
 
 // CTA-pair launch: 2-clusters along the M tiles (an odd tile count gets one idle partner: rows >= M gather zeros, store nothing)
-template <int NT, int STAGES, int MINB>
-int launch_fwd_pair(const JpbConvArgs* a, const CUtensorMap& half_map, cudaStream_t st) {
-  const int smem = STAGES * (A_STAGE + (NT / 2) * BK * 4) + 1024 + 256 + a->ntaps * a->nsrc * BM * 4;
+template <int NT, int STAGES, int MINB, bool ROWS = false>
+int launch_fwd_pair(const JpbConvArgs* a, const CUtensorMap& half_map, cudaStream_t st, const WgradRowMaps* xmaps = nullptr) {
+  const int smem = STAGES * (A_STAGE + (NT / 2) * BK * 4) + 1024 + 256 + (ROWS ? 0 : a->ntaps * a->nsrc * BM * 4);
   static int configured = 0;
   if (smem > 227 * 1024) return JPB_ERR_UNSUPPORTED;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES, MINB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel<NT, STAGES, MINB, 2, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return JPB_ERR_UNSUPPORTED;
     configured = smem;
   }
-  const int M = a->B * a->Ho * a->Wo;
+  const int M = a->B * a->Ho * (ROWS ? a->rows_wv : a->Wo);
   const int mt = (M + BM - 1) / BM;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((mt + 1) & ~1, (a->N + NT - 1) / NT, a->ksplit > 1 ? a->ksplit : 1);
@@ -1735,7 +1735,8 @@ int launch_fwd_pair(const JpbConvArgs* a, const CUtensorMap& half_map, cudaStrea
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, conv_tc_fwd_kernel<NT, STAGES, MINB, 2>, half_map, no_row_maps(), *a) != cudaSuccess) return jpb_status() ? jpb_status() : JPB_ERR_UNSUPPORTED;
+  if (cudaLaunchKernelEx(&cfg, conv_tc_fwd_kernel<NT, STAGES, MINB, 2, ROWS>, half_map, xmaps ? *xmaps : no_row_maps(), *a) != cudaSuccess)
+    return jpb_status() ? jpb_status() : JPB_ERR_UNSUPPORTED;
   return jpb_status();
 }
 
@@ -1893,6 +1894,15 @@ extern "C" int jpb_conv2d_fwd(const JpbConvArgs* a, void* stream) {
     const int rc = fwd_row_maps(a, enc, &xm);
     if (rc != JPB_OK) return rc;
     const long long tiles = (long long)((a->B * a->Ho * a->rows_wv + BM - 1) / BM) * ((a->N + nt - 1) / nt) * (a->ksplit > 1 ? a->ksplit : 1);
+    if (conv_pair() && nt == 256 && tiles > 148) {
+      // CTA pairs on top of the TMA-row operand (opt-in, JPB_CONV_PAIR): each CTA streams half of the weight tile, three stages
+      CUtensorMap hmap;
+      const cuuint32_t hbox[2] = {(cuuint32_t)BK, 128u};
+      if (enc(&hmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a->weight), gdim, gstr, hbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return JPB_ERR_ARG;
+      return launch_fwd_pair<256, 3, 2, true>(a, hmap, st, &xm);
+    }
     switch (nt) {
       case 64: return launch_fwd<64, 4, 2, true>(a, map, st, &xm);
       case 128: return tiles > 148 ? launch_fwd<128, 3, 2, true>(a, map, st, &xm) : launch_fwd<128, 5, 1, true>(a, map, st, &xm);
