@@ -309,9 +309,13 @@ int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const floa
 
 /* ---- NHWC max pooling (nn.MaxPool2d(k, s, p); layers.py:191, resnet.py:91, layout_model.py:84) --------------
  * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.
- * Backward: gx must be ZERO-FILLED by the caller (overlapping windows are scattered with red.global.add).      */
+ * Backward: the caller need not zero-fill gx.                                                                   */
 int jpb_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, int k, int s, int p, void* stream);
 int jpb_maxpool_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, int k, int s, int p, void* stream);
+/* Backward schedule: 0 = default (5x5 / stride 1: scatter with red.global.add over a gx the call clears itself; every other
+ * geometry: gather, gx written once per element); 1 = scatter for every overlapping window (round 1); 2 = 5x5 as a gather
+ * (deterministic; measured slower).  Process-wide.                                                              */
+int jpb_maxpool_set_bwd_variant(int variant);
 
 /* ---- flat-buffer optimizer step (mono/core/utils/dist_utils.py:34-60 + torch.optim.Adam) ---------
  * jpb_sumsq: acc[0] += sum g^2 (run on the all-reduced SUM of gradients).

@@ -189,6 +189,7 @@ class _Signatures:
     jpb_bn_eval_fwd = [P, P, P, P, P, I, P, C.c_longlong, I, V]
     jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, I, P, C.c_longlong, I, V]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
+    jpb_maxpool_set_bwd_variant = [I]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]
     jpb_depth_eval = [C.POINTER(DepthEvalArgs), V]
     jpb_resize_lanczos_u8 = [C.POINTER(ResizeArgs), V]

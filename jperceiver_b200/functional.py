@@ -410,7 +410,7 @@ class _MaxPool(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         B, H, W, Cc, k, s, p = ctx.geom
         gy = gy if gy.is_contiguous(memory_format=torch.channels_last) else gy.contiguous(memory_format=torch.channels_last)
-        gx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=gy.device, memory_format=torch.channels_last).zero_()
+        gx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=gy.device, memory_format=torch.channels_last)   # written once per element
         check(_launch("maxpool_bwd", gy, lambda: _lib.lib().jpb_maxpool_bwd(ptr(gy), ptr(idx), ptr(gx), B, H, W, Cc, k, s, p, stream_of(gy))),
               "jpb_maxpool_bwd")
         return gx, None, None, None

@@ -413,7 +413,7 @@ def test_photometric_backward_schedules_agree_full_size(s):
         assert (b - r.grad).abs().max().item() <= max(1.25 * (a - r.grad).abs().max().item(), 2e-3 * r.grad.abs().max().item())
 
 
-@pytest.mark.parametrize("k,s,p,H,W,C", [(5, 1, 2, 12, 20, 8), (3, 2, 1, 16, 24, 16), (2, 2, 0, 8, 8, 128), (3, 2, 1, 15, 21, 4)])
+@pytest.mark.parametrize("k,s,p,H,W,C", [(5, 1, 2, 12, 20, 8), (5, 1, 2, 45, 9, 4), (3, 2, 1, 16, 24, 16), (2, 2, 0, 8, 8, 128), (3, 2, 1, 15, 21, 4)])
 def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
     g = torch.Generator().manual_seed(4)
     x = torch.randn(2, C, H, W, generator=g)
@@ -428,6 +428,30 @@ def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
     got.backward(D(gy, dev))
     # overlapping windows accumulate by atomics: summation order differs from ATen's
     assert (x1.grad.cpu() - x0.grad).abs().max().item() <= 1e-5 * max(1.0, x0.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_maxpool_backward_schedules(dev, variant):
+    """jpb_maxpool_set_bwd_variant: scatter for every overlapping window (1) and the deterministic 5x5 gather (2) give the
+    gradients of the default schedule (5x5 scatter, 3x3 / stride 2 gather)."""
+    g = torch.Generator().manual_seed(8)
+    res = {}
+    try:
+        for v in (0, variant):
+            _lib.check(_lib.lib().jpb_maxpool_set_bwd_variant(v), "jpb_maxpool_set_bwd_variant")
+            out = []
+            for k, s, p, H, W, C in [(5, 1, 2, 23, 17, 8), (3, 2, 1, 16, 24, 16)]:
+                gg = torch.Generator().manual_seed(k)
+                x = D(torch.randn(2, C, H, W, generator=gg), dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+                y = JF.maxpool(x, k, s, p)
+                y.backward(D(torch.randn(y.shape, generator=gg), dev))
+                out.append(x.grad.cpu())
+            res[v] = out
+    finally:
+        _lib.check(_lib.lib().jpb_maxpool_set_bwd_variant(0), "jpb_maxpool_set_bwd_variant")
+    for a, b in zip(res[0], res[variant]):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item())
+    assert _lib.lib().jpb_maxpool_set_bwd_variant(7) != 0
 
 
 @pytest.mark.parametrize("C,N,up,reflect,act", [(256, 1, 1, 1, "sigmoid"), (16, 2, 0, 1, "none"), (32, 2, 0, 0, "leaky"), (64, 1, 1, 0, "none")])
