@@ -30,6 +30,7 @@ print("tf32 cuBLAS peak %.0f TFLOP/s, hbm %.0f GB/s" % (args.tf32_peak, pk["hbm_
 opt = bench.model_options(bench.CONFIGS["C2"], args.batch)
 torch.manual_seed(1024)
 model = MONO.module_dict["Baseline"](opt).to(dev).train()
+model.branch_streams = False          # one stream: the per-call event pairs must not overlap other trunks' kernels
 engine = TrainEngine(model)
 data = change_input_variable(synthetic.make_batch(opt, args.batch, seed=1024, pin=True), dev)
 for _ in range(3):
