@@ -218,6 +218,9 @@ typedef struct JpbConvArgs {
                                            Wo == Win.  2 = one deep CTA per SM for the 256-wide tiles                                         */
   int rows_wv;                          /* rows != 0: row length of the tile raster, a multiple of 32 and >= Wo; pixels Wo .. rows_wv - 1 of a
                                            row are computed and dropped (data gradient of reflection-padded layers: Wo = W + 2)              */
+  int dst_mul, dst_oy, dst_ox;          /* scatter: dst_mul > 1 writes output pixel (ty, tx) to (ty * dst_mul + dst_oy, tx * dst_mul + dst_ox) —
+                                           one parity class of the data gradient of a stride-2 convolution per launch (4x fewer taps in
+                                           all than the zero-stuffed form in_div = 2)                                                        */
 } JpbConvArgs;
 #define JPB_TF32_TRUNC_COMP 1.00067702f  /* 1 + 2 * 2^-11 * ln 2 */
 int jpb_conv2d_fwd(const JpbConvArgs* args, void* stream);

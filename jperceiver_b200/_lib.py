@@ -83,6 +83,7 @@ class ConvArgs(C.Structure):
         ("ntaps", C.c_int), ("kw", C.c_int), ("ksplit", C.c_int), ("kcol", C.c_void_p), ("l1_gather", C.c_int),
         ("dbg", C.c_void_p), ("dbg_skip", C.c_int), ("stats", C.c_void_p), ("acc_scale", C.c_float), ("patch", C.c_int), ("patch_ntaps", C.c_int), ("patch_halo", C.c_int), ("patch_org_y", C.c_int),
         ("patch_org_x", C.c_int), ("patch_tapoff", C.c_int * 16), ("patch_desc_mode", C.c_int), ("rows", C.c_int), ("rows_wv", C.c_int),
+        ("dst_mul", C.c_int), ("dst_oy", C.c_int), ("dst_ox", C.c_int),
     ]
 
 

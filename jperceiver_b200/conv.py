@@ -304,6 +304,67 @@ def act_bwd(gy, y, act, want_bias, bias_target=None):
     return (dz if need_dz else gy), gb
 
 
+S2_CLASSES = int(_os.environ.get("JPB_DGRAD_S2_CLASSES", "1"))   # 0: zero-stuffed stride-2 data gradient (in_div = 2) everywhere
+S2_MIN_PIXELS = int(_os.environ.get("JPB_DGRAD_S2_MIN_PIXELS", "16384"))   # below: four latency-sized launches cost more than the 27 zero taps
+_S2_TABLES: dict = {}
+
+
+def _s2_class_table(Nc, cy, cx, device):
+    """(table, kcol, kh_c, kw_c) of parity class (cy, cx) of the data gradient of a 3x3 / stride-2 / pad-1 convolution: input-gradient
+    pixels (2i + cy, 2j + cx) only see the flipped taps ky' in ({1}, {0, 2})[cy], kx' likewise; as a (1 + cy) x (1 + cx) stride-1
+    convolution over dz reading dz[i + ty, j + tx] (zero outside).  ``kcol``: column of each K block in the full flipped /
+    transposed weight matrix [Cin][9 * Nc]."""
+    key = (Nc, cy, cx, str(device))
+    r = _S2_TABLES.get(key)
+    if r is None:
+        kh_c, kw_c = 1 + cy, 1 + cx
+        rows, kcol = [], []
+        for ty in range(kh_c):
+            for tx in range(kw_c):
+                t = ty * kw_c + tx
+                kyf, kxf = (2 * ty if cy else 1), (2 * tx if cx else 1)
+                for cb in range(0, Nc, 32):
+                    kcol.append((kyf * 3 + kxf) * Nc + cb)
+                    for coff in range(cb, cb + 32, 4):
+                        rows.append((0 | (t << 8), (ty << 16) | tx, coff, 16))
+        r = _S2_TABLES[key] = (torch.tensor(rows, dtype=torch.int32, device=device).contiguous(),
+                               torch.tensor(kcol, dtype=torch.int32, device=device).contiguous(), kh_c, kw_c)
+    return r
+
+
+def _dgrad_s2_classes(dz, wmat, wcols, Cin, x, B, Ho, Wo, H, W):
+    """Data gradient of a 3x3 / stride-2 / pad-1 convolution as four parity-class launches (9 taps in all instead of 36 zero-stuffed
+    ones); every element of the gradient is written exactly once."""
+    Nc = dz.shape[1]
+    dev = dz.device
+    grad = torch.empty_like(x, memory_format=CL)
+    for cy in (0, 1):
+        for cx in (0, 1):
+            table, kcol, kh_c, kw_c = _s2_class_table(Nc, cy, cx, dev)
+            a = _lib.ConvArgs()
+            a.src[0] = ptr(dz)
+            a.src_C[0], a.src_H[0], a.src_W[0], a.src_up[0] = Nc, Ho, Wo, 0
+            a.nsrc = 1
+            a.B, a.Hin, a.Win = B, Ho, Wo
+            a.Ho, a.Wo, a.N = H // 2, W // 2, Cin
+            a.stride, a.pad, a.reflect = 1, 0, 0
+            a.weight, a.w_row, a.w_cols = ptr(wmat), wmat.stride(0), wcols
+            a.table, a.nkb = ptr(table), table.shape[0] // 8
+            a.ntaps, a.kw = kh_c * kw_c, kw_c
+            a.kcol = ptr(kcol)
+            a.acc_scale = _acc_scale()
+            a.scatter, a.ndst = 1, 1
+            a.dst[0] = ptr(grad)
+            a.dst_C[0], a.dst_H[0], a.dst_W[0], a.dst_up[0] = Cin, H, W, 0
+            a.fold_H, a.fold_W = H // 2, W // 2
+            a.dst_mul, a.dst_oy, a.dst_ox = 2, cy, cx
+            if FWD_ROWS and Nc % 32 == 0 and Cin > 32 and (W // 2) % 32 == 0:
+                a.rows, a.rows_wv = FWD_ROWS, W // 2
+            tag = (B * (H // 2) * (W // 2), Cin, table.shape[0] * 4, 3, 2, (Cin,), (0,), 0, 1)
+            check(_launch("conv_dgrad", dz, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_fwd(dgrad, stride-2 class)")
+    return [grad]
+
+
 def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     """Gradients w.r.t. the forward sources, through the forward kernel run on dz with the flipped/transposed weights."""
     N, Cin, kh, kw = weight.shape
@@ -318,6 +379,12 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
         wT = weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=CL)   # [Cin][kh][kw][Cout]
         if Nc == N and N % 4 == 0 and weight.is_contiguous(memory_format=CL):
             WT.register(weight)
+    if (S2_CLASSES and not three and stride == 2 and kh == 3 and kw == 3 and pad == 1 and not reflect and len(xs) == 1 and not ups[0]
+            and xs[0].shape[1] == Cin and Nc % 32 == 0 and Cin % 4 == 0 and H % 2 == 0 and W % 2 == 0 and Ho == H // 2 and Wo == W // 2
+            and B * H * W >= S2_MIN_PIXELS):
+        wmat_c, wcols_c = gemm_weight(wT, [Nc], [N])
+        if wcols_c == 9 * Nc:
+            return _dgrad_s2_classes(dz, wmat_c, wcols_c, Cin, xs[0], B, Ho, Wo, H, W)
     if three:
         dz_k = tf32_split(dz)                           # [B, 2*Nc, Ho, Wo]: hi | lo halves of every pixel
         wmat, wcols = gemm_weight3(wT, [Nc], [N])

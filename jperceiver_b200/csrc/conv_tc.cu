@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(192, MINB) conv_tc_fwd_kernel(const __grid_con
         if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
         atomic = split || a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
         if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
+        if (a.dst_mul > 1) { ty = ty * a.dst_mul + a.dst_oy; tx = tx * a.dst_mul + a.dst_ox; }   // one parity class of a stride-2 data gradient
         out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
       }
     }
@@ -1049,6 +1050,7 @@ __global__ void __launch_bounds__(320, MINB) conv_tc_fwd2_kernel(const __grid_co
           if (a.fold_reflect) { ty = jpb_reflect(ty, a.fold_H); tx = jpb_reflect(tx, a.fold_W); }
           atomic = split || a.dst_up[j] || (a.fold_reflect && (ty <= 1 || ty >= a.fold_H - 2 || tx <= 1 || tx >= a.fold_W - 2));
           if (a.dst_up[j]) { ty >>= 1; tx >>= 1; }
+          if (a.dst_mul > 1) { ty = ty * a.dst_mul + a.dst_oy; tx = tx * a.dst_mul + a.dst_ox; }   // one parity class of a stride-2 data gradient
           out = a.dst[j] + ((size_t)(b * a.dst_H[j] + ty) * a.dst_W[j] + tx) * a.dst_C[j] + (n0 - cbase);
         }
       }

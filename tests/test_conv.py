@@ -19,6 +19,7 @@ from emu.torch_ops import torch_conv  # noqa: E402
 from jperceiver_b200 import conv as JC
 
 pytestmark = pytest.mark.gpu
+JC.S2_MIN_PIXELS = 0          # the stride-2 parity-class data gradient at every test extent (the library only takes it for large layers)
 CL = torch.channels_last
 
 
@@ -54,6 +55,10 @@ CASES = [
     ("rows: refl 3x3 cat(64, up64, 1)->128 leaky @16x256", [(64, 16, 256, 0), (64, 8, 128, 1), (1, 16, 256, 0)], 128, 3, 1, 1, 1, "leaky", 1, 0),
     ("rows: 1x1 64->128 + residual @15x96", [(64, 15, 96, 0)], 128, 1, 1, 0, 0, "none", 0, 1),
     ("rows: 3x3 cat(64, 64)->64 relu @16x64", [(64, 16, 64, 0), (64, 16, 64, 0)], 64, 3, 1, 1, 0, "relu", 1, 0),
+    # data gradient of 3x3 / stride-2 layers as four parity-class launches (conv.py: _dgrad_s2_classes): TMA rows (W / 2 = 64) and
+    # the gather kernels (W / 2 = 40, pose extent)
+    ("s2 classes: layer3.0 3x3 s2 128->256 @40x128", [(128, 40, 128, 0)], 256, 3, 2, 1, 0, "none", 0, 0),
+    ("s2 classes: pose layer2.0 3x3 s2 64->128 @48x80", [(64, 48, 80, 0)], 128, 3, 2, 1, 0, "none", 0, 0),
 ]
 
 
