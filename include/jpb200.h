@@ -308,7 +308,9 @@ int jpb_bn_train_fwd(const float* x, const float* res, const float* gamma, const
 int jpb_bn_eval_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* stat, int relu, float* y,
                     long long rows, int C, void* stream);
 int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
-                     float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream);
+                     float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream,
+                     const float* beta /* relu != 0 with y == NULL (BatchNorm + ReLU without residual): the mask y > 0 is re-derived from
+                                          x, bit for bit, instead of reading y back; otherwise unused and may be NULL */);
 
 /* ---- NHWC max pooling (nn.MaxPool2d(k, s, p); layers.py:191, resnet.py:91, layout_model.py:84) --------------
  * idx: window-relative arg-max (ky*k + kx) per output element, first maximum wins; C % 4 == 0.

@@ -188,7 +188,7 @@ class _Signatures:
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_bn_train_fwd = [P, P, P, P, P, P, P, I, F, F, I, P, P, P, C.c_longlong, I, I, V]
     jpb_bn_eval_fwd = [P, P, P, P, P, I, P, C.c_longlong, I, V]
-    jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, I, P, C.c_longlong, I, V]
+    jpb_bn_train_bwd = [P, P, P, P, P, I, P, P, P, P, I, P, C.c_longlong, I, V, P]
     jpb_maxpool_bwd = [P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_set_bwd_variant = [I]
     jpb_adam_step = [P, P, P, P, C.c_longlong, C.POINTER(AdamArgs), V]

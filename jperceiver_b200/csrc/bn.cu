@@ -21,6 +21,13 @@ __device__ __forceinline__ int* bn_ticket(double* ws) { return reinterpret_cast<
 __device__ __forceinline__ double* bn_sums(double* ws) { return ws + 2; }
 __device__ __forceinline__ double* bn_running(double* ws) { return ws + 2 + 2 * BN_MAX_C; }
 
+// y = (x - mean) * rstd * gamma + beta with a FIXED rounding sequence (sub, mul, fma): the backward pass re-derives the ReLU mask of
+// a BatchNorm without residual from x instead of reading y back (two of its seven passes), which only works if forward and backward
+// round identically whatever the compiler would contract.
+__device__ __forceinline__ float bn_affine(float x, float mean, float rstd, float g, float b) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), g, b);
+}
+
 struct BnTail {   // what the last block to finish does after folding the partials (one launch instead of three)
   long long rows;
   float eps, momentum;
@@ -41,7 +48,7 @@ struct BnTail {   // what the last block to finish does after folding the partia
 // MODE 0: (x, x*x)    MODE 1: (g, g*xhat) with g = dy*[y>0 or no relu], xhat = (x-mean)*rstd
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const float* dy, const float* y, const float* stat, long long rows,
-                                                       int C, int relu, double* ws, BnTail tail) {
+                                                       int C, int relu, double* ws, BnTail tail, const float* gamma, const float* beta) {
   JPB_DYN_SMEM(float, part);   // [8][256]
   __shared__ int s_last;
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
@@ -59,8 +66,12 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
       if (c4 < C4) {
         float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
-        if (MODE == 1)
+        float gam[4] = {1.f, 1.f, 1.f, 1.f}, bet[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MODE == 1) {
           for (int k = 0; k < 4; ++k) { mean[k] = stat[c4 * 4 + k]; rstd[k] = stat[C + c4 * 4 + k]; }
+          if (relu && !y)
+            for (int k = 0; k < 4; ++k) { gam[k] = gamma[c4 * 4 + k]; bet[k] = beta[c4 * 4 + k]; }
+        }
 #pragma unroll 8
         for (long long r = r0 + lr; r < r1; r += lanes_r) {
           const long long i = r * C + c4 * 4;
@@ -74,11 +85,16 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* x, const fl
             float g[4] = {gv.x, gv.y, gv.z, gv.w};
             const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
             if (relu) {
-              const float4 yv = *reinterpret_cast<const float4*>(y + i);
-              if (!(yv.x > 0.f)) g[0] = 0.f;
-              if (!(yv.y > 0.f)) g[1] = 0.f;
-              if (!(yv.z > 0.f)) g[2] = 0.f;
-              if (!(yv.w > 0.f)) g[3] = 0.f;
+              if (y) {
+                const float4 yv = *reinterpret_cast<const float4*>(y + i);
+                if (!(yv.x > 0.f)) g[0] = 0.f;
+                if (!(yv.y > 0.f)) g[1] = 0.f;
+                if (!(yv.z > 0.f)) g[2] = 0.f;
+                if (!(yv.w > 0.f)) g[3] = 0.f;
+              } else {            // no residual: the forward's y > 0 is bn_affine(x) > 0, bit for bit
+                for (int k = 0; k < 4; ++k)
+                  if (!(bn_affine(xs[k], mean[k], rstd[k], gam[k], bet[k]) > 0.f)) g[k] = 0.f;
+              }
             }
             for (int k = 0; k < 4; ++k) { s1[k] += g[k]; s2[k] += g[k] * ((xs[k] - mean[k]) * rstd[k]); }
           }
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const flo
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (res) { const float4 q = *reinterpret_cast<const float4*>(res + i * 4); r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
     for (int k = 0; k < 4; ++k) {
-      float t = (o[k] - stat[c + k]) * stat[C + c + k] * gamma[c + k] + beta[c + k] + r[k];
+      float t = bn_affine(o[k], stat[c + k], stat[C + c + k], gamma[c + k], beta[c + k]) + r[k];
       if (relu && !(t > 0.f)) t = 0.f;
       o[k] = t;
     }
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(256) bn_apply_from_sums_kernel(const float* x,
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (res) { const float4 q = *reinterpret_cast<const float4*>(res + i * 4); r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
     for (int k = 0; k < 4; ++k) {
-      float t = (o[k] - sstat[c + k]) * sstat[C + c + k] * gamma[c + k] + beta[c + k] + r[k];
+      float t = bn_affine(o[k], sstat[c + k], sstat[C + c + k], gamma[c + k], beta[c + k]) + r[k];
       if (relu && !(t > 0.f)) t = 0.f;
       o[k] = t;
     }
@@ -210,7 +226,8 @@ __global__ void __launch_bounds__(256) bn_apply_from_sums_kernel(const float* x,
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* x, const float* dy, const float* y, const float* stat, const float* gamma,
-                                                          const double* acc, float* dx, float* dres, long long rows, long long n4, int C, int relu) {
+                                                          const double* acc, float* dx, float* dres, long long rows, long long n4, int C, int relu,
+                                                          const float* beta) {
   const double inv_n = 1.0 / (double)rows;
   for (long long i = (long long)blockIdx.x * JPB_NT + JPB_TID; i < n4; i += (long long)gridDim.x * JPB_NT) {
     const int c = (int)((i * 4) % C);
@@ -218,11 +235,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* x, const
     const float4 gv = *reinterpret_cast<const float4*>(dy + i * 4);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, g[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
     if (relu) {
-      const float4 yv = *reinterpret_cast<const float4*>(y + i * 4);
-      if (!(yv.x > 0.f)) g[0] = 0.f;
-      if (!(yv.y > 0.f)) g[1] = 0.f;
-      if (!(yv.z > 0.f)) g[2] = 0.f;
-      if (!(yv.w > 0.f)) g[3] = 0.f;
+      if (y) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + i * 4);
+        if (!(yv.x > 0.f)) g[0] = 0.f;
+        if (!(yv.y > 0.f)) g[1] = 0.f;
+        if (!(yv.z > 0.f)) g[2] = 0.f;
+        if (!(yv.w > 0.f)) g[3] = 0.f;
+      } else {
+        for (int k = 0; k < 4; ++k)
+          if (!(bn_affine(xs[k], stat[c + k], stat[C + c + k], gamma[c + k], beta[c + k]) > 0.f)) g[k] = 0.f;
+      }
     }
     for (int k = 0; k < 4; ++k) {
       const float mean = stat[c + k], rstd = stat[C + c + k];
@@ -271,7 +293,7 @@ extern "C" int jpb_bn_train_fwd(const float* x, const float* res, const float* g
                relu, ws, t);
     return jpb_status();
   }
-  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, ws, t);
+  JPB_LAUNCH(bn_colsum_kernel<0>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, nullptr, nullptr, nullptr, rows, C, 0, ws, t, nullptr, nullptr);
   const long long n4 = rows * C / 4;
   JPB_LAUNCH(bn_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, res, stat, gamma, beta, y, n4, C, relu);
   return jpb_status();
@@ -286,14 +308,16 @@ extern "C" int jpb_bn_eval_fwd(const float* x, const float* res, const float* ga
 }
 
 extern "C" int jpb_bn_train_bwd(const float* x, const float* dy, const float* y, const float* stat, const float* gamma, int relu, float* dx,
-                                float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream) {
-  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !ws || (relu && !y) || (C & 3) || C > BN_MAX_C) return JPB_ERR_ARG;
+                                float* dres, float* dgamma, float* dbeta, int accumulate, double* ws, long long rows, int C, void* stream,
+                                const float* beta) {
+  // relu without y: the mask is re-derived from x (BatchNorm + ReLU WITHOUT residual only; needs beta)
+  if (!x || !dy || !stat || !gamma || !dx || !dgamma || !dbeta || !ws || (relu && !y && (!beta || dres)) || (C & 3) || C > BN_MAX_C) return JPB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned nb = bn_colsum_grid(rows, C);
   BnTail t = {};
   t.rows = rows; t.dgamma = dgamma; t.dbeta = dbeta; t.accumulate = accumulate;
-  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, ws, t);
+  JPB_LAUNCH(bn_colsum_kernel<1>, dim3(nb), dim3(256), 8 * 256 * sizeof(float), st, x, dy, y, stat, rows, C, relu, ws, t, gamma, beta);
   const long long n4 = rows * C / 4;
-  JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, ws + 2, dx, dres, rows, n4, C, relu);
+  JPB_LAUNCH(bn_bwd_apply_kernel, dim3(bn_grid(n4, 256 * 4, 148 * 8)), dim3(256), 0, st, x, dy, y, stat, gamma, ws + 2, dx, dres, rows, n4, C, relu, beta);
   return jpb_status();
 }

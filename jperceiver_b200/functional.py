@@ -474,7 +474,9 @@ class _BNTrain(torch.autograd.Function):
             ptr(x), ptr(res), ptr(gamma.detach()), ptr(beta.detach()), ptr(running_mean), ptr(running_var),
             ptr(nbt) if nbt is not None else None, int(nbt_inc), float(momentum), float(eps),
             int(relu), ptr(y), ptr(stat), ptr(ws), rows, Cc, int(stats_ready), stream_of(x))), "jpb_bn_train_fwd")
-        ctx.save_for_backward(x, y if relu else None, stat, gamma, beta)
+        # BatchNorm + ReLU without residual: the backward re-derives the mask y > 0 from x (bit-exact: csrc/bn.cu bn_affine) instead of
+        # reading y back in both of its passes
+        ctx.save_for_backward(x, y if (relu and res is not None) else None, stat, gamma, beta)
         ctx.cfg = (rows, Cc, int(relu), res is not None)
         return y
 
@@ -492,7 +494,7 @@ class _BNTrain(torch.autograd.Function):
         ws = _bn_workspace(Cc, x.device)
         check(_launch("bn_bwd", x, lambda: _lib.lib().jpb_bn_train_bwd(
             ptr(x), ptr(gy), ptr(y), ptr(stat), ptr(gamma.detach()), relu, ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta), int(direct),
-            ptr(ws), rows, Cc, stream_of(x))), "jpb_bn_train_bwd")
+            ptr(ws), rows, Cc, stream_of(x), ptr(beta.detach()))), "jpb_bn_train_bwd")
         if has_res and not relu:
             dres = gy
         if direct:
