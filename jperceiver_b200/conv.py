@@ -459,6 +459,7 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
     return grads
 
 
+WGRAD_SLOTS = int(_os.environ.get("JPB_WGRAD_SLOTS", "222"))   # CTAs a weight-gradient launch is split into (pixel ranges x K tiles x N tiles)
 WGRAD_ROWS = int(_os.environ.get("JPB_WGRAD_ROWS", "1"))     # 0: always the gathered operand (A/B measurements); 2: deep CTAs for N tile 256
 _ROW_TABLES: dict = {}
 
@@ -582,7 +583,7 @@ def conv_wgrad(dz, weight, xs, ups, stride, pad, reflect, dbg=None, target=None,
         nt *= 2
     tiles = ((table.shape[0] + 31) // 32) * ((Nc + nt - 1) // nt)
     steps = (B * Ho * Wo + 31) // 32
-    a.splits = max(1, min(steps, (2 * 148 + tiles - 1) // tiles))
+    a.splits = max(1, min(steps, (WGRAD_SLOTS + tiles - 1) // tiles))
     if dbg is not None:
         a.dbg = ptr(dbg)
     tag = (B * Ho * Wo, Nc, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), a.splits)
