@@ -440,9 +440,29 @@ class TrainEngine:
         self._static_out = None
         self._stage = None
 
+    def _refresh_host_caches(self, data):
+        """Host-side caches whose device buffers were baked into the captured graph: the static scale label's quad mask is
+        rasterised on the host from sample 0's calibration (net.py:292-306).  When a replayed batch carries a different
+        calibration (KITTI-Odometry sequences differ in K / Tr) the mask is rasterised again INTO THE SAME device buffer, so the
+        graph reads the right one; batches without the host copies (``("_host", name)``) are taken to share the captured
+        calibration."""
+        model = self.model
+        cache = getattr(model, "_quad_cache", None)
+        hK, hT = data.get(("_host", "odometry_K")), data.get(("_host", "Tr_cam2_velo"))
+        if not cache or hK is None or hT is None:
+            return
+        (key, buf), = cache.items()
+        new = (hK[0].numpy().tobytes(), hT[0].numpy().tobytes(), key[2], key[3])
+        if new != key:
+            from ..model.mono_baseline.net import static_quad_mask_host
+            m = static_quad_mask_host(hK[0].numpy(), hT[0].numpy(), model.opt.split, model.opt.occ_map_size, key[2], key[3])
+            buf.copy_(torch.from_numpy(m).to(buf.dtype), non_blocking=False)
+            model._quad_cache = {new: buf}
+
     def replay(self, data=None):
         """Run the captured step; ``data`` (device or pinned-host tensors) is copied into the static inputs first."""
         if data is not None:
+            self._refresh_host_caches(data)
             for k, v in data.items():
                 dst = self._static_in.get(k)
                 if torch.is_tensor(dst) and dst.is_cuda and torch.is_tensor(v) and v is not dst:
@@ -463,12 +483,15 @@ class TrainEngine:
         cur = torch.cuda.current_stream()
         if self._staged_event is None:
             self._stage_batch(next_batch, after=None)
+            self._staged_batch = next_batch
         cur.wait_event(self._staged_event)
+        self._refresh_host_caches(self._staged_batch)        # the batch that runs now is the one staged by the previous call
         for k, st in self._stage.items():
             self._static_in[k].copy_(st, non_blocking=True)
         moved = torch.cuda.Event()
         moved.record(cur)
         self._stage_batch(next_batch, after=moved)
+        self._staged_batch = next_batch
         self._graph.replay()
         return self._static_out
 

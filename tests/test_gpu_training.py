@@ -214,3 +214,48 @@ def test_train_mono_runner_checkpoint_resume_eval_on_cuda(tmp_path):
     assert ck3["meta"]["epoch"] == 3 and ck3["meta"]["iter"] == 12
     assert bool(torch.isfinite(engine2.flat.param).all().item())
     assert not torch.equal(engine2.flat.param, params_after)
+
+
+def test_graph_replay_follows_a_changed_calibration():
+    """The static scale label's quad mask is rasterised on the host from sample 0's calibration and its device buffer is baked into
+    the captured step graph: replaying a batch with a DIFFERENT calibration must refresh that buffer (TrainEngine.
+    _refresh_host_caches) — the scale loss of the replay equals the eager step's on the same batch."""
+    import bench
+    from jperceiver_b200 import synthetic
+    from jperceiver_b200.apis import TrainEngine, change_input_variable
+    from jperceiver_b200.model import MONO
+    dev = torch.device("cuda:0")
+    opt = bench.model_options(dict(bench.CONFIGS["C2"], H=192, W=640), 1)
+    losses = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(3)
+        model = MONO.module_dict["Baseline"](opt).to(dev).train()
+        model.DepthDecoder.drop_p = 0.0                        # same disparities in both runs whatever the step counter
+        model.noise_scale = 0.0
+        engine = TrainEngine(model, dict(type="Adam", lr=0.0, weight_decay=0), dict(max_norm=35, norm_type=2))
+        a = synthetic.make_batch(opt, 1, seed=5, pin=True)
+        b = synthetic.make_batch(opt, 1, seed=5, pin=True)
+        for k in (("odometry_K", 0, 0), ("Tr_cam2_velo", 0, 0)):
+            b[k] = b[k].clone()
+        b[("odometry_K", 0, 0)][..., 0, 0] *= 1.15            # another sequence: different focal length / lever arm
+        b[("Tr_cam2_velo", 0, 0)][..., 0, 3] += 0.35
+        da, db = change_input_variable(a, dev), change_input_variable(b, dev)
+        if mode == "eager":
+            engine.step(da, need_log=True)
+            out = engine.step(db, need_log=True)
+        else:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                engine.capture(da, warmup=3)
+                engine.replay(da)
+                out = engine.replay(db).clone()
+            side.synchronize()
+            engine.release_graph()
+        names = engine.last_names
+        losses[mode] = {n: float(v) for n, v in zip(names, out.detach().cpu())}
+    keys = [n for n in losses["eager"] if "scale" in str(n)]
+    assert keys
+    for n in keys:
+        e, g = losses["eager"][n], losses["graph"][n]
+        assert abs(e - g) <= 1e-4 * max(abs(e), 1e-6), (n, e, g)
