@@ -225,7 +225,7 @@ def test_graph_replay_follows_a_changed_calibration():
     from jperceiver_b200.apis import TrainEngine, change_input_variable
     from jperceiver_b200.model import MONO
     dev = torch.device("cuda:0")
-    opt = bench.model_options(dict(bench.CONFIGS["C2"], H=192, W=640), 1)
+    opt = bench.model_options(bench.CONFIGS["C2"], 1)          # 320x1024: the two calibrations below give different, non-empty masks
     losses = {}
     for mode in ("eager", "graph"):
         torch.manual_seed(3)
@@ -254,6 +254,12 @@ def test_graph_replay_follows_a_changed_calibration():
             engine.release_graph()
         names = engine.last_names
         losses[mode] = {n: float(v) for n, v in zip(names, out.detach().cpu())}
+    from jperceiver_b200.model.mono_baseline.net import static_quad_mask_host
+    K0, T0 = a[("odometry_K", 0, 0)][0].numpy(), a[("Tr_cam2_velo", 0, 0)][0].numpy()
+    K1, T1 = b[("odometry_K", 0, 0)][0].numpy(), b[("Tr_cam2_velo", 0, 0)][0].numpy()
+    m0 = static_quad_mask_host(K0, T0, opt["split"], opt["occ_map_size"], 320, 1024)
+    m1 = static_quad_mask_host(K1, T1, opt["split"], opt["occ_map_size"], 320, 1024)
+    assert m0.sum() > 0 and (m0 != m1).sum() > 0               # the case is not vacuous
     keys = [n for n in losses["eager"] if "scale" in str(n)]
     assert keys
     for n in keys:
