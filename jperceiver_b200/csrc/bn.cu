@@ -6,12 +6,20 @@
 //   backward: reduce  acc[c] += (sum g, sum g*xhat),  g = dy * [y > 0]  one pass over (dy, x, y)
 //             apply   dx = gamma*rstd*(g - s1/n - xhat*s2/n), dres = g   one pass
 // The library path needs separate kernels for BN, the add and the ReLU in each direction.
+#include <stdlib.h>
 #include "jpb_common.cuh"
 #include "../../include/jpb200.h"
 
 namespace {
 
-constexpr int BN_MAX_BLOCKS = 148 * 2;
+constexpr int BN_MAX_BLOCKS = 148 * 2;      // cap of the column-sum grids.  Measured on B200 (JPB_BN_BLOCKS): 592 blocks run the big layers 10-18 % faster in
+                                            // isolation (268 MB layout stem backward 388 -> 327 us) but the multi-stream step 1 % SLOWER (18.9 -> 19.1 ms): they
+                                            // take SMs from the convolutions running beside them
+inline int bn_max_blocks() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("JPB_BN_BLOCKS"); v = e ? atoi(e) : BN_MAX_BLOCKS; if (v < 1) v = BN_MAX_BLOCKS; }
+  return v;
+}
 
 constexpr int BN_MAX_C = 2048;
 // Workspace layout (jpb_bn_workspace_doubles): one int ticket counter in the first 16 bytes | final[2 * BN_MAX_C] column sums
@@ -262,7 +270,7 @@ inline unsigned bn_colsum_grid(long long rows, int C) {
   const int C4 = C >> 2, Ct = C4 < 256 ? C4 : 256;
   const int lanes_r = 256 / Ct > 0 ? 256 / Ct : 1;
   long long g = (rows + 4LL * lanes_r - 1) / (4LL * lanes_r);
-  if (g > BN_MAX_BLOCKS) g = BN_MAX_BLOCKS;
+  if (g > bn_max_blocks()) g = bn_max_blocks();
   return (unsigned)(g < 1 ? 1 : g);
 }
 
