@@ -450,9 +450,9 @@ def conv_dgrad(dz, weight, xs, ups, stride, pad, reflect, needs):
         a.nt = nt
     if (FWD_ROWS and not three and not a.patch and stride == 1 and Nc % 32 == 0 and Cin > 32 and (a.nt == 0 or a.nt >= 64)):
         # TMA-row operand (dz is one dense source): the tile raster's row length is the gradient domain's, rounded up to 32 pixels
-        # (reflection-padded layers: W + 2 -> the surplus pixels are computed and dropped) when that costs at most a quarter more
+        # (reflection-padded layers: W + 2 -> the surplus pixels are computed and dropped) when that costs at most half as much again (measured in the step: 125 / 150 / 200 percent -> 18.99 / 18.79 / 19.05 ms)
         wv = (a.Wo + 31) // 32 * 32
-        if wv * 4 <= a.Wo * 5:
+        if wv * 100 <= a.Wo * ROWS_WV_MAX:
             a.rows, a.rows_wv = FWD_ROWS, wv
     tag = (B * a.Ho * a.Wo, Cin, table.shape[0] * 4, kh, stride, tuple(src_C), tuple(int(u) for u in ups), int(bool(reflect)), ks)
     check(_launch("conv_dgrad", dz, lambda: _lib.lib().jpb_conv2d_fwd(C.byref(a), stream_of(dz)), tag), "jpb_conv2d_fwd(dgrad)")
@@ -473,6 +473,7 @@ def upsample2x(x):
     return y
 
 
+ROWS_WV_MAX = int(_os.environ.get("JPB_ROWS_WV_MAX", "150"))   # padded raster of a data gradient: at most this many percent of the real row length
 FWD_ROWS = int(_os.environ.get("JPB_FWD_ROWS", "1"))         # 0: gathered A operand in the forward / data-gradient kernels (A/B measurements)
 
 
