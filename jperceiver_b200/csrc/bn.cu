@@ -33,7 +33,15 @@ __device__ __forceinline__ double* bn_running(double* ws) { return ws + 2 + 2 * 
 // a BatchNorm without residual from x instead of reading y back (two of its seven passes), which only works if forward and backward
 // round identically whatever the compiler would contract.
 __device__ __forceinline__ float bn_affine(float x, float mean, float rstd, float g, float b) {
+#ifdef JPB_HOST_EMU
+  // host emulation: the unfused sequence of the CPU oracle (sub, mul, mul, add), so that the hard arg-max ties downstream
+  // (CCT attention) resolve as in the oracle; what matters for the mask is only that forward and backward share THIS function
+  volatile float t = (x - mean) * rstd;
+  volatile float u = t * g;
+  return u + b;
+#else
   return __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), g, b);
+#endif
 }
 
 struct BnTail {   // what the last block to finish does after folding the partials (one launch instead of three)
