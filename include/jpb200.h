@@ -280,6 +280,10 @@ int jpb_stem_s2d(const float* x, float* x3, int B, int H, int W, int Cp, void* s
 /* ---- nearest 2x up-sampling, NHWC: x [B,H,W,C] (C % 4 == 0) -> y [B,2H,2W,C]  (layers.py:16-19) */
 int jpb_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);
 
+/* ---- y = ((xs[0] + xs[1]) + xs[2]) + ...  over n <= 8 equally shaped tensors of `count` floats (count % 4 == 0, 16-byte aligned):
+ * the residual chain of a CRP block (layers.py:186-199) in one pass.  xs is a HOST array of device pointers.                    */
+int jpb_sum_n(const float* const* xs, int n, float* y, long long count, void* stream);
+
 /* ---- zero-padded channel copy: x [rows][C] -> y [rows][Cp], Cp % 4 == 0, Cp >= C */
 int jpb_pad_channels(const float* x, float* y, long long rows, int C, int Cp, void* stream);
 

@@ -183,6 +183,7 @@ class _Signatures:
     jpb_stem_s2d = [P, P, I, I, I, I, V]
     jpb_upsample2x = [P, P, I, I, I, I, V]
     jpb_pad_channels = [P, P, C.c_longlong, I, I, V]
+    jpb_sum_n = [P, I, P, C.c_longlong, V]
     jpb_conv3x3_smalln_fwd = [P, P, P, P, P, I, I, I, I, I, I, I, I, V]
     jpb_conv3x3_smalln_bwd = [P, P, P, P, P, P, I, I, I, I, I, I, I, V]
     jpb_maxpool_fwd = [P, P, P, I, I, I, I, I, I, I, V]

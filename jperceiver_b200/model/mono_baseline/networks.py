@@ -116,11 +116,13 @@ class DepthDecoder(nn.Module):
     @staticmethod
     def _crp(crp, x):
         top = x
+        terms = [x]
         for i in range(crp.n_stages):
             top = ops.maxpool(top, 5, 1, 2)
             top = ops.conv2d(top, getattr(crp, "%d_pointwise" % (i + 1)).conv.weight)
-            x = top + x
-        return x
+            terms.append(top)
+        # x = top_i + x after every stage (layers.py:197): (((x + t1) + t2) + t3) + t4, one pass instead of four
+        return ops.sum_n(terms)
 
     def forward(self, input_features, frame_id=0):
         l0, l1, l2, l3, l4 = input_features

@@ -77,6 +77,15 @@ def batchnorm(x, bn, training, *, relu=False, residual=None, momentum=0.1, eps=1
     return JF.batchnorm_eval(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, eps, relu)
 
 
+def sum_n(xs):
+    """Left-to-right sum of several equally shaped tensors in one pass (csrc/elementwise.cu: sum_n_kernel)."""
+    _need_cuda(xs[0])
+    from . import functional as JF
+    if xs[0].numel() % 4:
+        raise _lib.JpbError("sum_n kernel needs a multiple of 4 elements")
+    return JF.sum_n(list(xs))
+
+
 def maxpool(x, k, stride, pad):
     _need_cuda(x)
     if x.shape[1] % 4:

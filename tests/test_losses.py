@@ -430,6 +430,22 @@ def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
     assert (x1.grad.cpu() - x0.grad).abs().max().item() <= 1e-5 * max(1.0, x0.grad.abs().max().item())
 
 
+def test_sum_n_equals_the_chain_of_binary_adds(dev):
+    """jpb_sum_n (the residual chain of a CRP block, layers.py:186-199) is bit-identical to x + t1 + t2 + t3 + t4 evaluated left
+    to right, and passes the upstream gradient to every term."""
+    g = torch.Generator().manual_seed(12)
+    xs = [D(torch.randn(2, 8, 5, 6, generator=g) * 10 ** (k - 2), dev).contiguous(memory_format=torch.channels_last).requires_grad_(True) for k in range(5)]
+    y = JF.sum_n(xs)
+    ref = xs[0].detach()
+    for t in xs[1:]:
+        ref = t.detach() + ref
+    assert torch.equal(y.detach().cpu(), ref.cpu())
+    gy = D(torch.randn(2, 8, 5, 6, generator=g), dev)
+    y.backward(gy)
+    for t in xs:
+        assert torch.equal(t.grad.cpu(), gy.cpu())
+
+
 @pytest.mark.parametrize("variant", [1, 2])
 def test_maxpool_backward_schedules(dev, variant):
     """jpb_maxpool_set_bwd_variant: scatter for every overlapping window (1) and the deterministic 5x5 gather (2) give the
