@@ -430,6 +430,30 @@ def test_maxpool_forward_backward_vs_torch(dev, k, s, p, H, W, C):
     assert (x1.grad.cpu() - x0.grad).abs().max().item() <= 1e-5 * max(1.0, x0.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("C,act,want_bias", [(256, "leaky", True), (64, "relu", True), (1028, "sigmoid", True), (34, "leaky", True), (6, "relu", True),
+                                             (128, "none", True), (96, "leaky", False)])
+def test_act_bwd_vs_torch(dev, C, act, want_bias):
+    """jpb_act_bwd (backward of the convolution epilogue: dz = dy * act'(y) and the bias gradient) in its 16-byte form (C % 4 == 0,
+    C >= 32, incl. more than 256 channel groups), the scalar form (C = 34) and the narrow form (C = 6) against torch."""
+    from jperceiver_b200 import conv as JC
+    g = torch.Generator().manual_seed(C)
+    B, H, W = 2, 7, 9
+    z = torch.randn(B, C, H, W, generator=g)
+    y = {"leaky": torch.nn.functional.leaky_relu(z, 0.01), "relu": torch.relu(z), "sigmoid": torch.sigmoid(z), "none": z}[act]
+    gy = torch.randn(B, C, H, W, generator=g)
+    z0 = z.clone().requires_grad_(True)
+    y0 = {"leaky": torch.nn.functional.leaky_relu(z0, 0.01), "relu": torch.relu(z0), "sigmoid": torch.sigmoid(z0), "none": z0 * 1.0}[act]
+    y0.backward(gy)
+    cl = torch.channels_last
+    dz, gb = JC.act_bwd(D(gy, dev).contiguous(memory_format=cl), D(y, dev).contiguous(memory_format=cl), act, want_bias)
+    assert (dz.cpu() - z0.grad).abs().max().item() <= 1e-6 * max(1.0, z0.grad.abs().max().item())
+    if want_bias:
+        ref = z0.grad.sum((0, 2, 3))
+        assert (gb.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    else:
+        assert gb is None
+
+
 def test_sum_n_equals_the_chain_of_binary_adds(dev):
     """jpb_sum_n (the residual chain of a CRP block, layers.py:186-199) is bit-identical to x + t1 + t2 + t3 + t4 evaluated left
     to right, and passes the upstream gradient to every term."""
