@@ -216,6 +216,9 @@ def lib():
         v = os.environ.get("JPB_PHOTO_FWD")      # opt-in forward schedule of the photometric kernel (2 default, 3 packed)
         if v:
             check(_handle.jpb_photometric_set_variant(int(v)), "jpb_photometric_set_variant(JPB_PHOTO_FWD=%s)" % v)
+        v = os.environ.get("JPB_POOL_BWD")       # backward schedule of the max-pools (measurements): 0 default, 1 scatter, 2 5x5 gather
+        if v:
+            check(_handle.jpb_maxpool_set_bwd_variant(int(v)), "jpb_maxpool_set_bwd_variant(JPB_POOL_BWD=%s)" % v)
     return _handle
 
 

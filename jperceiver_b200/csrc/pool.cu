@@ -187,19 +187,29 @@ __global__ void __launch_bounds__(256) maxpool5_bwd_kernel(const float* gy, cons
     const int iy = (int)(r % g.H);
     const int b = (int)(r / g.H);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // all 25 arg-max words first (independent loads, out-of-range windows read as "no match"), then the few matching gradients
+    unsigned eqs[25];
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
       const int oy = iy + 2 - ky;            // the output row whose window row ky is iy
-      if (oy < 0 || oy >= g.Ho) continue;
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         const int ox = ix + 2 - kx;
-        if (ox < 0 || ox >= g.Wo) continue;
-        const size_t o = ((size_t)(b * g.Ho + oy) * g.Wo + ox) * g.C + c4 * 4;
+        const bool ok = oy >= 0 && oy < g.Ho && ox >= 0 && ox < g.Wo;
+        const size_t o = ((size_t)(b * g.Ho + (ok ? oy : 0)) * g.Wo + (ok ? ox : 0)) * g.C + c4 * 4;
         const unsigned codes = __ldg(reinterpret_cast<const unsigned*>(idx + o));
-        const unsigned want = (unsigned)(ky * 5 + kx);
-        const unsigned eq = codes ^ (want * 0x01010101u);              // a zero byte = this channel's arg-max is (ky, kx)
+        eqs[ky * 5 + kx] = ok ? codes ^ ((unsigned)(ky * 5 + kx) * 0x01010101u) : 0xffffffffu;   // a zero byte = this channel's arg-max is (ky, kx)
+      }
+    }
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const int oy = iy + 2 - ky;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const unsigned eq = eqs[ky * 5 + kx];
         if (((eq - 0x01010101u) & ~eq & 0x80808080u) == 0u) continue;  // no zero byte: nothing to add (the common case)
+        const int ox = ix + 2 - kx;
+        const size_t o = ((size_t)(b * g.Ho + oy) * g.Wo + ox) * g.C + c4 * 4;
         const float4 v = __ldg(reinterpret_cast<const float4*>(gy + o));
         if (!(eq & 0x000000ffu)) a0 += v.x;
         if (!(eq & 0x0000ff00u)) a1 += v.y;
