@@ -365,11 +365,26 @@ class TrainEngine:
         from .. import functional as JF, conv as JC
         self.flat.zero_grad()
         JC.WT.enabled = True
-        JC.WT.refresh()            # one launch: flipped/transposed weights of every convolution for this step's data gradients
+        # one launch: flipped/transposed weights of every convolution for this step's data gradients.  Only the backward reads
+        # them, so on the GPU the launch runs on a side stream beside the forward (it used to sit alone in front of the step)
+        wt_event = None
+        if self.flat.grad.is_cuda:
+            cur = torch.cuda.current_stream(self.flat.grad.device)
+            if getattr(self, "_wt_stream", None) is None:
+                self._wt_stream = torch.cuda.Stream(self.flat.grad.device)
+            self._wt_stream.wait_stream(cur)       # the weights are final: the previous optimizer step is ordered before this point
+            with torch.cuda.stream(self._wt_stream):
+                JC.WT.refresh()
+                wt_event = torch.cuda.Event()
+                wt_event.record(self._wt_stream)
+        else:
+            JC.WT.refresh()
         try:
             _, losses = self.model(data)
             names, vals, total = loss_scalars(losses)
             JF.DIRECT_GRAD = True  # backward kernels add parameter gradients straight into the flat gradient buffer
+            if wt_event is not None:
+                torch.cuda.current_stream(self.flat.grad.device).wait_event(wt_event)   # every backward node is ordered after this
             total.backward()
             # branch-concurrent model: its side streams ran backward nodes that wrote parameter gradients straight into the flat
             # buffer (no AccumulateGrad node, so autograd's end-of-backward stream sync does not cover them)
