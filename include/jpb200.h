@@ -256,6 +256,11 @@ typedef struct JpbConvWgradArgs {
                                 -1 for padding rows (the table order is then free)                                              */
 } JpbConvWgradArgs;
 int jpb_conv2d_wgrad(const JpbConvWgradArgs* args, void* stream);
+/* Schedule of the 256-wide forward / data-gradient tiles with more than 148 tiles: 0 = one tile per CTA (default); 1 = CTA pairs
+ * (tcgen05 cta_group::2, two pairs per TPC, each CTA streams half of the weight tile); 2 = one pair per TPC, four stages.  Same
+ * results; measured slower on B200 (profiles/r2_conv_pair_ab.txt), kept as a tested schedule.  Process-wide (JPB_CONV_PAIR sets the
+ * initial value).                                                                                                                 */
+int jpb_conv_set_pair(int mode);
 
 /* ---- 3x3 stride-1 pad-1 convolutions with 1..2 output channels on the CUDA cores (disparity heads
  * depth_decoder.py:35-38, BEV topview heads layout_model.py:158), as nine 1x1 projections + a shift-and-add gather.

@@ -124,7 +124,7 @@ class AdamArgs(C.Structure):
                 ("grad_scale", C.c_float), ("max_norm", C.c_float), ("normsq", C.c_void_p), ("step", C.c_void_p)]
 
 
-EMU_MISSING = ("jpb_conv2d_fwd", "jpb_conv2d_wgrad")   # tcgen05/TMA entry points do not exist in the host-emulation build
+EMU_MISSING = ("jpb_conv2d_fwd", "jpb_conv2d_wgrad", "jpb_conv_set_pair")   # tcgen05/TMA entry points do not exist in the host-emulation build
 
 
 def _declare(h):
@@ -177,6 +177,7 @@ class _Signatures:
     jpb_sumsq = [P, C.c_longlong, P, V]
     jpb_conv2d_fwd = [C.POINTER(ConvArgs), V]
     jpb_conv2d_wgrad = [C.POINTER(ConvWgradArgs), V]
+    jpb_conv_set_pair = [I]
     jpb_act_bwd = [P, P, P, C.c_longlong, I, I, P, V]
     jpb_bias_act = [P, P, P, C.c_longlong, I, I, V]
     jpb_tf32_split = [P, P, C.c_longlong, I, V]

@@ -1748,10 +1748,10 @@ int launch_fwd_pair(const JpbConvArgs* a, const CUtensorMap& half_map, cudaStrea
 // layers (the same conclusion as removing the weight TMA altogether, profiles/README.md), and the full multi-stream step did not
 // finish with it (bench.py ran into its time limit) — kept as a tested schedule for single-stream use and as the starting point of
 // a persistent 2-CTA kernel.
+int g_conv_pair = -1;
 int conv_pair() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("JPB_CONV_PAIR"); v = e ? atoi(e) : 0; }
-  return v;
+  if (g_conv_pair < 0) { const char* e = getenv("JPB_CONV_PAIR"); g_conv_pair = e ? atoi(e) : 0; }
+  return g_conv_pair;
 }
 
 template <int NT, int TR, int PSTAGES, int BSTAGES>
@@ -2011,6 +2011,12 @@ int wgrad_row_maps(const JpbConvWgradArgs* a, EncodeTiledFn enc, WgradRowMaps* o
   return JPB_OK;
 }
 }  // namespace
+
+extern "C" int jpb_conv_set_pair(int mode) {
+  if (mode < 0 || mode > 2) return JPB_ERR_ARG;
+  g_conv_pair = mode;
+  return JPB_OK;
+}
 
 extern "C" int jpb_conv2d_wgrad(const JpbConvWgradArgs* a, void* stream) {
   if (!a || !a->dy || !a->dw || !a->table || a->nsrc < 1 || a->nsrc > JPB_CONV_MAX_SRC || a->nchunks < 1 || a->splits < 1) return JPB_ERR_ARG;

@@ -44,11 +44,10 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_forward_many_tiles_per_cta(case):
     name, B, srcs, cout, k, stride, pad, reflect, act, has_bias = case
-    if name.startswith("CTA pairs") and os.environ.get("JPB_CONV_PAIR", "0") in ("", "0"):
-        # the opt-in cta_group::2 schedule (csrc/conv_tc.cu: conv_pair): run with JPB_CONV_PAIR=1; without it the same cases
-        # exercise the default wide-tile kernel at these extents
-        pass
     _lib._handle, _lib._emulated = None, False
+    pair = name.startswith("CTA pairs")
+    if pair:      # the opt-in cta_group::2 schedule (csrc/conv_tc.cu: conv_pair), switched on for these cases only
+        _lib.check(_lib.lib().jpb_conv_set_pair(1), "jpb_conv_set_pair")
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(len(name))
     xs = [tf32(torch.randn(B, c, h, w, generator=g)).to(dev).contiguous(memory_format=CL) for c, h, w, up in srcs]
@@ -66,10 +65,14 @@ def test_conv_forward_many_tiles_per_cta(case):
         ref = torch_conv(xs, ups, weight, bias, stride, pad, reflect, act, None)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    for rep in range(2):                      # twice: the second launch meets warm caches and a different block schedule
-        with JC.trunc_comp(1.0):      # TF32-representable operands: nothing is truncated
-            got = JC.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, None)
-        torch.cuda.synchronize()
-        err = (got - ref).abs().max().item()
-        scale = max(ref0.abs().max().item(), 1e-6)
-        assert err <= 5e-5 * scale, (name, rep, err, scale)
+    try:
+        for rep in range(2):                      # twice: the second launch meets warm caches and a different block schedule
+            with JC.trunc_comp(1.0):      # TF32-representable operands: nothing is truncated
+                got = JC.conv2d_tc(xs, ups, weight, bias, stride, pad, reflect, act, None)
+            torch.cuda.synchronize()
+            err = (got - ref).abs().max().item()
+            scale = max(ref0.abs().max().item(), 1e-6)
+            assert err <= 5e-5 * scale, (name, rep, err, scale)
+    finally:
+        if pair:
+            _lib.check(_lib.lib().jpb_conv_set_pair(0), "jpb_conv_set_pair")
