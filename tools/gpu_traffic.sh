@@ -3,7 +3,7 @@
 # command: after 3 warm-up steps, inside the 3-step profiling pass).  Parsed by tools/ncu_traffic.py.
 mkdir -p gpurun_out
 PER=$(python - <<'PY'
-print(474 + 8)
+print(487 + 8)   # conv_tc launches (176 forward + 164 data gradient + 147 weight gradient) + 8 photometric launches per step
 PY
 )
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_tc|photometric" \
